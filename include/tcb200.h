@@ -1,0 +1,199 @@
+/*
+ * tcb200.h -- C ABI of the B200-native statevector engine behind TensorCircuit's
+ * circuit-evaluation hot path.
+ *
+ * The reference (tencent-quantum-lab/tensorcircuit) has no FFI of its own: the path is pure
+ * Python that hands a tensor-network node graph to a contractor
+ * (tensorcircuit/cons.py:523-631) which executes numpy/jax tensordot calls.  Each entry point
+ * below names the reference interface whose O(2^n) work it replaces; INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, ints.  No torch / C++ types cross this boundary.
+ *   - every function returns 0 on success, a negative code on failure; the message is
+ *     retrievable (thread-local) through tcb200_last_error().  Nothing throws.
+ *   - `state` is a DEVICE pointer to `batch` contiguous vectors of 2^nbits amplitudes,
+ *     interleaved (re, im); dtype TCB200_C64 = float2, TCB200_C128 = double2.  Caller-owned,
+ *     never freed or reallocated by the library; kernels update it in place.
+ *   - amplitude index bit b of a vector <-> TensorCircuit qubit (nbits-1-b): qubit 0 is the
+ *     most significant bit (tensorcircuit/quantum.py:1439, quantum.py:2104-2119).
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and the calls
+ *     are asynchronous unless stated otherwise.  Re-entrant; no hidden global state besides a
+ *     per-process cache of device attributes.
+ *   - there is no CPU fallback: every call fails with TCB200_ERR_CUDA when no device/context
+ *     is usable.
+ */
+#ifndef TCB200_H
+#define TCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCB200_C64 0
+#define TCB200_C128 1
+
+#define TCB200_OK 0
+#define TCB200_ERR_ARG (-1)         /* bad argument (null pointer, bit out of range, duplicate bit ...) */
+#define TCB200_ERR_UNSUPPORTED (-2) /* e.g. k > TCB200_MAX_K */
+#define TCB200_ERR_WORKSPACE (-3)   /* workspace too small */
+#define TCB200_ERR_CUDA (-1000)     /* -(1000 + cudaError_t) */
+
+#define TCB200_MAX_K 5          /* widest dense fused block (2^5 x 2^5) */
+#define TCB200_MAX_DIAG_K 12    /* widest diagonal fused block (2^12 entries) */
+#define TCB200_MAX_PASS_OPS 16  /* fused blocks executed by one staged pass */
+#define TCB200_MAX_PASS_K 4     /* widest block inside a staged multi-block pass */
+#define TCB200_MAX_TERMS 8      /* Pauli strings per expectation launch */
+
+/* Library / build identification: "tcb200 <version> sm_100a". */
+const char* tcb200_version(void);
+
+/* Message of the last failing call made by this thread ("" if none). */
+const char* tcb200_last_error(void);
+
+/*
+ * |0...0> for every batch element.
+ * Replaces BaseCircuit.all_zero_nodes (tensorcircuit/basecircuit.py:46-60) + the contraction
+ * that materialises it.
+ */
+int tcb200_init_zero(void* state, int nbits, int dtype, int64_t batch, void* stream);
+
+/*
+ * Cast/copy an initial state into the engine buffer (device -> device, complex128 source):
+ * Circuit(n, inputs=...) (tensorcircuit/circuit.py:86-96).  `src_c128` holds 2^nbits double2.
+ */
+int tcb200_load_c128(void* state, int nbits, int dtype, const void* src_c128, void* stream);
+
+/*
+ * In-place application of one fused dense block  psi <- U psi  on k <= TCB200_MAX_K bits.
+ *
+ *   bits[k]   HOST array, strictly ascending amplitude-index bit positions.
+ *   mat       HOST array of 2^k x 2^k complex128 (re, im interleaved), row-major U[out][in];
+ *             bit j of the row/column index is the value of amplitude bit bits[j].
+ *             It is cast to the state's dtype and travels in the kernel-parameter constant
+ *             bank.  U need not be unitary (gates.py:225-232 allows complex parameters).
+ *
+ * One HBM read + one HBM write of the state.  Replaces the per-path-step
+ * tn.contract_between -> backend.tensordot of tensorcircuit/cons.py:605-623 and the final
+ * reorder_edges transpose (cons.py:629-630) for the gates merged into U.
+ */
+int tcb200_apply_dense(void* state, int nbits, int dtype, int k, const int* bits,
+                       const double* mat, int64_t batch, void* stream);
+
+/*
+ * Batched variant for backend.vmap (tensorcircuit/backends/jax_backend.py:718-730): batch
+ * element b is multiplied by its own matrix.
+ *   mats_dev  DEVICE array [batch][2^k][2^k] in the state's dtype.
+ */
+int tcb200_apply_dense_batched(void* state, int nbits, int dtype, int k, const int* bits,
+                               const void* mats_dev, int64_t batch, void* stream);
+
+/*
+ * In-place multiplication by a diagonal fused block on k <= TCB200_MAX_DIAG_K bits
+ * (rz / phase / rzz / cz / cphase runs): psi_r <- d[idx(r)] psi_r with idx bit j = bit bits[j]
+ * of r.  `diag` is a HOST array of 2^k complex128.  `diag_dev` (optional, may be NULL) is the
+ * batched form, DEVICE [batch][2^k] in the state's dtype; when given, `diag` is ignored.
+ */
+int tcb200_apply_diag(void* state, int nbits, int dtype, int k, const int* bits,
+                      const double* diag, const void* diag_dev, int64_t batch, void* stream);
+
+/*
+ * Staged multi-block pass: the tile {low bits} U {tile_hi bits} is brought into shared memory
+ * once, `nops` dense blocks whose bits all lie inside the tile are applied back to back, and
+ * the tile is written back -- one HBM read + write for the whole run of blocks.
+ *
+ *   ops_k[nops]         HOST, k of each block (<= TCB200_MAX_PASS_K)
+ *   ops_bits[sum k]     HOST, concatenated ascending bit lists
+ *   ops_mats_dev        DEVICE, concatenated matrices in the state's dtype, block i holding
+ *                       [batch_mats][2^k_i][2^k_i]; batch_mats is 1 (shared) or `batch`
+ *   tile_hi[n_hi]       HOST, ascending bit positions >= the contiguous low part that the
+ *                       tile gathers (every block bit must be < nbits_low or in tile_hi)
+ */
+int tcb200_apply_pass(void* state, int nbits, int dtype, int nops, const int* ops_k,
+                      const int* ops_bits, const void* ops_mats_dev, int64_t batch_mats,
+                      int n_hi, const int* tile_hi, int64_t batch, void* stream);
+
+/* Geometry the pass planner needs: log2 of the tile size (amplitudes) used by
+ * tcb200_apply_pass for `dtype`. */
+int tcb200_pass_tile_bits(int dtype);
+
+/*
+ * sum_r |psi_r|^2 per batch element -> out_dev[batch] (DEVICE, double).  Deterministic
+ * (fixed reduction order).  workspace: tcb200_reduce_workspace_bytes(nbits, batch).
+ */
+int tcb200_norm2(const void* state, int nbits, int dtype, int64_t batch, double* out_dev,
+                 void* workspace, size_t ws_bytes, void* stream);
+size_t tcb200_reduce_workspace_bytes(int nbits, int64_t batch);
+
+/*
+ * p_r = |psi_r|^2 into a real DEVICE array of the matching real dtype (float / double):
+ * BaseCircuit.probability (tensorcircuit/basecircuit.py:510-523).
+ */
+int tcb200_probability(const void* state, int nbits, int dtype, void* prob_dev, int64_t batch,
+                       void* stream);
+
+/*
+ * Pauli-string expectations  <psi| P_t |psi>, t < nterms <= TCB200_MAX_TERMS, for every
+ * batch element, in one read of the state:
+ *     sum_r conj(psi_r) (-1)^{popc(r & sign[t])} (-i)^{ny[t]} psi_{r ^ flip[t]}
+ * (closed form of tensorcircuit/quantum.py:1461-1482; replaces expectation_before +
+ * contractor, tensorcircuit/basecircuit.py:267-319, circuit.py:914-990, once per term).
+ *
+ *   flip/sign/ny   HOST arrays (amplitude-index bit masks; ny = number of Y factors)
+ *   tile_hi[n_hi]  HOST ascending bit positions gathered into the tile; every bit of every
+ *                  flip mask must be below the contiguous low part or in tile_hi
+ *   out_dev        DEVICE double [batch][nterms][2] (re, im); not normalised
+ *   workspace      tcb200_expect_workspace_bytes(nbits, batch)
+ * Accumulation is float64 for both dtypes, reduction order fixed (run-to-run deterministic).
+ */
+int tcb200_expect_pauli(const void* state, int nbits, int dtype, int nterms,
+                        const uint64_t* flip, const uint64_t* sign, const int* ny, int n_hi,
+                        const int* tile_hi, double* out_dev, int64_t batch, void* workspace,
+                        size_t ws_bytes, void* stream);
+size_t tcb200_expect_workspace_bytes(int nbits, int64_t batch);
+/* log2 tile size (amplitudes) used by tcb200_expect_pauli for `dtype`. */
+int tcb200_expect_tile_bits(int dtype);
+
+/*
+ * CDF sampler driven by caller-supplied uniforms, the rule of
+ * ExtendedBackend.probability_sample (tensorcircuit/backends/abstract_backend.py:1145-1157):
+ *     r = total * (1 - u);  index = first i with CDF[i] >= r   (searchsorted side="left")
+ * evaluated with a two-level float64 CDF (block sums + in-block scan); the 2^n-entry p / CDF
+ * arrays of the reference are never materialised.
+ *
+ *   uniforms_dev  DEVICE double[shots], values in [0, 1)
+ *   out_idx_dev   DEVICE int64[shots]
+ *   total_dev     DEVICE double[1] (optional, may be NULL): receives sum |psi|^2
+ *   workspace     tcb200_sample_workspace_bytes(nbits)
+ * The state must be a single vector (batch 1).  `cdf_offset`/`cdf_total` support a state
+ * sharded over ranks: pass this shard's exclusive prefix of the per-shard masses and the
+ * global mass (or 0 and a negative total for "single shard"); shots whose r falls outside
+ * this shard's interval get index -1.
+ */
+int tcb200_sample(const void* state, int nbits, int dtype, const double* uniforms_dev,
+                  int64_t shots, int64_t* out_idx_dev, double* total_dev, double cdf_offset,
+                  double cdf_total, void* workspace, size_t ws_bytes, void* stream);
+size_t tcb200_sample_workspace_bytes(int nbits);
+
+/*
+ * Host-buffer convenience entry point (what a reference-side binding would call for the whole
+ * path): uploads nothing but the small per-block matrices, runs `npasses` dense blocks on the
+ * device-resident state, then -- if shots > 0 -- draws samples for HOST uniforms into a HOST
+ * index buffer.  Blocking (synchronises `stream` before returning).
+ *   pass_k[npasses], pass_bits[sum k], pass_mats[sum 4^k complex128] : HOST
+ */
+int tcb200_run_circuit_host(void* state, int nbits, int dtype, int init_zero, int npasses,
+                            const int* pass_k, const int* pass_bits, const double* pass_mats,
+                            int64_t shots, const double* uniforms_host, int64_t* out_idx_host,
+                            void* workspace, size_t ws_bytes, void* stream);
+
+/* Number of kernel launches issued by this process through the library so far. */
+int64_t tcb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCB200_H */

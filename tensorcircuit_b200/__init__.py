@@ -1,0 +1,45 @@
+"""tensorcircuit_b200 -- a B200-native statevector engine behind TensorCircuit's circuit API.
+
+``import tensorcircuit_b200 as tc`` gives the hot-path surface of the reference
+(tensorcircuit/__init__.py:1-72): ``tc.Circuit``, ``tc.gates``, ``tc.backend``,
+``tc.set_backend / set_dtype / set_contractor``, ``tc.quantum``, ``tc.templates``.
+Everything O(2^n) runs in hand-written sm_100a CUDA kernels behind the C ABI of
+``include/tcb200.h``; there is no CPU, jax, tensorflow or torch-op execution path."""
+
+__version__ = "0.1.0"
+__author__ = "tensorcircuit_b200"
+
+from . import _lib  # noqa: F401  (fails loudly when the CUDA library is missing)
+from .cons import (  # noqa: F401
+    contractor,
+    dtypestr,
+    npdtype,
+    rdtypestr,
+    runtime_backend,
+    runtime_contractor,
+    runtime_dtype,
+    set_backend,
+    set_contractor,
+    set_dtype,
+    set_function_backend,
+    set_function_contractor,
+    set_function_dtype,
+)
+from . import b200_backend as _backend_module  # noqa: F401  binds cons.backend
+from . import gates  # noqa: F401
+from .gates import Gate, array_to_tensor, num_to_tensor  # noqa: F401
+from . import quantum  # noqa: F401
+from .circuit import Circuit, DeviceArray, expectation  # noqa: F401
+from . import templates  # noqa: F401
+from . import engine  # noqa: F401
+from . import parallel  # noqa: F401
+
+backend = _backend_module.get_backend()
+
+
+def __getattr__(name):  # live view of the mutable globals (set_dtype rebinds them in cons)
+    from . import cons as _cons
+
+    if name in ("dtypestr", "rdtypestr", "npdtype"):
+        return getattr(_cons, name)
+    raise AttributeError(name)

@@ -1,0 +1,318 @@
+// Shared declarations for the tcb200 engine (sm_100a).
+//
+// Everything that computes an address or an index is __host__ __device__ so that
+// tests/emu/ can execute the exact kernel bodies thread by thread on the CPU (the build
+// container has no GPU); the product never runs those host instantiations.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tcb200.h"
+
+#define TCB_HD __host__ __device__ __forceinline__
+
+namespace tcb {
+
+// ---- error plumbing (abi.cu) ---------------------------------------------------------------
+int fail(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define TCB_CUDA(x)                                          \
+    do {                                                     \
+        cudaError_t _e = (x);                                \
+        if (_e != cudaSuccess) return cuda_fail(_e, #x);     \
+    } while (0)
+
+#define TCB_LAUNCH_CHECK(name)                               \
+    do {                                                     \
+        cudaError_t _e = cudaGetLastError();                 \
+        if (_e != cudaSuccess) return cuda_fail(_e, name);   \
+        count_launch();                                      \
+    } while (0)
+
+// ---- complex types -------------------------------------------------------------------------
+template <typename Real>
+struct CT;
+template <>
+struct CT<float> {
+    using type = float2;
+    static constexpr int APU = 2;  // amplitudes per 16-byte unit
+};
+template <>
+struct CT<double> {
+    using type = double2;
+    static constexpr int APU = 1;
+};
+
+template <typename C, typename R>
+TCB_HD C mk(R x, R y) {
+    C c;
+    c.x = x;
+    c.y = y;
+    return c;
+}
+
+// acc += m * v  (4 FMA)
+template <typename C>
+TCB_HD void cfma(C& acc, const C m, const C v) {
+    acc.x = fma(m.x, v.x, acc.x);
+    acc.x = fma(-m.y, v.y, acc.x);
+    acc.y = fma(m.x, v.y, acc.y);
+    acc.y = fma(m.y, v.x, acc.y);
+}
+
+template <typename C>
+TCB_HD C cmul(const C a, const C b) {
+    C r;
+    r.x = a.x * b.x - a.y * b.y;
+    r.y = a.x * b.y + a.y * b.x;
+    return r;
+}
+
+// ---- shared-memory swizzle -----------------------------------------------------------------
+// Tiles live in shared memory as 16-byte units.  Unit u is stored at slot
+//   swz(u) = u ^ ((u>>3)&7) ^ ((u>>6)&7)
+// i.e. the 3 slot bits that select the 16-byte bank group are XORed with the next two 3-bit
+// fields.  The map is GF(2)-linear and only touches the low 3 bits, so
+//   swz(a ^ b) == swz(a) ^ swz(b)   and   it permutes every aligned run of 8 units.
+// Consequences: (i) staging a tile with consecutive lanes -> consecutive units is
+// conflict-free; (ii) a gate group can be addressed as swz(base) ^ swz(target offset), both
+// precomputed; (iii) the host can order the lane bits of the group index so that the lanes of
+// a quarter/half warp always hit distinct banks, whatever the target bits are.
+TCB_HD uint32_t swz_unit(uint32_t u) { return u ^ ((u >> 3) & 7u) ^ ((u >> 6) & 7u); }
+
+template <int APU>
+TCB_HD uint32_t swz_amp(uint32_t e) {
+    if (APU == 2) return (swz_unit(e >> 1) << 1) | (e & 1u);
+    return swz_unit(e);
+}
+
+// ---- tile geometry -------------------------------------------------------------------------
+// A tile is the set of 2^T amplitudes whose index agrees outside the bit set
+//   S = [0, lrow)  U  { hb[0] < hb[1] < ... < hb[h-1] },  hb[j] >= lrow,  T = lrow + h.
+// Local index e (T bits): low lrow bits = position inside a contiguous row, bit lrow+j = hb[j].
+struct TileGeom {
+    int n;      // bits of one state vector
+    int T;      // log2(tile amplitudes)
+    int h;      // gathered high bits
+    int lrow;   // T - h: log2(row length)
+    int hb[8];  // ascending
+};
+
+TCB_HD uint64_t tile_base(const TileGeom& g, uint64_t t) {
+    uint64_t x = t << g.lrow;
+    for (int j = 0; j < g.h; ++j) {
+        const int pos = g.hb[j];
+        const uint64_t lo = x & ((1ull << pos) - 1ull);
+        x = ((x >> pos) << (pos + 1)) | lo;
+    }
+    return x;
+}
+
+TCB_HD uint64_t row_offset(const TileGeom& g, uint32_t row) {
+    uint64_t o = 0;
+    for (int j = 0; j < g.h; ++j)
+        if ((row >> j) & 1u) o |= 1ull << g.hb[j];
+    return o;
+}
+
+// global bit position -> local tile bit (or -1)
+inline int local_bit(const TileGeom& g, int b) {
+    if (b < g.lrow) return b;
+    for (int j = 0; j < g.h; ++j)
+        if (g.hb[j] == b) return g.lrow + j;
+    return -1;
+}
+
+// deposit the low bits of j into the positions pos[0..k)
+TCB_HD uint32_t deposit(uint32_t j, const int* pos, int k) {
+    uint32_t o = 0;
+    for (int i = 0; i < k; ++i)
+        if ((j >> i) & 1u) o |= 1u << pos[i];
+    return o;
+}
+
+// ---- staging (global <-> shared), 16 bytes per lane ------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#endif
+}
+
+struct alignas(16) Unit16 {
+    uint32_t w[4];
+};
+
+// Bring the tile with base amplitude index `base` into shared memory.  `rowoff` holds
+// row_offset() of the 2^h rows.  SWZ selects the swizzled layout.
+template <typename C, bool SWZ>
+TCB_HD void stage_in(const TileGeom& g, const C* vec, uint64_t base, C* tile,
+                     const uint64_t* rowoff, int tid, int nthr) {
+    constexpr int APU = 16 / (int)sizeof(C);
+    const uint32_t nunits = (1u << g.T) / APU;
+    const uint32_t rowmask = (1u << g.lrow) - 1u;
+    Unit16* t16 = reinterpret_cast<Unit16*>(tile);
+    for (uint32_t u = tid; u < nunits; u += nthr) {
+        const uint32_t e = u * APU;
+        const uint64_t gi = base + rowoff[e >> g.lrow] + (e & rowmask);
+        const uint32_t slot = SWZ ? swz_unit(u) : u;
+#if defined(__CUDA_ARCH__)
+        cp_async16(t16 + slot, vec + gi);
+#else
+        t16[slot] = *reinterpret_cast<const Unit16*>(vec + gi);
+#endif
+    }
+}
+
+template <typename C, bool SWZ>
+TCB_HD void stage_out(const TileGeom& g, C* vec, uint64_t base, const C* tile,
+                      const uint64_t* rowoff, int tid, int nthr) {
+    constexpr int APU = 16 / (int)sizeof(C);
+    const uint32_t nunits = (1u << g.T) / APU;
+    const uint32_t rowmask = (1u << g.lrow) - 1u;
+    const Unit16* t16 = reinterpret_cast<const Unit16*>(tile);
+    for (uint32_t u = tid; u < nunits; u += nthr) {
+        const uint32_t e = u * APU;
+        const uint64_t gi = base + rowoff[e >> g.lrow] + (e & rowmask);
+        const uint32_t slot = SWZ ? swz_unit(u) : u;
+        *reinterpret_cast<Unit16*>(vec + gi) = t16[slot];
+    }
+}
+
+// ---- dense block on a staged tile ----------------------------------------------------------
+// Group index gidx (T-K bits) -> swizzled local amplitude index of the group's element 0:
+// XOR of ntval[i] over the set bits i of gidx.  The element with target combination j is at
+// (that) ^ tval[j].
+struct GroupMap {
+    int ngb;              // T - K
+    uint32_t ntval[16];   // swz_amp(1 << (local non-target bit i)), in host-chosen lane order
+    uint32_t tval[32];    // swz_amp(deposit(j, local target bits))
+    int vec0;             // 1: local bit 0 is target bit 0 and sizeof(C)==8 -> pairs are one 16B unit
+};
+
+TCB_HD uint32_t group_base(const GroupMap& m, uint32_t gidx) {
+    uint32_t b = 0;
+    for (int i = 0; i < m.ngb; ++i) b ^= (0u - ((gidx >> i) & 1u)) & m.ntval[i];
+    return b;
+}
+
+// One group: v <- M v with M(i, j) supplied by `mat` (any callable returning C).
+template <typename C, int K, typename Mat>
+TCB_HD void apply_group(C* tile, const uint32_t base, const uint32_t* tval, const bool vec0,
+                        const Mat& mat) {
+    constexpr int D = 1 << K;
+    C v[D];
+    if (sizeof(C) == 8 && vec0) {
+        // bit 0 of the local index is target bit 0: (j, j|1) share one aligned 16-byte unit
+#pragma unroll
+        for (int j = 0; j < D; j += 2) {
+            const Unit16 q = *reinterpret_cast<const Unit16*>(tile + (base ^ tval[j]));
+            const C* qc = reinterpret_cast<const C*>(&q);
+            v[j] = qc[0];
+            v[j + 1] = qc[1];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < D; ++j) v[j] = tile[base ^ tval[j]];
+    }
+    if (sizeof(C) == 8 && vec0) {
+#pragma unroll
+        for (int i = 0; i < D; i += 2) {
+            Unit16 q;
+            C* qc = reinterpret_cast<C*>(&q);
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii) {
+                C acc = cmul(mat(i + ii, 0), v[0]);
+#pragma unroll
+                for (int j = 1; j < D; ++j) cfma(acc, mat(i + ii, j), v[j]);
+                qc[ii] = acc;
+            }
+            *reinterpret_cast<Unit16*>(tile + (base ^ tval[i])) = q;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            C acc = cmul(mat(i, 0), v[0]);
+#pragma unroll
+            for (int j = 1; j < D; ++j) cfma(acc, mat(i, j), v[j]);
+            tile[base ^ tval[i]] = acc;
+        }
+    }
+}
+
+// All groups of a tile owned by thread `tid` of `nthr` (power of two, tb = log2(nthr)).
+template <typename C, int K, typename Mat>
+TCB_HD void apply_block_on_tile(C* tile, const GroupMap& gm, int tid, int nthr, int tb,
+                                const Mat& mat) {
+    const uint32_t ngroups = 1u << gm.ngb;
+    if ((uint32_t)tid >= ngroups) return;
+    // bits of the group index that come from tid are fixed for this thread
+    const uint32_t base_tid = group_base(gm, (uint32_t)tid);
+    const bool vec0 = gm.vec0 != 0;
+    for (uint32_t it = 0; ((it << tb) | (uint32_t)tid) < ngroups; ++it) {
+        uint32_t b = base_tid;
+        for (int i = tb; i < gm.ngb; ++i) b ^= (0u - ((it >> (i - tb)) & 1u)) & gm.ntval[i];
+        apply_group<C, K>(tile, b, gm.tval, vec0, mat);
+    }
+}
+
+// ---- host helpers (plan.cpp part of abi.cu) ------------------------------------------------
+// Choose the tile for a set of ascending target bits: gathers exactly the targets that do not
+// fall into the contiguous low part.  Returns <0 on error.
+int make_geom(int nbits, int tile_bits, int k, const int* bits, TileGeom* g);
+// Tile with explicitly requested gathered bits.
+int make_geom_hi(int nbits, int tile_bits, int n_hi, const int* tile_hi, TileGeom* g);
+// Fill the GroupMap for a block with the given ascending global bits inside geometry g.
+int make_group_map(const TileGeom& g, int apu, int k, const int* bits, GroupMap* gm);
+int pick_threads(int T, int k, int apu);   // log2(blockDim.x)
+int dense_tile_bits(int dtype, int k);     // log2(tile amplitudes) of the single-block kernel
+int pass_tile_bits(int dtype);             // ... of the multi-block pass kernel
+int expect_tile_bits(int dtype);           // ... of the expectation kernel
+
+// ---- expectation: one term on one staged tile, elements owned by thread tid ------------------
+template <typename C, typename R>
+TCB_HD void expect_tile_term(const C* tile, uint32_t tsz, uint32_t fl, uint32_t sl, int tid, int nthr,
+                             R* out_re, R* out_im) {
+    R pr = 0, pi = 0;
+    for (uint32_t e = tid; e < tsz; e += nthr) {
+        const C a = tile[e];
+        const C b = tile[e ^ fl];
+        R re = a.x * b.x + a.y * b.y;
+        R im = a.x * b.y - a.y * b.x;
+        uint32_t par = e & sl;
+        par ^= par >> 16;
+        par ^= par >> 8;
+        par ^= par >> 4;
+        par ^= par >> 2;
+        par ^= par >> 1;
+        if (par & 1u) {
+            re = -re;
+            im = -im;
+        }
+        pr += re;
+        pi += im;
+    }
+    *out_re = pr;
+    *out_im = pi;
+}
+
+TCB_HD bool parity64(uint64_t x) {
+    x ^= x >> 32;
+    x ^= x >> 16;
+    x ^= x >> 8;
+    x ^= x >> 4;
+    x ^= x >> 2;
+    x ^= x >> 1;
+    return (x & 1ull) != 0;
+}
+
+}  // namespace tcb

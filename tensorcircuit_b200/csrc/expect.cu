@@ -1,0 +1,211 @@
+// Pauli-string expectation values: up to TCB200_MAX_TERMS strings per read of the state.
+//
+// A CTA walks over tiles (same gather geometry as the apply kernels, linear layout).  For a
+// term with local flip mask f and local sign mask s the contribution of tile element e is
+//     conj(psi_e) * psi_{e^f} * (-1)^{popc(e & s)}     (quantum.py:1461-1482)
+// times a per-tile sign from the sign bits outside the tile.  Per-thread partials of one tile
+// are formed in the state's real type (16 products), then accumulated in float64 across
+// tiles; warp-shuffle + block reduce at the end; the cross-CTA sum and the (-i)^{n_y} phase
+// are applied by a second tiny kernel in a fixed order, so results are deterministic.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace tcb {
+
+struct ExpectParams {
+    const void* state;
+    double* partials;  // [batch][gridDim.x][MAXT][2]
+    TileGeom g;
+    int nterms;
+    uint32_t flip_l[TCB200_MAX_TERMS];
+    uint32_t sign_l[TCB200_MAX_TERMS];
+    uint64_t sign_hi[TCB200_MAX_TERMS];  // sign bits outside the tile (global positions)
+};
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) expect_kernel(const __grid_constant__ ExpectParams p) {
+    using C = typename CT<Real>::type;
+    constexpr int MT = TCB200_MAX_TERMS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    C* tile = reinterpret_cast<C*>(smem_raw);
+    __shared__ uint64_t rowoff[32];
+    __shared__ double red[8][MT][2];
+
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    if (tid < (1 << p.g.h)) rowoff[tid] = row_offset(p.g, tid);
+    __syncthreads();
+    const C* vec = static_cast<const C*>(p.state) + ((uint64_t)blockIdx.y << p.g.n);
+    const uint64_t ntiles = 1ull << (p.g.n - p.g.T);
+    const uint32_t tsz = 1u << p.g.T;
+
+    double acc_re[MT], acc_im[MT];
+#pragma unroll
+    for (int t = 0; t < MT; ++t) acc_re[t] = acc_im[t] = 0.0;
+
+    for (uint64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        const uint64_t base = tile_base(p.g, tl);
+        stage_in<C, false>(p.g, vec, base, tile, rowoff, tid, nthr);
+        cp_async_wait_all();
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < MT; ++t) {
+            if (t < p.nterms) {
+                Real pr, pi;
+                expect_tile_term<C, Real>(tile, tsz, p.flip_l[t], p.sign_l[t], tid, nthr, &pr, &pi);
+                const bool neg = parity64(base & p.sign_hi[t]);
+                acc_re[t] += neg ? -(double)pr : (double)pr;
+                acc_im[t] += neg ? -(double)pi : (double)pi;
+            }
+        }
+        __syncthreads();  // tile is overwritten by the next iteration
+    }
+    // CTA reduction
+    const int w = tid >> 5, l = tid & 31;
+#pragma unroll
+    for (int t = 0; t < MT; ++t) {
+        if (t < p.nterms) {
+            const double r = warp_sum_d(acc_re[t]);
+            const double i = warp_sum_d(acc_im[t]);
+            if (l == 0) {
+                red[w][t][0] = r;
+                red[w][t][1] = i;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < p.nterms * 2) {
+        const int t = tid >> 1, c = tid & 1;
+        double s = 0.0;
+        const int nw = nthr >> 5;
+        for (int ww = 0; ww < nw; ++ww) s += red[ww][t][c];
+        p.partials[(((uint64_t)blockIdx.y * gridDim.x + blockIdx.x) * MT + t) * 2 + c] = s;
+    }
+}
+
+struct ExpectFinalParams {
+    const double* partials;
+    double* out;  // [batch][nterms][2]
+    int nctas;
+    int nterms;
+    int ny[TCB200_MAX_TERMS];
+};
+
+__global__ void expect_final_kernel(const __grid_constant__ ExpectFinalParams p) {
+    constexpr int MT = TCB200_MAX_TERMS;
+    const int t = threadIdx.x;
+    if (t >= p.nterms) return;
+    const double* src = p.partials + (uint64_t)blockIdx.x * p.nctas * MT * 2;
+    double re = 0.0, im = 0.0;
+    for (int c = 0; c < p.nctas; ++c) {
+        re += src[((uint64_t)c * MT + t) * 2];
+        im += src[((uint64_t)c * MT + t) * 2 + 1];
+    }
+    // times (-i)^ny
+    double ore = re, oim = im;
+    switch (p.ny[t] & 3) {
+        case 1: ore = im; oim = -re; break;
+        case 2: ore = -re; oim = -im; break;
+        case 3: ore = -im; oim = re; break;
+        default: break;
+    }
+    double* o = p.out + ((uint64_t)blockIdx.x * p.nterms + t) * 2;
+    o[0] = ore;
+    o[1] = oim;
+}
+
+static unsigned expect_grid_x(int nbits, int dtype, int64_t batch) {
+    const int T = expect_tile_bits(dtype);
+    const uint64_t ntiles = nbits > T ? (1ull << (nbits - T)) : 1ull;
+    uint64_t cap = (148ull * 16) / (uint64_t)batch;
+    if (cap < 4) cap = 4;
+    return (unsigned)(ntiles < cap ? ntiles : cap);
+}
+
+}  // namespace tcb
+
+using namespace tcb;
+
+extern "C" {
+
+int tcb200_expect_tile_bits(int dtype) { return expect_tile_bits(dtype); }
+
+size_t tcb200_expect_workspace_bytes(int nbits, int64_t batch) {
+    // sized for either dtype
+    const unsigned g0 = expect_grid_x(nbits, TCB200_C64, batch), g1 = expect_grid_x(nbits, TCB200_C128, batch);
+    const unsigned gx = g0 > g1 ? g0 : g1;
+    return (size_t)batch * gx * TCB200_MAX_TERMS * 2 * sizeof(double) + 256;
+}
+
+int tcb200_expect_pauli(const void* state, int nbits, int dtype, int nterms,
+                        const uint64_t* flip, const uint64_t* sign, const int* ny, int n_hi,
+                        const int* tile_hi, double* out_dev, int64_t batch, void* workspace,
+                        size_t ws_bytes, void* stream) {
+    if (!state || !flip || !sign || !ny || !out_dev || !workspace) return fail(TCB200_ERR_ARG, "NULL argument");
+    if (dtype != TCB200_C64 && dtype != TCB200_C128) return fail(TCB200_ERR_ARG, "bad dtype %d", dtype);
+    if (nbits < 1 || nbits > 40) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
+    if (nterms < 1 || nterms > TCB200_MAX_TERMS) return fail(TCB200_ERR_ARG, "nterms=%d out of range", nterms);
+    if (batch < 1 || batch > 65535) return fail(TCB200_ERR_ARG, "batch=%lld out of range", (long long)batch);
+    if (ws_bytes < tcb200_expect_workspace_bytes(nbits, batch)) return fail(TCB200_ERR_WORKSPACE, "workspace too small");
+    ExpectParams p;
+    memset(&p, 0, sizeof(p));
+    const int T = expect_tile_bits(dtype);
+    int rc = make_geom_hi(nbits, T, nbits <= T ? 0 : n_hi, tile_hi, &p.g);
+    if (rc) return rc;
+    p.state = state;
+    p.partials = static_cast<double*>(workspace);
+    p.nterms = nterms;
+    const uint64_t full = nbits >= 64 ? ~0ull : ((1ull << nbits) - 1ull);
+    for (int t = 0; t < nterms; ++t) {
+        if ((flip[t] & ~full) || (sign[t] & ~full)) return fail(TCB200_ERR_ARG, "mask of term %d exceeds the state", t);
+        uint32_t fl = 0, sl = 0;
+        uint64_t shi = sign[t];
+        for (int b = 0; b < nbits; ++b) {
+            const int lb = local_bit(p.g, b);
+            if ((flip[t] >> b) & 1ull) {
+                if (lb < 0) return fail(TCB200_ERR_ARG, "flip bit %d of term %d is not inside the tile", b, t);
+                fl |= 1u << lb;
+            }
+            if (((sign[t] >> b) & 1ull) && lb >= 0) {
+                sl |= 1u << lb;
+                shi &= ~(1ull << b);
+            }
+        }
+        p.flip_l[t] = fl;
+        p.sign_l[t] = sl;
+        p.sign_hi[t] = shi;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned gx = expect_grid_x(nbits, dtype, batch);
+    const size_t esz = dtype == TCB200_C64 ? 8 : 16;
+    size_t smem = esz << p.g.T;
+    if (smem < 16) smem = 16;
+    int tb = p.g.T - (dtype == TCB200_C64 ? 1 : 0);
+    if (tb > 8) tb = 8;
+    if (tb < 5) tb = 5;
+    dim3 grid(gx, (unsigned)batch);
+    if (dtype == TCB200_C64)
+        expect_kernel<float><<<grid, 1u << tb, smem, st>>>(p);
+    else
+        expect_kernel<double><<<grid, 1u << tb, smem, st>>>(p);
+    TCB_LAUNCH_CHECK("expect_kernel");
+    ExpectFinalParams f;
+    memset(&f, 0, sizeof(f));
+    f.partials = p.partials;
+    f.out = out_dev;
+    f.nctas = (int)gx;
+    f.nterms = nterms;
+    for (int t = 0; t < nterms; ++t) f.ny[t] = ny[t];
+    expect_final_kernel<<<(unsigned)batch, 32, 0, st>>>(f);
+    TCB_LAUNCH_CHECK("expect_final_kernel");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,227 @@
+"""Device-resident state vector driven through the C ABI (include/tcb200.h).
+
+PyTorch is used for exactly three things here: owning device memory (caching allocator),
+naming the CUDA stream, and host<->device copies of small buffers.  No torch op ever touches
+O(2^n) data; every such step is a tcb200 kernel.  There is no CPU path: constructing a
+:class:`DeviceState` without a CUDA device raises."""
+
+from __future__ import annotations
+
+from ctypes import c_void_p
+from typing import Any, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+from .fusion import Block
+
+_TORCH_C = {"complex64": torch.complex64, "complex128": torch.complex128}
+_DT = {"complex64": _lib.C64, "complex128": _lib.C128}
+
+# counters the benchmark reads (bytes are algorithmic: one read + one write per pass)
+STATS = {"apply_launches": 0, "apply_bytes": 0, "expect_launches": 0, "sample_launches": 0}
+
+
+def reset_stats() -> None:
+    for k in STATS:
+        STATS[k] = 0
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise _lib.EngineError(
+            "tensorcircuit_b200 needs a CUDA device (sm_100a); there is no CPU execution path"
+        )
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: torch.Tensor) -> c_void_p:
+    return c_void_p(t.data_ptr())
+
+
+def tile_hi_fixpoint(bits: Sequence[int], tile_bits: int, nbits: int) -> List[int]:
+    """Bits of ``bits`` that do not fall into the contiguous low part [0, tile_bits - h)."""
+    if nbits <= tile_bits:
+        return []
+    h = 0
+    while True:
+        c = sum(1 for b in bits if b >= tile_bits - h)
+        if c == h:
+            break
+        h = c
+    return sorted(b for b in set(bits) if b >= tile_bits - h)
+
+
+def plan_expect_groups(flips: Sequence[int], nbits: int, tile_bits: int, max_hi: int = 5,
+                       max_terms: int = _lib.MAX_TERMS) -> List[Tuple[List[int], List[int]]]:
+    """Group Pauli terms into launches: each group holds <= max_terms terms whose flip bits fit
+    one tile geometry (<= max_hi gathered bits).  Returns [(term ids, union of flip bits)]."""
+    groups: List[Tuple[List[int], List[int]]] = []
+    for t in range(len(flips)):
+        fb = [b for b in range(nbits) if (int(flips[t]) >> b) & 1]
+        if len(tile_hi_fixpoint(fb, tile_bits, nbits)) > max_hi:
+            raise _lib.EngineError("Pauli string flips more than %d bits above the tile" % max_hi)
+        placed = False
+        for ids, union in groups:
+            if len(ids) >= max_terms:
+                continue
+            u = sorted(set(union) | set(fb))
+            if len(tile_hi_fixpoint(u, tile_bits, nbits)) <= max_hi:
+                ids.append(t)
+                union[:] = u
+                placed = True
+                break
+        if not placed:
+            groups.append(([t], sorted(fb)))
+    return groups
+
+
+class DeviceState:
+    def __init__(self, nbits: int, dtype: str = "complex64", batch: int = 1, device: Any = None,
+                 buffer: Optional[torch.Tensor] = None):
+        require_cuda()
+        if dtype not in _DT:
+            raise ValueError(f"Unsupported data type: {dtype}")
+        self.nbits = int(nbits)
+        self.dtype = dtype
+        self.dt = _DT[dtype]
+        self.batch = int(batch)
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        if buffer is not None:
+            assert buffer.is_cuda and buffer.dtype == _TORCH_C[dtype] and buffer.numel() == self.batch << self.nbits
+            self.buf = buffer.view(self.batch, -1)
+        else:
+            self.buf = torch.empty((self.batch, 1 << self.nbits), dtype=_TORCH_C[dtype], device=self.device)
+        self._ws: Optional[torch.Tensor] = None
+
+    # -- helpers ----------------------------------------------------------------------------
+    @property
+    def amp_bytes(self) -> int:
+        return 8 if self.dtype == "complex64" else 16
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _dev_matrix(self, m: np.ndarray) -> torch.Tensor:
+        h = np.ascontiguousarray(m.astype(np.complex64 if self.dtype == "complex64" else np.complex128))
+        return torch.from_numpy(h).to(self.device, non_blocking=False)
+
+    # -- initial state ------------------------------------------------------------------------
+    def init_zero(self) -> None:
+        check(lib.tcb200_init_zero(_ptr(self.buf), self.nbits, self.dt, self.batch, _stream()))
+
+    def load(self, src: Any) -> None:
+        """Copy an initial state (host array / torch tensor of 2^nbits entries) into every batch row."""
+        if isinstance(src, torch.Tensor):
+            s = src.reshape(-1).to(self.device, dtype=torch.complex128)
+        else:
+            s = torch.from_numpy(np.ascontiguousarray(np.asarray(src).reshape(-1).astype(np.complex128))).to(self.device)
+        if s.numel() != 1 << self.nbits:
+            raise ValueError("initial state has %d entries, expected %d" % (s.numel(), 1 << self.nbits))
+        for b in range(self.batch):
+            check(lib.tcb200_load_c128(_ptr(self.buf[b]), self.nbits, self.dt, _ptr(s), _stream()))
+        torch.cuda.current_stream().synchronize()  # `s` may be freed by the allocator afterwards
+
+    # -- gates ------------------------------------------------------------------------------
+    def apply_block(self, blk: Block) -> None:
+        k = len(blk.bits)
+        bits = np.asarray(blk.bits, dtype=np.int32)
+        if blk.batched:
+            if blk.matrix.shape[0] != self.batch:
+                raise ValueError("batched block of size %d on a state of batch %d" % (blk.matrix.shape[0], self.batch))
+            md = self._dev_matrix(blk.matrix)
+            check(lib.tcb200_apply_dense_batched(_ptr(self.buf), self.nbits, self.dt, k, _lib.iptr(bits), _ptr(md), self.batch, _stream()))
+        else:
+            m = np.ascontiguousarray(blk.matrix, dtype=np.complex128)
+            check(lib.tcb200_apply_dense(_ptr(self.buf), self.nbits, self.dt, k, _lib.iptr(bits), _lib.dptr(m.view(np.float64)), self.batch, _stream()))
+        STATS["apply_launches"] += 1
+        STATS["apply_bytes"] += 2 * self.amp_bytes * (self.batch << self.nbits)
+
+    def apply_blocks(self, blocks: Sequence[Block]) -> None:
+        for b in blocks:
+            self.apply_block(b)
+
+    def apply_pass(self, blocks: Sequence[Block], tile_hi: Sequence[int]) -> None:
+        """Several blocks inside one staged tile pass (one HBM read + write)."""
+        ks = np.asarray([len(b.bits) for b in blocks], dtype=np.int32)
+        bits = np.asarray([x for b in blocks for x in b.bits], dtype=np.int32)
+        batched = any(b.batched for b in blocks)
+        mats = []
+        for b in blocks:
+            m = b.matrix
+            if batched and m.ndim == 2:
+                m = np.broadcast_to(m, (self.batch,) + m.shape)
+            mats.append(np.ascontiguousarray(m).reshape(-1))
+        md = self._dev_matrix(np.concatenate(mats))
+        hi = np.asarray(list(tile_hi) if len(tile_hi) else [0], dtype=np.int32)
+        check(lib.tcb200_apply_pass(_ptr(self.buf), self.nbits, self.dt, len(blocks), _lib.iptr(ks), _lib.iptr(bits), _ptr(md),
+                                    self.batch if batched else 1, len(tile_hi), _lib.iptr(hi), self.batch, _stream()))
+        STATS["apply_launches"] += 1
+        STATS["apply_bytes"] += 2 * self.amp_bytes * (self.batch << self.nbits)
+
+    # -- reductions ---------------------------------------------------------------------------
+    def norm2(self) -> np.ndarray:
+        ws = self._workspace(lib.tcb200_reduce_workspace_bytes(self.nbits, self.batch))
+        out = torch.empty(self.batch, dtype=torch.float64, device=self.device)
+        check(lib.tcb200_norm2(_ptr(self.buf), self.nbits, self.dt, self.batch, _ptr(out), _ptr(ws), ws.numel(), _stream()))
+        return out.cpu().numpy()
+
+    def probability(self) -> torch.Tensor:
+        rd = torch.float32 if self.dtype == "complex64" else torch.float64
+        p = torch.empty((self.batch, 1 << self.nbits), dtype=rd, device=self.device)
+        check(lib.tcb200_probability(_ptr(self.buf), self.nbits, self.dt, _ptr(p), self.batch, _stream()))
+        return p
+
+    def expectation_terms(self, flips: Sequence[int], signs: Sequence[int], nys: Sequence[int]) -> np.ndarray:
+        """<P_t> for every term (amplitude-bit masks) and batch element -> complex [batch, nterms].
+
+        Terms are grouped so that each launch covers up to MAX_TERMS strings whose flip masks
+        fit one tile geometry; each launch reads the state once."""
+        nt = len(flips)
+        out_all = np.zeros((self.batch, nt), dtype=np.complex128)
+        if nt == 0:
+            return out_all
+        T = lib.tcb200_expect_tile_bits(self.dt)
+        groups = plan_expect_groups(flips, self.nbits, T)
+        ws = self._workspace(lib.tcb200_expect_workspace_bytes(self.nbits, self.batch))
+        outs = []
+        for ids, union in groups:
+            hi = tile_hi_fixpoint(union, T, self.nbits)
+            f = np.asarray([int(flips[t]) for t in ids], dtype=np.uint64)
+            s = np.asarray([int(signs[t]) for t in ids], dtype=np.uint64)
+            ny = np.asarray([int(nys[t]) for t in ids], dtype=np.int32)
+            hia = np.asarray(hi if hi else [0], dtype=np.int32)
+            out = torch.empty((self.batch, len(ids), 2), dtype=torch.float64, device=self.device)
+            check(lib.tcb200_expect_pauli(_ptr(self.buf), self.nbits, self.dt, len(ids), _lib.u64ptr(f), _lib.u64ptr(s), _lib.iptr(ny),
+                                          len(hi), _lib.iptr(hia), _ptr(out), self.batch, _ptr(ws), ws.numel(), _stream()))
+            STATS["expect_launches"] += 1
+            outs.append((ids, out))
+        for ids, out in outs:
+            o = out.cpu().numpy()
+            out_all[:, ids] = o[..., 0] + 1j * o[..., 1]
+        return out_all
+
+    # -- sampler ------------------------------------------------------------------------------
+    def sample(self, uniforms: Any, cdf_offset: float = 0.0, cdf_total: float = -1.0, return_total: bool = False) -> Any:
+        if self.batch != 1:
+            raise _lib.EngineError("sampling a batched state is not supported")
+        u = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64).reshape(-1))
+        shots = u.shape[0]
+        ud = torch.from_numpy(u).to(self.device)
+        idx = torch.empty(max(shots, 1), dtype=torch.int64, device=self.device)
+        tot = torch.empty(1, dtype=torch.float64, device=self.device)
+        ws = self._workspace(lib.tcb200_sample_workspace_bytes(self.nbits))
+        check(lib.tcb200_sample(_ptr(self.buf), self.nbits, self.dt, _ptr(ud), shots, _ptr(idx), _ptr(tot), float(cdf_offset), float(cdf_total),
+                                _ptr(ws), ws.numel(), _stream()))
+        STATS["sample_launches"] += 1
+        res = idx[:shots].cpu().numpy()
+        if return_total:
+            return res, float(tot.cpu().item())
+        return res

@@ -1,0 +1,184 @@
+"""Measurement post-processing and Pauli-string utilities used on the hot path (host side,
+O(shots) or O(n) data).  Mirrors tensorcircuit/quantum.py:1025-1068 (ps2xyz/xyz2ps),
+:2048-2157 (count conversions), :2217-2368 (measurement_counts / sample2all) and :2371-2451
+(spin_by_basis / correlations)."""
+
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+Tensor = Any
+
+
+def ps2xyz(ps: List[int]) -> Dict[str, List[int]]:
+    xyz: Dict[str, List[int]] = {"x": [], "y": [], "z": []}
+    for i, j in enumerate(ps):
+        j = int(j)
+        if j == 1:
+            xyz["x"].append(i)
+        if j == 2:
+            xyz["y"].append(i)
+        if j == 3:
+            xyz["z"].append(i)
+    return xyz
+
+
+def xyz2ps(xyz: Dict[str, List[int]], n: Optional[int] = None) -> List[int]:
+    if n is None:
+        n = max(xyz.get("x", []) + xyz.get("y", []) + xyz.get("z", [])) + 1
+    ps = [0 for _ in range(n)]
+    for i in range(n):
+        if i in xyz.get("x", []):
+            ps[i] = 1
+        elif i in xyz.get("y", []):
+            ps[i] = 2
+        elif i in xyz.get("z", []):
+            ps[i] = 3
+    return ps
+
+
+def sample_int2bin(sample: Tensor, n: int) -> Tensor:
+    sample = np.asarray(sample)
+    return np.mod(np.right_shift(sample[..., None], np.arange(n)[::-1]), 2)
+
+
+def sample_bin2int(sample: Tensor, n: int) -> Tensor:
+    power = np.array([2**j for j in reversed(range(n))])
+    return np.sum(np.asarray(sample) * power, axis=-1)
+
+
+def sample2count(sample: Tensor, n: int, jittable: bool = True) -> Tuple[Tensor, Tensor]:
+    return np.unique(np.asarray(sample), return_counts=True)
+
+
+def count_s2d(srepr: Tuple[Tensor, Tensor], n: int) -> Tensor:
+    out = np.zeros([2**n], dtype=np.asarray(srepr[1]).dtype)
+    out[np.asarray(srepr[0]).reshape(-1)] = srepr[1]
+    return out
+
+
+counts_v2t = count_s2d
+
+
+def count_d2s(drepr: Tensor, eps: float = 1e-7) -> Tuple[Tensor, Tensor]:
+    drepr = np.asarray(drepr)
+    x = np.nonzero(np.abs(drepr) > eps)[0]
+    return x, drepr[x]
+
+
+count_t2v = count_d2s
+
+
+def count_vector2dict(count: Tensor, n: int, key: str = "bin") -> Dict[Any, int]:
+    count = np.asarray(count)
+    d = {i: count[i].item() for i in range(2**n)}
+    if key == "int":
+        return d
+    return {bin(k)[2:].zfill(n): v for k, v in d.items()}
+
+
+def count_tuple2dict(count: Tuple[Tensor, Tensor], n: int, key: str = "bin") -> Dict[Any, int]:
+    d = {int(i): int(j) for i, j in zip(count[0], count[1]) if i >= 0}
+    if key == "int":
+        return d
+    return {bin(k)[2:].zfill(n): v for k, v in d.items()}
+
+
+def sample2all(sample: Tensor, n: int, format: str = "count_vector", jittable: bool = False, format_: Optional[str] = None) -> Any:
+    if format_ is not None:
+        format = format_
+    sample = np.asarray(sample)
+    if sample.ndim == 1:
+        sample_int = sample
+        sample_bin = sample_int2bin(sample, n)
+    elif sample.ndim == 2:
+        sample_int = sample_bin2int(sample, n)
+        sample_bin = sample
+    else:
+        raise ValueError("unrecognized tensor shape for sample")
+    if format == "sample_int":
+        return sample_int
+    if format == "sample_bin":
+        return sample_bin
+    count_tuple = sample2count(sample_int, n, jittable)
+    if format == "count_tuple":
+        return count_tuple
+    if format == "count_vector":
+        return count_s2d(count_tuple, n)
+    if format == "count_dict_bin":
+        return count_tuple2dict(count_tuple, n, key="bin")
+    if format == "count_dict_int":
+        return count_tuple2dict(count_tuple, n, key="int")
+    raise ValueError("unsupported format %s for finite shots measurement" % format)
+
+
+def measurement_counts(
+    state: Tensor,
+    counts: Optional[int] = 8192,
+    format: str = "count_vector",
+    is_prob: bool = False,
+    random_generator: Optional[Any] = None,
+    status: Optional[Tensor] = None,
+    jittable: bool = False,
+    format_: Optional[str] = None,
+) -> Any:
+    """quantum.py:2217-2318: simulate ``counts`` shots on a state (or probability) vector.
+    The state goes to the device and through the engine's CDF sampler."""
+    from . import cons
+    from .circuit import Circuit
+
+    if format_ is not None:
+        format = format_
+    v = np.asarray(state)
+    n = int(round(np.log2(v.shape[0])))
+    if v.ndim == 2:  # density matrix: use its diagonal
+        v = np.sqrt(np.abs(np.diagonal(v)))
+    elif is_prob:
+        v = np.sqrt(np.abs(v))
+    if counts is None or counts <= 0:
+        p = np.abs(v) ** 2
+        p = p / np.sum(p)
+        if counts is not None and counts < 0:
+            p = p * (-counts)
+        if format == "count_vector":
+            return p
+        if format == "count_tuple":
+            return count_d2s(p)
+        if format == "count_dict_bin":
+            return count_vector2dict(p, n, key="bin")
+        if format == "count_dict_int":
+            return count_vector2dict(p, n, key="int")
+        raise ValueError("unsupported format %s for analytical measurement" % format)
+    c = Circuit(n, inputs=v)
+    return c.sample(batch=counts, allow_state=True, format=format, random_generator=random_generator, status=status)
+
+
+measurement_results = measurement_counts
+
+
+def spin_by_basis(n: int, m: int, elements: Tuple[int, int] = (1, -1)) -> Tensor:
+    r = np.arange(2**n)
+    b = (r >> (n - 1 - m)) & 1
+    return np.where(b == 0, elements[0], elements[1])
+
+
+def correlation_from_samples(index: Sequence[int], results: Tensor, n: int) -> Tensor:
+    results = np.asarray(results)
+    if results.ndim == 1:
+        results = sample_int2bin(results, n)
+    results = 1 - results * 2
+    r = results[:, index[0]]
+    for i in index[1:]:
+        r = r * results[:, i]
+    return np.mean(r.astype(np.float64))
+
+
+def correlation_from_counts(index: Sequence[int], results: Tensor) -> Tensor:
+    results = np.asarray(results, dtype=np.float64)
+    results = results / np.sum(results)
+    n = int(round(np.log2(results.shape[0])))
+    for i in index:
+        results = results * spin_by_basis(n, i)
+    return np.sum(results)

@@ -1,0 +1,83 @@
+"""Measurement shortcuts (tensorcircuit/templates/measurements.py:18-208, 290-335) mapped onto the
+multi-term Pauli expectation kernel."""
+
+from __future__ import annotations
+
+from typing import Any, Optional, Sequence
+
+import numpy as np
+
+from .. import cons
+from ..batching import BatchArray, is_batched
+from ..circuit import Circuit
+
+Tensor = Any
+
+
+def any_measurements(c: Circuit, structures: Tensor, onehot: bool = False, reuse: bool = True) -> Tensor:
+    """measurements.py:18-87: expectation of the Pauli string given as a *tensor* (so it can be
+    vmapped): ``structures`` is [n] ints in 0..3 (``onehot=True``) or [n, 4] weights."""
+    n = c._nqubits
+    if onehot:
+        if is_batched(structures):
+            raise NotImplementedError("batched integer structures: pass one-hot weights [n, 4]")
+        ps = [int(v) for v in np.asarray(structures).reshape(-1)]
+        return np.real(c.expectation_ps(ps=ps))
+    s = structures
+    obs = []
+    from .. import gates
+
+    paulis = [np.eye(2), gates._x_matrix, gates._y_matrix, gates._z_matrix]
+    for i in range(n):
+        op = sum(s[i, k] * paulis[k] for k in range(4))
+        obs.append([gates.Gate(op), (i,)])
+    return np.real(c.expectation(*obs, reuse=reuse))
+
+
+parameterized_measurements = any_measurements
+
+
+def any_local_measurements(c: Circuit, structures: Tensor, onehot: bool = False, reuse: bool = True) -> Tensor:
+    """measurements.py:90-153: vector of single-site expectations, one per qubit."""
+    n = c._nqubits
+    ps_all = []
+    st = [int(v) for v in np.asarray(structures).reshape(-1)] if onehot else None
+    if st is None:
+        raise NotImplementedError("weighted local measurements: pass onehot=True")
+    for i in range(n):
+        ps = [0] * n
+        ps[i] = st[i]
+        ps_all.append(ps)
+    return np.real(c.expectation_ps_many(ps_all))
+
+
+parameterized_local_measurements = any_local_measurements
+
+
+def pauli_sum_expectation(c: Circuit, pss: Sequence[Sequence[int]], weights: Optional[Sequence[float]] = None) -> Tensor:
+    """sum_t w_t <P_t> for a Hamiltonian given as Pauli strings -- all terms in as few reads of
+    the state as possible (the one-pass counterpart of looping over ``expectation_ps``)."""
+    vals = c.expectation_ps_many(pss)
+    w = np.ones(len(pss)) if weights is None else np.asarray(weights)
+    if is_batched(vals):
+        return BatchArray(np.real(vals.a) @ w)
+    return np.real(np.sum(w * vals))
+
+
+def spin_glass_measurements(c: Circuit, g: Any, reuse: bool = True) -> Tensor:
+    """measurements.py:290-335: sum_ij w_ij <Z_i Z_j> + sum_i h_i <Z_i>."""
+    n = c._nqubits
+    pss, ws = [], []
+    for e1, e2 in g.edges:
+        ps = [0] * n
+        ps[e1] = ps[e2] = 3
+        pss.append(ps)
+        ws.append(g[e1][e2].get("weight", 1.0))
+    for i in g.nodes:
+        w = g.nodes[i].get("weight", 0.0)
+        if w != 0.0:
+            ps = [0] * n
+            ps[i] = 3
+            pss.append(ps)
+            ws.append(w)
+    return pauli_sum_expectation(c, pss, ws)

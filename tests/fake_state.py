@@ -1,0 +1,97 @@
+"""CPU stand-in for ``engine.DeviceState`` -- TEST INFRASTRUCTURE ONLY.
+
+Lets the host-side logic (Circuit recording, fusion, Pauli decomposition, expectation grouping,
+vmap batching, sample formats) run in the GPU-less build container.  Gate blocks and
+expectations execute the real kernel bodies through tests/emu (CPU emulation of the CUDA
+code); the sampler uses the oracle's restatement of the reference rule.  The product never
+imports this module: ``tensorcircuit_b200.engine.DeviceState`` raises without a CUDA device."""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from oracle import tc_oracle as orc
+from tensorcircuit_b200 import engine
+
+from .test_emu_kernels import EMU_LIB, _build_emu
+
+
+def _ip(a):
+    return np.ascontiguousarray(a, dtype=np.int32).ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+class FakeState:
+    _lib = None
+
+    def __init__(self, nbits, dtype="complex64", batch=1, device=None, buffer=None):
+        if FakeState._lib is None:
+            _build_emu()
+            FakeState._lib = ctypes.CDLL(EMU_LIB)
+            FakeState._lib.emu_last_error.restype = ctypes.c_char_p
+        self.nbits, self.dtype, self.batch = int(nbits), dtype, int(batch)
+        self.dt = 0 if dtype == "complex64" else 1
+        self.np = np.zeros((self.batch, 1 << self.nbits), dtype=dtype)
+        self.buf = torch.from_numpy(self.np)  # shares memory
+        self.device = torch.device("cpu")
+
+    @property
+    def amp_bytes(self):
+        return 8 if self.dtype == "complex64" else 16
+
+    def init_zero(self):
+        self.np[:] = 0
+        self.np[:, 0] = 1
+
+    def load(self, src):
+        if isinstance(src, torch.Tensor):
+            src = src.cpu().numpy()
+        s = np.asarray(src).reshape(-1)
+        if s.size != 1 << self.nbits:
+            raise ValueError("initial state has %d entries" % s.size)
+        self.np[:] = s.astype(self.dtype)[None, :]
+
+    def apply_block(self, blk):
+        bits = list(blk.bits)
+        for b in range(self.batch):
+            m = blk.matrix[b] if blk.batched else blk.matrix
+            m = np.ascontiguousarray(m, dtype=np.complex128)
+            row = self.np[b]
+            rc = self._lib.emu_apply_dense(row.ctypes.data_as(ctypes.c_void_p), self.nbits, self.dt, len(bits), _ip(bits),
+                                           m.view(np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+            assert rc == 0, self._lib.emu_last_error()
+        engine.STATS["apply_launches"] += 1
+
+    def apply_blocks(self, blocks):
+        for b in blocks:
+            self.apply_block(b)
+
+    def norm2(self):
+        return np.sum(np.abs(self.np.astype(np.complex128)) ** 2, axis=1)
+
+    def probability(self):
+        rd = np.float32 if self.dtype == "complex64" else np.float64
+        return torch.from_numpy((np.abs(self.np) ** 2).astype(rd))
+
+    def expectation_terms(self, flips, signs, nys):
+        nt = len(flips)
+        out = np.zeros((self.batch, nt), dtype=np.complex128)
+        T = self._lib.emu_expect_tile_bits(self.dt)
+        for ids, union in engine.plan_expect_groups(flips, self.nbits, T):
+            hi = engine.tile_hi_fixpoint(union, T, self.nbits)
+            f = np.asarray([int(flips[t]) for t in ids], dtype=np.uint64)
+            s = np.asarray([int(signs[t]) for t in ids], dtype=np.uint64)
+            ny = np.asarray([int(nys[t]) for t in ids], dtype=np.int32)
+            for b in range(self.batch):
+                o = np.zeros(2 * len(ids))
+                rc = self._lib.emu_expect(self.np[b].ctypes.data_as(ctypes.c_void_p), self.nbits, self.dt, len(ids),
+                                          f.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), s.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                                          _ip(ny), len(hi), _ip(hi if hi else [0]), o.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+                assert rc == 0, self._lib.emu_last_error()
+                out[b, ids] = o[0::2] + 1j * o[1::2]
+        return out
+
+    def sample(self, uniforms, cdf_offset=0.0, cdf_total=-1.0, return_total=False):
+        p = np.abs(self.np[0].astype(np.complex128)) ** 2
+        r = orc.probability_sample(p, uniforms)
+        return (r, float(p.sum())) if return_total else r
