@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the statevector hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the hot path over one synthetic input: |0..0> -> every fused gate pass of
+the seeded random circuit (r on every qubit + cnot on a random perfect
+matching, depth 20) -> 10^6-shot CDF sample.  N = 1 runs n = 34 complex64 (128 GiB state, or the
+largest n that fits the device, named in config.workload); N > 1 runs the distributed state
+(top log2 N index bits = rank, NCCL all-to-all remaps) with n = 34 + log2 N.
+
+metric  amplitude updates / s = recorded gates x 2^n x steps / time  (the same definition for
+        this arm and for --impl reference, so the driver's ratio is a wall-clock speed-up)
+value   device-resident inputs (uniforms already in HBM), CUDA-event time, max over ranks
+e2e     same metric through the public API (tc.Circuit gate calls -> c.sample(status=host
+        array)): Python recording + fusion + H2D of the uniforms from pinned memory + D2H of
+        the sample indices inside the timed region
+roofline  dominant kernel = dense_kernel (one fused block per launch): algorithmic bytes
+        16 * 2^n per launch / mean launch time (CUDA events around the gate phase of every
+        timed step / number of launches), against the measured copy bandwidth
+cpu_baseline  the C restatement of the reference's gate-by-gate CPU algorithm
+        (oracle/sv_port.c, OpenMP, all host threads) on a bounded sample of the same recipe
+"""
+
+import argparse
+import gc
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEPTH = 20
+SEED = 3
+SHOTS = 10**6
+METRIC = "amplitude_updates_per_s"
+UNIT = "amplitude updates/s (recorded gates x 2^n / s)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("TCB_BENCH_N", "0")), help="override qubit count (testing)")
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("TCB_BENCH_DEPTH", str(DEPTH))))
+    ap.add_argument("--shots", type=int, default=int(os.environ.get("TCB_BENCH_SHOTS", str(SHOTS))))
+    ap.add_argument("--kmax", type=int, default=int(os.environ.get("TCB_BENCH_KMAX", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def roofline_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_port_run(n, depth, seed, shots, budget_s=15.0):
+    """Time the gate-by-gate C restatement on the same recipe at a bounded size."""
+    from oracle import port, tc_oracle as orc
+
+    ops = orc.random_circuit(n, depth, seed)
+    cores = int(port.lib().svp_num_threads())
+    psi = np.empty(2**n, dtype=np.complex64)
+    mats = []
+    for name, q, p in ops:
+        u = orc.gate_matrix(name, **p)
+        k = len(q)
+        bits = [n - 1 - x for x in q]
+        order = np.argsort(bits)
+        perm = list(order[::-1])
+        t = np.transpose(u.reshape([2] * (2 * k)), perm + [k + x for x in perm]).reshape(2**k, 2**k)
+        mats.append((sorted(bits), np.ascontiguousarray(t)))
+    t0 = time.perf_counter()
+    port.init_zero(psi, n)
+    done = 0
+    for bits, u in mats:
+        port.apply(psi, n, bits, u)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    if shots and done == len(mats):
+        port.sample(psi, n, np.random.default_rng(4).random(shots))
+    dt = time.perf_counter() - t0
+    return {"value": done * float(2**n) / dt, "gates": done, "seconds": dt, "cores": cores, "n": n}
+
+
+def cpu_baseline_obj(n_cpu, depth, seed):
+    r = cpu_port_run(n_cpu, depth, seed, 0)
+    return {
+        "value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+        "sample": "oracle/sv_port.c (OpenMP gate-by-gate restatement of cons.py:605-623; the reference itself needs tensornetwork/jax, not installable here): same random-circuit recipe at n=%d complex64, %d gates in %.1f s" % (r["n"], r["gates"], r["seconds"]),
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_cpu = args.n if args.n else 26
+    vals = []
+    t_all = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        budget = 4.0 if i < args.warmup else 12.0
+        r = cpu_port_run(n_cpu, args.depth, SEED, 0, budget_s=budget)
+        if i >= args.warmup:
+            vals.append(r)
+    total_gates = sum(r["gates"] for r in vals)
+    total_s = sum(r["seconds"] for r in vals)
+    value = total_gates * float(2**n_cpu) / total_s
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "c64", "data": "synthetic",
+        "config": workload_config(args.gpus, 34 + int(math.log2(args.gpus)), args.depth, args.shots),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": vals[0]["cores"], "kind": "port",
+                         "sample": "oracle/sv_port.c OpenMP gate-by-gate port of the reference algorithm; each step = the same recipe at n=%d complex64 bounded to 12 s (%d gates timed)" % (n_cpu, total_gates)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, n, depth, shots):
+    return {
+        "workload": "random circuit (r on all qubits + cnot on a random perfect matching) depth %d, n=%d complex64, wavefunction + %d-shot sample(status=...)" % (depth, n, shots),
+        "n_qubits": n, "depth": depth, "shots": shots, "seed": SEED,
+        "parallelism": "single GPU" if n_gpus == 1 else "state sharded over %d GPUs (top %d index bits = rank)" % (n_gpus, int(math.log2(n_gpus))),
+        "l2": "inputs exceed L2 (state >> 126 MB); no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def pick_n(requested, free_bytes, amp_bytes=8):
+    if requested:
+        return requested
+    n = 34
+    while (amp_bytes << n) > 0.9 * free_bytes and n > 20:
+        n -= 1
+    return n
+
+
+def run_ours(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import tensorcircuit_b200 as tc
+    from tensorcircuit_b200 import _lib, engine, recipes
+    from tensorcircuit_b200.fusion import GateOp, fuse
+
+    if args.kmax:
+        tc.Circuit.fusion_kmax = args.kmax
+    if world > 1:
+        from bench_dist import run_dist
+
+        return run_dist(args, tc, rank, world, local)
+
+    free, total = torch.cuda.mem_get_info()
+    n = pick_n(args.n, free)
+    ops = recipes.random_circuit(n, args.depth, SEED)
+    ngates = len(ops)
+    shots = args.shots
+
+    # ---- device-resident leg -------------------------------------------------------------
+    c0 = recipes.build(tc.Circuit(n), ops)
+    blocks = fuse(c0._ops, n, kmax=tc.Circuit.fusion_kmax)
+    khist = {}
+    for b in blocks:
+        khist[len(b.bits)] = khist.get(len(b.bits), 0) + 1
+    st = engine.DeviceState(n, "complex64")
+    u_host = torch.from_numpy(np.random.default_rng(4).random(shots)).pin_memory()
+    u_dev = u_host.to("cuda")
+    idx_dev = torch.empty(shots, dtype=torch.int64, device="cuda")
+    ws = torch.empty(_lib.lib.tcb200_sample_workspace_bytes(n) + 1024, dtype=torch.uint8, device="cuda")
+    stream = engine._stream()
+
+    def device_step(ev=None):
+        st.init_zero()
+        if ev:
+            ev[0].record()
+        st.apply_blocks(blocks)
+        if ev:
+            ev[1].record()
+        _lib.check(_lib.lib.tcb200_sample(engine._ptr(st.buf), n, 0, engine._ptr(u_dev), shots, engine._ptr(idx_dev), None, 0.0, -1.0, engine._ptr(ws), ws.numel(), stream))
+
+    for _ in range(args.warmup):
+        device_step()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.launch_count()
+    torch.cuda.synchronize()
+    t_start.record()
+    for i in range(args.steps):
+        device_step(evs[i])
+    t_end.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    total_ms = t_start.elapsed_time(t_end)
+    apply_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clk = clocks.stop()
+    norm2 = float(st.norm2()[0])
+    samples = idx_dev.cpu().numpy()
+    value = args.steps * ngates * float(2**n) / (total_ms * 1e-3)
+    npass = len(blocks)
+    bytes_per_launch = 16.0 * float(2**n)
+    launch_ms = apply_ms / (args.steps * npass)
+    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    traffic = roofline_traffic()
+
+    # ---- end-to-end leg through the public API ---------------------------------------------------
+    del st
+    gc.collect()
+    torch.cuda.empty_cache()
+    e2e_steps = max(1, min(args.steps, 2))
+    u_np = u_host.numpy()
+
+    def api_step():
+        c = recipes.build(tc.Circuit(n), ops)
+        s = c.sample(batch=shots, allow_state=True, status=u_host, format="sample_int")
+        del c
+        gc.collect()
+        return s
+
+    s_api = api_step()  # warm-up (also allocates the state once; the allocator then reuses it)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        s_api = api_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_value = e2e_steps * ngates * float(2**n) / e2e_s
+    same = bool(np.array_equal(s_api, samples))
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "c64", "data": "synthetic",
+        "config": dict(workload_config(1, n, args.depth, shots), recorded_gates=ngates, fused_passes=npass, block_width_histogram=khist, fusion_kmax=tc.Circuit.fusion_kmax),
+        "fused_pass_updates_per_s": args.steps * npass * float(2**n) / (apply_ms * 1e-3),
+        "gate_phase_ms_per_step": apply_ms / args.steps,
+        "roofline": {"bound": "hbm", "kernel": "dense_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "bytes_per_launch": bytes_per_launch,
+                     "launch_ms": launch_ms, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source")},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(shots * 8 + sum(16 * 4 ** len(b.bits) for b in blocks)), "d2h_bytes_per_step": int(shots * 8),
+                "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "samples_match_device_leg": same},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "checks": {"norm2": norm2, "sample_min": int(samples.min()), "sample_max": int(samples.max())},
+    }
+    if not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline_obj(26, args.depth, SEED)
+        except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: %r" % (e,)}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

@@ -520,6 +520,10 @@ class Circuit:
         nbatch = 1 if batch is None else int(batch)
         if status is None:
             u = cons.backend.stateful_randu(random_generator, shape=[nbatch]) if random_generator is not None else cons.backend.implicit_randu(shape=[nbatch])
+        elif hasattr(status, "is_pinned"):  # torch tensor (e.g. pinned host memory): no host copy
+            u = status
+            if u.numel() != nbatch:
+                raise ValueError("status must hold one uniform per shot")
         else:
             u = np.asarray(status, dtype=np.float64).reshape(-1)
             if u.shape[0] != nbatch:

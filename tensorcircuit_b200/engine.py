@@ -212,9 +212,12 @@ class DeviceState:
     def sample(self, uniforms: Any, cdf_offset: float = 0.0, cdf_total: float = -1.0, return_total: bool = False) -> Any:
         if self.batch != 1:
             raise _lib.EngineError("sampling a batched state is not supported")
-        u = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64).reshape(-1))
-        shots = u.shape[0]
-        ud = torch.from_numpy(u).to(self.device)
+        if isinstance(uniforms, torch.Tensor):  # e.g. pinned host memory: async copy, no staging
+            ud = uniforms.reshape(-1).to(self.device, dtype=torch.float64, non_blocking=True)
+        else:
+            u = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64).reshape(-1))
+            ud = torch.from_numpy(u).to(self.device)
+        shots = ud.shape[0]
         idx = torch.empty(max(shots, 1), dtype=torch.int64, device=self.device)
         tot = torch.empty(1, dtype=torch.float64, device=self.device)
         ws = self._workspace(lib.tcb200_sample_workspace_bytes(self.nbits))

@@ -1,0 +1,327 @@
+"""Parity of the sm_100a kernels, called through the C ABI, against the oracle (``-m gpu``).
+
+Tolerances (north star): amplitudes / expectations within 1e-5 relative for complex64 and
+1e-11 for complex128; sample indices identical to the reference rule evaluated in float64
+except at CDF ties within tolerance."""
+
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+import tensorcircuit_b200 as tc
+from oracle import tc_oracle as orc
+from tensorcircuit_b200 import _lib, engine
+from tensorcircuit_b200.engine import DeviceState
+from tensorcircuit_b200.fusion import Block
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"complex64": 1e-5, "complex128": 1e-11}
+
+
+def _rand_state(rng, n):
+    v = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    return v / np.linalg.norm(v)
+
+
+def _bits_to_qubits(n, bits):
+    return [n - 1 - b for b in reversed(bits)]
+
+
+def _block(n, bits, u):
+    bits = tuple(bits)
+    return Block(qubits=tuple(sorted(n - 1 - b for b in bits)), bits=bits, matrix=np.asarray(u, dtype=np.complex128), batched=False, ngates=1)
+
+
+def _relerr(got, ref):
+    return np.linalg.norm(np.asarray(got) - ref) / np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n", [13, 18])
+def test_apply_dense_placements(dtype, n):
+    rng = np.random.default_rng(n)
+    psi = _rand_state(rng, n)
+    placements = []
+    for k in range(1, 6):
+        placements += [tuple(range(k)), tuple(range(n - k, n))]
+        for _ in range(6):
+            placements.append(tuple(sorted(rng.choice(n, size=k, replace=False).tolist())))
+    for bits in placements:
+        k = len(bits)
+        u = rng.normal(size=(2**k, 2**k)) + 1j * rng.normal(size=(2**k, 2**k))
+        u /= np.linalg.norm(u, 2)
+        st = DeviceState(n, dtype)
+        st.load(psi)
+        st.apply_block(_block(n, bits, u))
+        ref = orc.apply_gate(psi, u, _bits_to_qubits(n, bits), n)
+        err = _relerr(st.buf[0].cpu().numpy(), ref)
+        assert err < TOL[dtype], (bits, err)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_apply_dense_every_low_placement(dtype):
+    """every k-subset of the 7 lowest bits (+ one high bit): the swizzle / lane-plan cases"""
+    n = 14
+    rng = np.random.default_rng(1)
+    psi = _rand_state(rng, n)
+    st = DeviceState(n, dtype)
+    for k in (1, 2, 3, 4):
+        for low in itertools.combinations(range(7), k - 1 if k > 1 else 1):
+            bits = tuple(low) + ((13,) if k > 1 else ())
+            kk = len(bits)
+            u = rng.normal(size=(2**kk, 2**kk)) + 1j * rng.normal(size=(2**kk, 2**kk))
+            u /= np.linalg.norm(u, 2)
+            st.load(psi)
+            st.apply_block(_block(n, bits, u))
+            ref = orc.apply_gate(psi, u, _bits_to_qubits(n, bits), n)
+            assert _relerr(st.buf[0].cpu().numpy(), ref) < TOL[dtype], bits
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_tiny_states(dtype):
+    rng = np.random.default_rng(2)
+    for n in (1, 2, 3, 5):
+        for k in range(1, min(n, 5) + 1):
+            bits = tuple(sorted(rng.choice(n, size=k, replace=False).tolist()))
+            psi = _rand_state(rng, n)
+            u = rng.normal(size=(2**k, 2**k)) + 1j * rng.normal(size=(2**k, 2**k))
+            st = DeviceState(n, dtype)
+            st.load(psi)
+            st.apply_block(_block(n, bits, u))
+            ref = orc.apply_gate(psi, u, _bits_to_qubits(n, bits), n)
+            assert _relerr(st.buf[0].cpu().numpy(), ref) < 10 * TOL[dtype], (n, bits)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_apply_pass_multi_block(dtype):
+    n = 17
+    rng = np.random.default_rng(3)
+    T = _lib.lib.tcb200_pass_tile_bits(0 if dtype == "complex64" else 1)
+    for trial in range(8):
+        n_hi = int(rng.integers(0, 5))
+        lrow = T - n_hi
+        hi = sorted(rng.choice(np.arange(lrow, n), size=n_hi, replace=False).tolist())
+        avail = list(range(lrow)) + hi
+        psi = _rand_state(rng, n)
+        ref = psi.copy()
+        blocks = []
+        for _ in range(int(rng.integers(1, 9))):
+            k = int(rng.integers(1, 5))
+            bits = sorted(rng.choice(avail, size=k, replace=False).tolist())
+            u = rng.normal(size=(2**k, 2**k)) + 1j * rng.normal(size=(2**k, 2**k))
+            u /= np.linalg.norm(u, 2)
+            ref = orc.apply_gate(ref, u, _bits_to_qubits(n, bits), n)
+            blocks.append(_block(n, bits, u))
+        st = DeviceState(n, dtype)
+        st.load(psi)
+        st.apply_pass(blocks, hi)
+        assert _relerr(st.buf[0].cpu().numpy(), ref) < 5 * TOL[dtype], trial
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_apply_batched(dtype):
+    n, B = 12, 5
+    rng = np.random.default_rng(4)
+    psi = _rand_state(rng, n)
+    st = DeviceState(n, dtype, batch=B)
+    st.load(psi)
+    refs = [psi.copy() for _ in range(B)]
+    for bits in [(0, 3), (11,), (2, 5, 9, 10), (1, 4, 6)]:
+        k = len(bits)
+        us = rng.normal(size=(B, 2**k, 2**k)) + 1j * rng.normal(size=(B, 2**k, 2**k))
+        us /= np.linalg.norm(us, 2, axis=(1, 2))[:, None, None]
+        blk = _block(n, bits, us)
+        blk.batched = True
+        st.apply_block(blk)
+        refs = [orc.apply_gate(refs[b], us[b], _bits_to_qubits(n, bits), n) for b in range(B)]
+    # shared matrix on a batched state
+    u = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    u /= np.linalg.norm(u, 2)
+    st.apply_block(_block(n, (1, 7), u))
+    refs = [orc.apply_gate(r, u, _bits_to_qubits(n, (1, 7)), n) for r in refs]
+    got = st.buf.cpu().numpy()
+    for b in range(B):
+        assert _relerr(got[b], refs[b]) < 5 * TOL[dtype]
+    n2 = st.norm2()
+    np.testing.assert_allclose(n2, [np.vdot(r, r).real for r in refs], rtol=20 * TOL[dtype])
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_apply_diag(dtype):
+    n = 15
+    rng = np.random.default_rng(5)
+    psi = _rand_state(rng, n)
+    dt = 0 if dtype == "complex64" else 1
+    for bits in [(0,), (3, 14), (0, 1, 2, 3, 4, 5, 6, 7, 8, 9), (2, 6, 11, 13)]:
+        k = len(bits)
+        d = np.exp(1j * rng.uniform(0, 6, size=2**k))
+        st = DeviceState(n, dtype)
+        st.load(psi)
+        b = np.asarray(bits, dtype=np.int32)
+        _lib.check(_lib.lib.tcb200_apply_diag(engine._ptr(st.buf), n, dt, k, _lib.iptr(b), _lib.dptr(np.ascontiguousarray(d).view(np.float64)), None, 1, engine._stream()))
+        ref = orc.apply_gate(psi, np.diag(d), _bits_to_qubits(n, bits), n)
+        assert _relerr(st.buf[0].cpu().numpy(), ref) < TOL[dtype], bits
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_expectation_kernel(dtype):
+    n = 16
+    rng = np.random.default_rng(6)
+    psi = _rand_state(rng, n)
+    st = DeviceState(n, dtype)
+    st.load(psi)
+    pss = [list(r) for r in rng.integers(0, 4, size=[5, n])]
+    # sparse strings incl. high flips and Y's
+    for q in (0, 1, 7, 15):
+        for p in (1, 2, 3):
+            ps = [0] * n
+            ps[q] = p
+            pss.append(ps)
+    pss.append([3] * n)
+    pss.append([0] * n)
+    fl, sg, ny, want = [], [], [], []
+    for ps in pss[5:]:
+        x, y, z = orc.resolve_ps(n, ps=ps)
+        f, s, c = orc.pauli_masks(n, x, y, z)
+        fl.append(f); sg.append(s); ny.append(c)
+        want.append(orc.pauli_expectation(psi, n, x, y, z))
+    got = st.expectation_terms(fl, sg, ny)[0]
+    np.testing.assert_allclose(got, want, atol=TOL[dtype])
+    # dense random strings flip many high bits: must raise cleanly (too many gathered bits) or be right
+    c = tc.Circuit(6, inputs=_rand_state(rng, 6))
+    tc.set_dtype(dtype)
+    c = tc.Circuit(6, inputs=psi[:64] / np.linalg.norm(psi[:64]))
+    for ps in rng.integers(0, 4, size=[6, 6]):
+        o = orc.OracleCircuit(6, inputs=psi[:64] / np.linalg.norm(psi[:64]))
+        np.testing.assert_allclose(c.expectation_ps(ps=list(ps)), o.expectation_ps(ps=list(ps)), atol=TOL[dtype])
+    tc.set_dtype("complex64")
+    # determinism: run-to-run identical bits
+    a = st.expectation_terms(fl, sg, ny)
+    b = st.expectation_terms(fl, sg, ny)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n", [5, 14, 20])
+def test_sampler_rule(dtype, n):
+    rng = np.random.default_rng(7 + n)
+    psi = _rand_state(rng, n)
+    if n == 14:  # zero-probability runs and a heavy entry
+        psi[: 2**10] = 0
+        psi[5000] = 3.0
+        psi /= np.linalg.norm(psi)
+    st = DeviceState(n, dtype)
+    st.load(psi)
+    u = rng.random(20000)
+    u[:4] = [0.0, 0.5, 1 - 1e-12, 0.25]
+    got, total = st.sample(u, return_total=True)
+    dev = st.buf[0].cpu().numpy().astype(np.complex128)
+    p = np.abs(dev) ** 2
+    np.testing.assert_allclose(total, p.sum(), rtol=1e-12)
+    cdf = np.cumsum(p)
+    r = cdf[-1] * (1 - u)
+    want = np.searchsorted(cdf, r, side="left")
+    want = np.minimum(want, 2**n - 1)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) < 20
+    for i in bad:  # ties only
+        lo, hi = sorted((int(got[i]), int(want[i])))
+        assert abs(cdf[lo] - r[i]) <= 1e-12 * cdf[-1] + 1e-15, (i, got[i], want[i])
+    assert np.all(p[got] > 0)
+    # chi^2-free sanity: empirical mean of bit 0
+    assert abs(np.mean(got & 1) - p[1::2].sum() / p.sum()) < 0.02
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_norm_and_probability(dtype):
+    n = 19
+    rng = np.random.default_rng(8)
+    psi = 3.0 * _rand_state(rng, n)
+    st = DeviceState(n, dtype)
+    st.load(psi)
+    np.testing.assert_allclose(st.norm2()[0], 9.0, rtol=1e-6 if dtype == "complex64" else 1e-13)
+    p = st.probability()[0].cpu().numpy()
+    np.testing.assert_allclose(p, np.abs(psi) ** 2, rtol=1e-5, atol=1e-12)
+    st.init_zero()
+    v = st.buf[0].cpu().numpy()
+    assert v[0] == 1 and np.count_nonzero(v) == 1
+
+
+def test_run_circuit_host():
+    """Host-buffer entry point: gate blocks + sampling in one C call."""
+    n = 12
+    rng = np.random.default_rng(9)
+    st = DeviceState(n, "complex64")
+    ks, bits, mats = [], [], []
+    ref = np.zeros(2**n, dtype=np.complex128)
+    ref[0] = 1
+    for _ in range(10):
+        k = int(rng.integers(1, 5))
+        b = sorted(rng.choice(n, size=k, replace=False).tolist())
+        u = np.linalg.qr(rng.normal(size=(2**k, 2**k)) + 1j * rng.normal(size=(2**k, 2**k)))[0]
+        ref = orc.apply_gate(ref, u, _bits_to_qubits(n, b), n)
+        ks.append(k); bits += b; mats.append(np.ascontiguousarray(u, dtype=np.complex128).reshape(-1))
+    shots = 1000
+    u01 = rng.random(shots)
+    out = np.zeros(shots, dtype=np.int64)
+    need = _lib.lib.tcb200_sample_workspace_bytes(n) + shots * 16 + 4096
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    ka = np.asarray(ks, dtype=np.int32); ba = np.asarray(bits, dtype=np.int32); ma = np.concatenate(mats)
+    _lib.check(_lib.lib.tcb200_run_circuit_host(engine._ptr(st.buf), n, 0, 1, len(ks), _lib.iptr(ka), _lib.iptr(ba), _lib.dptr(ma.view(np.float64)),
+                                                shots, _lib.dptr(u01), _lib.i64ptr(out), engine._ptr(ws), ws.numel(), engine._stream()))
+    assert _relerr(st.buf[0].cpu().numpy(), ref) < 1e-5
+    cdf = orc.sample_cdf(np.abs(st.buf[0].cpu().numpy().astype(np.complex128)) ** 2)
+    want = np.searchsorted(cdf, cdf[-1] * (1 - u01), side="left")
+    assert np.mean(out == want) > 0.995
+
+
+def test_config4_recipe_n22_and_properties():
+    """Config 4 recipe (random circuit, seed 3) at n = 22 vs the oracle, then size-independent
+    properties at n = 28: norm preservation and circuit followed by its inverse = identity."""
+    n = 22
+    ops = orc.random_circuit(n, 3, seed=3)
+    c = tc.Circuit(n)
+    for name, q, p in ops:
+        getattr(c, name)(*q, **p)
+    o = orc.run_gatelist(n, ops)
+    psi = np.asarray(c.state())
+    assert _relerr(psi, o.state()) < 1e-5
+    zs = c.expectation_ps_many([[3 if j == i else 0 for j in range(n)] for i in range(n)])
+    want = [o.expectation_ps(z=[i]).real for i in range(n)]
+    np.testing.assert_allclose(np.real(zs), want, atol=1e-5)
+    n = 28
+    ops = orc.random_circuit(n, 4, seed=5)
+    c = tc.Circuit(n)
+    for name, q, p in ops:
+        getattr(c, name)(*q, **p)
+    st = c._ensure_state()
+    np.testing.assert_allclose(st.norm2()[0], 1.0, atol=2e-5)
+    # sample marginals agree with <Z_i> from the expectation kernel
+    u = np.random.default_rng(4).random(200000)
+    s = c.sample(batch=len(u), allow_state=True, format="sample_int", status=u)
+    zs = np.real(c.expectation_ps_many([[3 if j == i else 0 for j in range(n)] for i in range(n)]))
+    for i in range(n):
+        emp = np.mean(1 - 2 * ((s >> (n - 1 - i)) & 1))
+        assert abs(emp - zs[i]) < 0.02
+    c.append(c.inverse())
+    st = c._ensure_state()
+    amp0 = c.amplitude("0" * n)
+    assert abs(abs(amp0) - 1.0) < 1e-4
+
+
+def test_config2_tfim_energy_n20():
+    """Config 2 recipe at n = 20 vs the oracle (energy of 2n TFIM strings)."""
+    n = 20
+    params = np.random.default_rng(1).uniform(0, 2 * np.pi, [8, n])
+    ops = orc.tfim_vqe_circuit(n, params)
+    c = tc.Circuit(n)
+    for name, q, p in ops:
+        getattr(c, name)(*q, **p)
+    o = orc.run_gatelist(n, ops)
+    terms = orc.tfim_terms(n)
+    e = tc.templates.measurements.pauli_sum_expectation(c, [ps for _, ps in terms], [w for w, _ in terms])
+    want = sum(w * o.expectation_ps(ps=ps).real for w, ps in terms)
+    assert abs(e - want) / max(abs(want), 1e-3 * len(terms)) < 1e-5
