@@ -62,6 +62,18 @@ const char* tcb200_last_error(void);
 int tcb200_init_zero(void* state, int nbits, int dtype, int64_t batch, void* stream);
 
 /*
+ * All-zero vector (a shard of a distributed |0...0> that does not hold amplitude 0).
+ */
+int tcb200_set_zero(void* state, int nbits, int dtype, int64_t batch, void* stream);
+
+/*
+ * Device-to-device copy of `nrows` runs of `row_bytes` bytes (pitches in bytes): the pack /
+ * unpack step of a chunked global<->local qubit remap.  Runs on the copy path of `stream`.
+ */
+int tcb200_copy_rows(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                     size_t row_bytes, size_t nrows, void* stream);
+
+/*
  * Cast/copy an initial state into the engine buffer (device -> device, complex128 source):
  * Circuit(n, inputs=...) (tensorcircuit/circuit.py:86-96).  `src_c128` holds 2^nbits double2.
  */

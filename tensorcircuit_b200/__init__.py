@@ -20,6 +20,7 @@ from .cons import (  # noqa: F401
     runtime_dtype,
     set_backend,
     set_contractor,
+    set_distributed,
     set_dtype,
     set_function_backend,
     set_function_contractor,

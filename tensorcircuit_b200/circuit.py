@@ -331,6 +331,11 @@ class Circuit:
 
         batch = self._batch or 1
         if self._state is None or self._state.batch != batch:
+            if cons.distributed_state:
+                from .parallel import world
+
+                if world()[1] > 1:
+                    from .dist import DistEngineState as DeviceState  # noqa: F811
             st = DeviceState(self._ntot, self._dtype, batch)
             if self.inputs is None:
                 st.init_zero()

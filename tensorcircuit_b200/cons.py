@@ -25,6 +25,8 @@ rdtypestr = "float32"
 npdtype = np.complex64
 backend: Any = None  # bound by b200_backend.py at import
 contractor: Any = None
+# True: under torchrun (world size > 1) every Circuit shards its state over the ranks
+distributed_state = False
 
 _BACKEND_ALIASES = ("b200", "cuda", "numpy", "jax", "tensorflow", "pytorch", "cupy")
 
@@ -75,6 +77,14 @@ def set_dtype(dtype: Optional[str] = None, set_global: bool = True) -> Any:
 
 
 get_dtype = set_dtype
+
+
+def set_distributed(flag: bool = True) -> bool:
+    """Shard every Circuit's state vector over the ranks of the default process group (top
+    log2(G) index bits = rank; see tensorcircuit_b200.dist).  SPMD: all ranks run the same
+    script and get identical host-side results."""
+    _rebind("distributed_state", bool(flag))
+    return bool(flag)
 
 
 def set_contractor(method: Optional[str] = None, *args: Any, **kws: Any) -> Any:

@@ -71,6 +71,24 @@ TCB_HD C cmul(const C a, const C b) {
     return r;
 }
 
+// complex64 on Blackwell: one complex multiply-add = 2 packed FFMA2 (sm_100 fma.rn.f32x2).
+// ptxas folds the broadcast of m.x / m.y, the (v.y, v.x) half swap and the (-,+) sign pattern
+// into operand modifiers (UR.F32 scalar operand, .F32x2.LO_HI, .NP), so the matrix stays a plain
+// (re, im) pair in the constant bank and the instruction count per amplitude halves -- which
+// is what moves the k=4 block from issue-bound to HBM-bound (profiles/r1_dense_k4.md).
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+template <>
+__device__ __forceinline__ void cfma<float2>(float2& acc, const float2 m, const float2 v) {
+    acc = __ffma2_rn(make_float2(m.x, m.x), v, acc);
+    acc = __ffma2_rn(make_float2(-m.y, m.y), make_float2(v.y, v.x), acc);
+}
+template <>
+__device__ __forceinline__ float2 cmul<float2>(const float2 m, const float2 v) {
+    float2 acc = __ffma2_rn(make_float2(m.x, m.x), v, make_float2(0.f, 0.f));
+    return __ffma2_rn(make_float2(-m.y, m.y), make_float2(v.y, v.x), acc);
+}
+#endif
+
 // ---- shared-memory swizzle -----------------------------------------------------------------
 // Tiles live in shared memory as 16-byte units.  Unit u is stored at slot
 //   swz(u) = u ^ ((u>>3)&7) ^ ((u>>6)&7)

@@ -287,6 +287,25 @@ int tcb200_init_zero(void* state, int nbits, int dtype, int64_t batch, void* str
     return 0;
 }
 
+int tcb200_set_zero(void* state, int nbits, int dtype, int64_t batch, void* stream) {
+    if (!state) return fail(TCB200_ERR_ARG, "state is NULL");
+    if (dtype != TCB200_C64 && dtype != TCB200_C128) return fail(TCB200_ERR_ARG, "bad dtype %d", dtype);
+    if (nbits < 1 || nbits > 40 || batch < 1) return fail(TCB200_ERR_ARG, "bad size");
+    const size_t esz = dtype == TCB200_C64 ? 8 : 16;
+    TCB_CUDA(cudaMemsetAsync(state, 0, (esz << nbits) * (size_t)batch, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int tcb200_copy_rows(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                     size_t row_bytes, size_t nrows, void* stream) {
+    if (!dst || !src) return fail(TCB200_ERR_ARG, "NULL argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (size_t r = 0; r < nrows; ++r)
+        TCB_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + r * dst_pitch, static_cast<const char*>(src) + r * src_pitch,
+                                 row_bytes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 int tcb200_load_c128(void* state, int nbits, int dtype, const void* src, void* stream) {
     if (!state || !src) return fail(TCB200_ERR_ARG, "NULL argument");
     if (dtype != TCB200_C64 && dtype != TCB200_C128) return fail(TCB200_ERR_ARG, "bad dtype %d", dtype);

@@ -93,5 +93,11 @@ class FakeState:
 
     def sample(self, uniforms, cdf_offset=0.0, cdf_total=-1.0, return_total=False):
         p = np.abs(self.np[0].astype(np.complex128)) ** 2
-        r = orc.probability_sample(p, uniforms)
+        if cdf_total < 0:
+            r = orc.probability_sample(p, uniforms)
+        else:  # shard of a distributed state: same contract as tcb200_sample
+            cdf = np.cumsum(p)
+            t = cdf_total * (1 - np.asarray(uniforms, dtype=np.float64)) - cdf_offset
+            own = (t > 0) & (t <= cdf[-1])
+            r = np.where(own, np.minimum(np.searchsorted(cdf, t, side="left"), p.size - 1), -1).astype(np.int64)
         return (r, float(p.sum())) if return_total else r
