@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--shots", type=int, default=int(os.environ.get("TCB_BENCH_SHOTS", str(SHOTS))))
     ap.add_argument("--kmax", type=int, default=int(os.environ.get("TCB_BENCH_KMAX", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-block", action="store_true", help="one fused block per pass (dense_kernel only)")
     return ap.parse_args()
 
 
@@ -231,7 +232,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import tensorcircuit_b200 as tc
     from tensorcircuit_b200 import _lib, engine, recipes
-    from tensorcircuit_b200.fusion import GateOp, fuse
+    from tensorcircuit_b200.fusion import Block, GateOp, fuse
 
     if args.kmax:
         tc.Circuit.fusion_kmax = args.kmax
@@ -258,12 +259,17 @@ def run_ours(args):
     idx_dev = torch.empty(shots, dtype=torch.int64, device="cuda")
     ws = torch.empty(_lib.lib.tcb200_sample_workspace_bytes(n) + 1024, dtype=torch.uint8, device="cuda")
     stream = engine._stream()
+    use_passes = bool(tc.Circuit.use_passes) and not args.single_block
+    npass_box = [len(blocks)]
 
     def device_step(ev=None):
         st.init_zero()
         if ev:
             ev[0].record()
-        st.apply_blocks(blocks)
+        if use_passes:
+            npass_box[0] = st.apply_planned(blocks)
+        else:
+            st.apply_blocks(blocks)
         if ev:
             ev[1].record()
         _lib.check(_lib.lib.tcb200_sample(engine._ptr(st.buf), n, 0, engine._ptr(u_dev), shots, engine._ptr(idx_dev), None, 0.0, -1.0, engine._ptr(ws), ws.numel(), stream))
@@ -288,12 +294,29 @@ def run_ours(args):
     norm2 = float(st.norm2()[0])
     samples = idx_dev.cpu().numpy()
     value = args.steps * ngates * float(2**n) / (total_ms * 1e-3)
-    npass = len(blocks)
+    npass = npass_box[0]
     bytes_per_launch = 16.0 * float(2**n)
     launch_ms = apply_ms / (args.steps * npass)
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     traffic = roofline_traffic()
+    # single fused block per pass (north-star item 2), measured live in the same run: k = 3 on
+    # spread targets, 2 warm-up + 5 timed launches
+    probe = {}
+    for k in (3, 4):
+        bits = tuple(sorted(set(np.linspace(1, n - 2, k).astype(int).tolist())))
+        u = np.linalg.qr(np.random.default_rng(k).normal(size=(2**k, 2**k)) + 1j * np.random.default_rng(k + 9).normal(size=(2**k, 2**k)))[0]
+        blk = Block(qubits=tuple(sorted(n - 1 - b for b in bits)), bits=bits, matrix=u, batched=False, ngates=1)
+        for _ in range(2):
+            st.apply_block(blk)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(5):
+            st.apply_block(blk)
+        p1.record()
+        torch.cuda.synchronize()
+        pms = p0.elapsed_time(p1) / 5
+        probe["k%d" % k] = {"launch_ms": pms, "achieved": bytes_per_launch / (pms * 1e-3) / 1e9, "frac": bytes_per_launch / (pms * 1e-3) / 1e9 / peak}
 
     # ---- end-to-end leg through the public API ---------------------------------------------------
     del st
@@ -304,6 +327,7 @@ def run_ours(args):
 
     def api_step():
         c = recipes.build(tc.Circuit(n), ops)
+        c.use_passes = use_passes
         s = c.sample(batch=shots, allow_state=True, status=u_host, format="sample_int")
         del c
         gc.collect()
@@ -326,9 +350,12 @@ def run_ours(args):
         "config": dict(workload_config(1, n, args.depth, shots), recorded_gates=ngates, fused_passes=npass, block_width_histogram=khist, fusion_kmax=tc.Circuit.fusion_kmax),
         "fused_pass_updates_per_s": args.steps * npass * float(2**n) / (apply_ms * 1e-3),
         "gate_phase_ms_per_step": apply_ms / args.steps,
-        "roofline": {"bound": "hbm", "kernel": "dense_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "roofline": {"bound": "hbm", "kernel": "cpass_kernel (staged multi-block pass)" if use_passes else "dense_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "bytes_per_launch": bytes_per_launch,
-                     "launch_ms": launch_ms, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source")},
+                     "launch_ms": launch_ms, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
+                     "fp32_fma_per_amp_per_launch": sum(4 * 2 ** len(b.bits) for b in blocks) / max(1, npass),
+                     "note": "a staged pass holding several blocks is FP32-FMA-bound, not HBM-bound: see roofline_single_block for the one-block-per-pass kernel"},
+        "roofline_single_block": dict(probe, bound="hbm", kernel="dense_kernel", peak=peak, unit="GB/s"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(shots * 8 + sum(16 * 4 ** len(b.bits) for b in blocks)), "d2h_bytes_per_step": int(shots * 8),
                 "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "samples_match_device_leg": same},
         "gpu_launches": int(launches),

@@ -128,8 +128,19 @@ int tcb200_apply_pass(void* state, int nbits, int dtype, int nops, const int* op
                       const int* ops_bits, const void* ops_mats_dev, int64_t batch_mats,
                       int n_hi, const int* tile_hi, int64_t batch, void* stream);
 
+/*
+ * Same staged multi-block pass for matrices shared by all batch elements, given on the HOST
+ * (complex128, concatenated, 4^k_i entries each, at most 12 KiB in the state's dtype): they are
+ * cast and travel in the kernel-parameter constant bank, so the FMAs read them as constant
+ * operands.  This is the kernel the pass planner (fusion.plan_passes) drives: a run of fused
+ * blocks costs one HBM read + write however many blocks it holds.
+ */
+int tcb200_apply_pass_host(void* state, int nbits, int dtype, int nops, const int* ops_k,
+                           const int* ops_bits, const double* ops_mats, int n_hi,
+                           const int* tile_hi, int64_t batch, void* stream);
+
 /* Geometry the pass planner needs: log2 of the tile size (amplitudes) used by
- * tcb200_apply_pass for `dtype`. */
+ * tcb200_apply_pass / tcb200_apply_pass_host for `dtype`. */
 int tcb200_pass_tile_bits(int dtype);
 
 /*

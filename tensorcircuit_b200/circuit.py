@@ -101,8 +101,12 @@ class Circuit:
     vgates = vgates
     mpogates = mpogates
     gate_aliases = gate_aliases
-    # widest dense block the fusion pass builds (roofline cost model, see fusion.py)
-    fusion_kmax = 4
+    # Fusion width.  With staged multi-block passes (use_passes) the state is read and written
+    # once per *pass*, so narrow blocks are best: they minimise the FP32 work (8*2^k flop per
+    # amplitude per block), which is what bounds a pass once several blocks share it.  Without
+    # passes k=3 is the widest block that stays HBM-bound (measured).
+    fusion_kmax = 2
+    use_passes = True
 
     def __init__(
         self,
@@ -347,7 +351,10 @@ class Circuit:
         if self._applied < len(self._ops):
             pending = self._ops[self._applied :]
             blocks = fuse(pending, self._ntot, kmax=self.fusion_kmax)
-            self._state.apply_blocks(blocks)
+            if self.use_passes and hasattr(self._state, "apply_planned"):
+                self._state.apply_planned(blocks)
+            else:
+                self._state.apply_blocks(blocks)
             self._applied = len(self._ops)
         return self._state
 

@@ -276,6 +276,117 @@ static int launch_pass(void* state, int nbits, int nops, const int* ops_k, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// multi-block pass, shared matrices in the parameter constant bank
+// ------------------------------------------------------------------------------------------------
+constexpr int CPASS_MAT_BYTES = 12 * 1024;
+
+template <typename Real>
+struct CPassParams {
+    typename CT<Real>::type* state;
+    TileGeom g;
+    int tb;
+    int nops;
+    PassOp op[TCB200_MAX_PASS_OPS];
+    typename CT<Real>::type m[CPASS_MAT_BYTES / sizeof(typename CT<Real>::type)];
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(256) cpass_kernel(const __grid_constant__ CPassParams<Real> p) {
+    using C = typename CT<Real>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    C* tile = reinterpret_cast<C*>(smem_raw);
+    __shared__ uint64_t rowoff[32];
+
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    if (tid < (1 << p.g.h)) rowoff[tid] = row_offset(p.g, tid);
+    C* vec = p.state + ((uint64_t)blockIdx.y << p.g.n);
+    const uint64_t base = tile_base(p.g, blockIdx.x);
+    __syncthreads();
+    stage_in<C, true>(p.g, vec, base, tile, rowoff, tid, nthr);
+    cp_async_wait_all();
+    __syncthreads();
+
+    for (int o = 0; o < p.nops; ++o) {
+        const PassOp& op = p.op[o];
+        const int mo = op.moff;
+        switch (op.k) {
+            case 1:
+                apply_block_on_tile<C, 1>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return p.m[mo + i * 2 + j]; });
+                break;
+            case 2:
+                apply_block_on_tile<C, 2>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return p.m[mo + i * 4 + j]; });
+                break;
+            case 3:
+                apply_block_on_tile<C, 3>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return p.m[mo + i * 8 + j]; });
+                break;
+            default:
+                apply_block_on_tile<C, 4>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return p.m[mo + i * 16 + j]; });
+                break;
+        }
+        __syncthreads();
+    }
+    stage_out<C, true>(p.g, vec, base, tile, rowoff, tid, nthr);
+}
+
+template <typename Real>
+static int launch_cpass(void* state, int nbits, int nops, const int* ops_k, const int* ops_bits,
+                        const double* mats, int n_hi, const int* tile_hi, int64_t batch, cudaStream_t st) {
+    using C = typename CT<Real>::type;
+    constexpr int APU = CT<Real>::APU;
+    constexpr int MAXM = CPASS_MAT_BYTES / (int)sizeof(C);
+    static thread_local CPassParams<Real>* tp = nullptr;
+    if (!tp) tp = new CPassParams<Real>();
+    CPassParams<Real>& q = *tp;
+    q.state = static_cast<C*>(state);
+    const int tile_bits = pass_tile_bits(sizeof(Real) == 4 ? TCB200_C64 : TCB200_C128);
+    int rc = make_geom_hi(nbits, tile_bits, nbits <= tile_bits ? 0 : n_hi, tile_hi, &q.g);
+    if (rc) return rc;
+    q.nops = nops;
+    int kmin = 99;
+    int moff = 0;
+    const int* b = ops_bits;
+    const double* mp = mats;
+    for (int o = 0; o < nops; ++o) {
+        const int k = ops_k[o];
+        if (k < 1 || k > TCB200_MAX_PASS_K)
+            return fail(TCB200_ERR_UNSUPPORTED, "block of %d bits inside a pass (max %d)", k, TCB200_MAX_PASS_K);
+        for (int i = 0; i < k; ++i)
+            if (b[i] < 0 || b[i] >= nbits) return fail(TCB200_ERR_ARG, "bit %d out of range", b[i]);
+        const int sz = 1 << (2 * k);
+        if (moff + sz > MAXM) return fail(TCB200_ERR_UNSUPPORTED, "pass matrices exceed %d bytes", CPASS_MAT_BYTES);
+        q.op[o].k = k;
+        q.op[o].moff = moff;
+        rc = make_group_map(q.g, APU, k, b, &q.op[o].gm);
+        if (rc) return rc;
+        for (int i = 0; i < sz; ++i) {
+            q.m[moff + i].x = (Real)mp[2 * i];
+            q.m[moff + i].y = (Real)mp[2 * i + 1];
+        }
+        moff += sz;
+        mp += 2 * sz;
+        b += k;
+        if (k < kmin) kmin = k;
+    }
+    q.tb = pick_threads(q.g.T, kmin, APU);
+    const uint64_t ntiles = 1ull << (nbits - q.g.T);
+    if (ntiles > 0x7fffffffull) return fail(TCB200_ERR_UNSUPPORTED, "state too large for one grid");
+    if (batch < 1 || batch > 65535) return fail(TCB200_ERR_ARG, "batch=%lld out of range", (long long)batch);
+    size_t smem = ((size_t)sizeof(C) << q.g.T);
+    if (smem < 16) smem = 16;
+    static bool attr = false;
+    if (!attr) {
+        TCB_CUDA(cudaFuncSetAttribute(cpass_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    dim3 grid((unsigned)ntiles, (unsigned)batch);
+    dim3 block(1u << q.tb);
+    cpass_kernel<Real><<<grid, block, smem, st>>>(q);
+    TCB_LAUNCH_CHECK("cpass_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // diagonal block
 // ------------------------------------------------------------------------------------------------
 struct DiagParams {
@@ -355,6 +466,19 @@ int tcb200_apply_pass(void* state, int nbits, int dtype, int nops, const int* op
     if (dtype == TCB200_C64)
         return launch_pass<float>(state, nbits, nops, ops_k, ops_bits, ops_mats_dev, batch_mats, n_hi, tile_hi, batch, st);
     return launch_pass<double>(state, nbits, nops, ops_k, ops_bits, ops_mats_dev, batch_mats, n_hi, tile_hi, batch, st);
+}
+
+int tcb200_apply_pass_host(void* state, int nbits, int dtype, int nops, const int* ops_k,
+                           const int* ops_bits, const double* ops_mats, int n_hi,
+                           const int* tile_hi, int64_t batch, void* stream) {
+    if (!state || !ops_k || !ops_bits || !ops_mats) return fail(TCB200_ERR_ARG, "NULL argument");
+    if (dtype != TCB200_C64 && dtype != TCB200_C128) return fail(TCB200_ERR_ARG, "bad dtype %d", dtype);
+    if (nops < 1 || nops > TCB200_MAX_PASS_OPS) return fail(TCB200_ERR_ARG, "nops=%d out of range", nops);
+    if (nbits < 1 || nbits > 40) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == TCB200_C64)
+        return launch_cpass<float>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, batch, st);
+    return launch_cpass<double>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, batch, st);
 }
 
 int tcb200_apply_diag(void* state, int nbits, int dtype, int k, const int* bits,

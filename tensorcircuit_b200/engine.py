@@ -7,6 +7,7 @@ O(2^n) data; every such step is a tcb200 kernel.  There is no CPU path: construc
 
 from __future__ import annotations
 
+import os
 from ctypes import c_void_p
 from typing import Any, List, Optional, Sequence, Tuple
 
@@ -15,7 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import check, lib
-from .fusion import Block
+from .fusion import Block, plan_passes, tile_hi_fixpoint  # noqa: F401
 
 _TORCH_C = {"complex64": torch.complex64, "complex128": torch.complex128}
 _DT = {"complex64": _lib.C64, "complex128": _lib.C128}
@@ -42,19 +43,6 @@ def _stream() -> c_void_p:
 
 def _ptr(t: torch.Tensor) -> c_void_p:
     return c_void_p(t.data_ptr())
-
-
-def tile_hi_fixpoint(bits: Sequence[int], tile_bits: int, nbits: int) -> List[int]:
-    """Bits of ``bits`` that do not fall into the contiguous low part [0, tile_bits - h)."""
-    if nbits <= tile_bits:
-        return []
-    h = 0
-    while True:
-        c = sum(1 for b in bits if b >= tile_bits - h)
-        if c == h:
-            break
-        h = c
-    return sorted(b for b in set(bits) if b >= tile_bits - h)
 
 
 def plan_expect_groups(flips: Sequence[int], nbits: int, tile_bits: int, max_hi: int = 5,
@@ -147,6 +135,40 @@ class DeviceState:
     def apply_blocks(self, blocks: Sequence[Block]) -> None:
         for b in blocks:
             self.apply_block(b)
+
+    # widest set of gathered high bits a staged pass may use (64 KiB tile: 7 low bits stay
+    # contiguous = 1 KiB rows for complex64)
+    pass_max_hi = int(os.environ.get("TCB200_PASS_MAX_HI", "6"))
+
+    def apply_planned(self, blocks: Sequence[Block]) -> int:
+        """Run ``blocks`` as staged multi-block passes (fusion.plan_passes): each pass is one HBM
+        read + write of the state however many blocks it holds.  Returns the number of passes."""
+        if not blocks:
+            return 0
+        T = lib.tcb200_pass_tile_bits(self.dt)
+        mat_elems = (12 * 1024) // self.amp_bytes
+        passes = plan_passes([b.bits for b in blocks], self.nbits, T, max_hi=self.pass_max_hi,
+                             max_ops=_lib.MAX_PASS_OPS, max_mat_elems=mat_elems, max_pass_k=_lib.MAX_PASS_K)
+        for p in passes:
+            blks = [blocks[i] for i in p.block_ids]
+            if len(blks) == 1:
+                self.apply_block(blks[0])
+            elif any(b.batched for b in blks):
+                self.apply_pass(blks, p.tile_hi)
+            else:
+                self.apply_pass_host(blks, p.tile_hi)
+        return len(passes)
+
+    def apply_pass_host(self, blocks: Sequence[Block], tile_hi: Sequence[int]) -> None:
+        """Several shared-matrix blocks in one staged pass, matrices in the constant bank."""
+        ks = np.asarray([len(b.bits) for b in blocks], dtype=np.int32)
+        bits = np.asarray([x for b in blocks for x in b.bits], dtype=np.int32)
+        mats = np.ascontiguousarray(np.concatenate([np.asarray(b.matrix, dtype=np.complex128).reshape(-1) for b in blocks]))
+        hi = np.asarray(list(tile_hi) if len(tile_hi) else [0], dtype=np.int32)
+        check(lib.tcb200_apply_pass_host(_ptr(self.buf), self.nbits, self.dt, len(blocks), _lib.iptr(ks), _lib.iptr(bits),
+                                         _lib.dptr(mats.view(np.float64)), len(tile_hi), _lib.iptr(hi), self.batch, _stream()))
+        STATS["apply_launches"] += 1
+        STATS["apply_bytes"] += 2 * self.amp_bytes * (self.batch << self.nbits)
 
     def apply_pass(self, blocks: Sequence[Block], tile_hi: Sequence[int]) -> None:
         """Several blocks inside one staged tile pass (one HBM read + write)."""

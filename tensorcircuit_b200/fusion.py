@@ -24,6 +24,9 @@ import numpy as np
 from .batching import BatchArray, is_batched
 
 
+MAX_BLOCK_K = 5  # TCB200_MAX_K: widest dense block the kernels apply
+
+
 @dataclass
 class GateOp:
     """One recorded gate: ``qubits`` in the caller's order, ``matrix`` [D, D] or batched."""
@@ -107,8 +110,14 @@ def plan_structure(gate_qubits: Sequence[Tuple[int, ...]], kmax: int) -> FusionP
     bq: List[set] = []
     last: Dict[int, int] = {}  # qubit -> index of the latest block touching it
     for gi, qs in enumerate(gate_qubits):
-        if len(qs) > kmax:
-            raise ValueError("gate on %d qubits exceeds the widest supported block (%d)" % (len(qs), kmax))
+        if len(qs) > MAX_BLOCK_K:
+            raise ValueError("gate on %d qubits exceeds the widest supported block (%d)" % (len(qs), MAX_BLOCK_K))
+        if len(qs) > kmax:  # wider than the fusion cap: a block of its own
+            groups.append([gi])
+            bq.append(set(qs))
+            for q in qs:
+                last[q] = len(groups) - 1
+            continue
         deps = [last[q] for q in qs if q in last]
         target = -1
         # the gate must run after block b = latest block touching its qubits; blocks after b
@@ -160,3 +169,118 @@ def fuse(ops: Sequence[GateOp], nqubits: int, kmax: int = 4) -> List[Block]:
 
 def clear_plan_cache() -> None:
     _PLAN_CACHE.clear()
+    _PASS_CACHE.clear()
+
+
+# ------------------------------------------------------------------------------------------------
+# pass planning: several fused blocks per HBM read + write
+# ------------------------------------------------------------------------------------------------
+def tile_hi_fixpoint(bits: Sequence[int], tile_bits: int, nbits: int) -> List[int]:
+    """Bits of ``bits`` that do not fall into the contiguous low part [0, tile_bits - h) of a
+    tile gathering h high bits (the geometry make_geom_hi builds on the device side)."""
+    if nbits <= tile_bits:
+        return []
+    h = 0
+    while True:
+        c = sum(1 for b in set(bits) if b >= tile_bits - h)
+        if c == h:
+            break
+        h = c
+    return sorted(b for b in set(bits) if b >= tile_bits - h)
+
+
+@dataclass
+class Pass:
+    """Blocks executed on one staged tile: one HBM read + write of the state."""
+
+    block_ids: List[int]
+    tile_hi: List[int]
+
+
+_PASS_CACHE: Dict[Any, List[Pass]] = {}
+
+
+def plan_passes(block_bits: Sequence[Tuple[int, ...]], nbits: int, tile_bits: int, max_hi: int = 6,
+                max_ops: int = 16, max_mat_elems: int = 1536, max_pass_k: int = 4) -> List[Pass]:
+    """Greedy list scheduling of fused blocks into tile passes.
+
+    A tile holds the ``tile_bits - h`` lowest index bits plus ``h <= max_hi`` gathered high bits;
+    a block can run in a pass when all its bits are in the tile.  Blocks are taken in dependency
+    order (a block is ready when every earlier block sharing a bit with it is done -- possibly
+    earlier in the same pass); among ready blocks the one that needs the fewest new gathered bits
+    goes first.  The plan depends only on the bit structure and is cached."""
+    max_hi = max(0, min(max_hi, tile_bits - 4))  # keep rows of >= 16 amplitudes contiguous
+    key = (tuple(block_bits), nbits, tile_bits, max_hi, max_ops, max_mat_elems, max_pass_k)
+    hit = _PASS_CACHE.get(key)
+    if hit is not None:
+        return hit
+    nb = len(block_bits)
+    preds: List[set] = [set() for _ in range(nb)]
+    succs: List[List[int]] = [[] for _ in range(nb)]
+    last: Dict[int, int] = {}
+    for i, bits in enumerate(block_bits):
+        for q in bits:
+            if q in last:
+                preds[i].add(last[q])
+            last[q] = i
+    for i in range(nb):
+        for p in preds[i]:
+            succs[p].append(i)
+    indeg = [len(p) for p in preds]
+    ready = [i for i in range(nb) if indeg[i] == 0]
+    passes: List[Pass] = []
+    remaining = nb
+    while remaining:
+        cur: List[int] = []
+        used: set = set()
+        cur_hi: List[int] = []
+        mat = 0
+        while len(cur) < max_ops:
+            best, best_score, best_hi = -1, None, None
+            for i in ready:
+                bits = block_bits[i]
+                k = len(bits)
+                if k > max_pass_k:
+                    if not cur:  # too wide for the staged pass: runs alone through the dense kernel
+                        best, best_hi, best_score = i, [], (0, i)
+                        break
+                    continue
+                if mat + (1 << (2 * k)) > max_mat_elems:
+                    continue
+                hi = tile_hi_fixpoint(list(used | set(bits)), tile_bits, nbits)
+                if len(hi) > max_hi:
+                    continue
+                score = (len(hi) - len(cur_hi), i)
+                if best_score is None or score < best_score:
+                    best, best_score, best_hi = i, score, hi
+                    if score[0] <= 0:
+                        break
+            if best < 0:
+                if cur or not ready:
+                    break
+                # nothing fits an empty tile (more high bits than it can gather): the block runs
+                # alone through the single-block kernel, which chooses its own geometry
+                best, best_hi = ready[0], []
+                standalone = True
+            else:
+                standalone = len(block_bits[best]) > max_pass_k
+            cur.append(best)
+            used |= set(block_bits[best])
+            cur_hi = best_hi
+            mat += 1 << (2 * len(block_bits[best]))
+            ready.remove(best)
+            remaining -= 1
+            for s in succs[best]:
+                indeg[s] -= 1
+                if indeg[s] == 0:
+                    ready.append(s)
+            ready.sort()
+            if standalone:
+                break
+        if not cur:
+            raise RuntimeError("pass planner made no progress")
+        passes.append(Pass(block_ids=cur, tile_hi=tile_hi_fixpoint(list(used), tile_bits, nbits)))
+    if len(_PASS_CACHE) > 64:
+        _PASS_CACHE.clear()
+    _PASS_CACHE[key] = passes
+    return passes

@@ -66,6 +66,34 @@ class FakeState:
         for b in blocks:
             self.apply_block(b)
 
+    pass_max_hi = 6
+
+    def apply_planned(self, blocks):
+        """Same planner as DeviceState.apply_planned; passes run through the emulated pass kernel."""
+        from tensorcircuit_b200.fusion import plan_passes
+
+        if not blocks:
+            return 0
+        T = self._lib.emu_pass_tile_bits(self.dt)
+        passes = plan_passes([b.bits for b in blocks], self.nbits, T, max_hi=self.pass_max_hi, max_ops=16,
+                             max_mat_elems=(12 * 1024) // self.amp_bytes, max_pass_k=4)
+        assert sorted(i for p in passes for i in p.block_ids) == list(range(len(blocks)))
+        for p in passes:
+            blks = [blocks[i] for i in p.block_ids]
+            if len(blks) == 1 or any(b.batched for b in blks):
+                for b in blks:
+                    self.apply_block(b)
+                continue
+            ks = [len(b.bits) for b in blks]
+            bits = [x for b in blks for x in b.bits]
+            mats = np.ascontiguousarray(np.concatenate([np.asarray(b.matrix, dtype=np.complex128).reshape(-1) for b in blks]))
+            for r in range(self.batch):
+                rc = self._lib.emu_apply_pass(self.np[r].ctypes.data_as(ctypes.c_void_p), self.nbits, self.dt, len(blks), _ip(ks), _ip(bits),
+                                              mats.view(np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(p.tile_hi), _ip(p.tile_hi if p.tile_hi else [0]))
+                assert rc == 0, self._lib.emu_last_error()
+            engine.STATS["apply_launches"] += 1
+        return len(passes)
+
     def norm2(self):
         return np.sum(np.abs(self.np.astype(np.complex128)) ** 2, axis=1)
 

@@ -585,3 +585,40 @@ def test_vmap_hea_energy(eng):
         np.testing.assert_allclose(got[b], want, atol=2e-5)
     # jit is the identity on this backend
     assert tc.backend.jit(energy) is energy
+
+
+# ---- pass planner --------------------------------------------------------------------------------
+@pytest.mark.parametrize("kf", [2, 3, 4])
+def test_planned_passes_small_tiles(eng, kf, monkeypatch):
+    """Multi-block staged passes with a tiny tile (many passes, gathered high bits) == oracle."""
+    from tensorcircuit_b200.fusion import fuse, plan_passes
+
+    monkeypatch.setenv("TCB200_PASS_TILE_BYTES_LOG2", "9")  # 64 complex64 amplitudes per tile
+    monkeypatch.setattr(tc.Circuit, "fusion_kmax", kf)
+    monkeypatch.setattr(tc.Circuit, "use_passes", True)
+    n = 11
+    ops = orc.random_circuit(n, 4, seed=7) + orc.hea_circuit(n, np.random.default_rng(3).uniform(0, 6, size=[1, 2, n]))
+    c = _run_gatelist(n, ops)
+    o = orc.run_gatelist(n, ops)
+    assert np.linalg.norm(A(c.state()) - o.state()) / np.linalg.norm(o.state()) < 2e-5
+    # plan properties: every block exactly once, dependency order respected, geometry limits
+    blocks = fuse(c._ops, n, kmax=kf)
+    passes = plan_passes([b.bits for b in blocks], n, 6, max_hi=3)
+    order = [i for p in passes for i in p.block_ids]
+    assert sorted(order) == list(range(len(blocks)))
+    pos = {b: i for i, b in enumerate(order)}
+    last = {}
+    for i, b in enumerate(blocks):
+        for q in b.bits:
+            if q in last:
+                assert pos[last[q]] < pos[i]
+            last[q] = i
+    for p in passes:
+        if len(p.block_ids) == 1:  # standalone blocks go through the single-block kernel
+            continue
+        assert len(p.tile_hi) <= 2 and len(p.block_ids) <= 16
+        lrow = 6 - len(p.tile_hi)
+        for i in p.block_ids:
+            if len(blocks[i].bits) <= 4:
+                assert all(q < lrow or q in p.tile_hi for q in blocks[i].bits)
+    assert len(passes) < len(blocks)

@@ -325,3 +325,25 @@ def test_config2_tfim_energy_n20():
     e = tc.templates.measurements.pauli_sum_expectation(c, [ps for _, ps in terms], [w for w, _ in terms])
     want = sum(w * o.expectation_ps(ps=ps).real for w, ps in terms)
     assert abs(e - want) / max(abs(want), 1e-3 * len(terms)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("kf", [2, 3])
+def test_apply_planned_vs_oracle(dtype, kf):
+    """Pass planner + constant-bank multi-block pass kernel on a 21-qubit circuit."""
+    from tensorcircuit_b200.fusion import fuse
+
+    n = 21
+    ops = orc.random_circuit(n, 4, seed=11)
+    tc.set_dtype(dtype)
+    c = tc.Circuit(n)
+    for name, q, p in ops:
+        getattr(c, name)(*q, **p)
+    blocks = fuse(c._ops, n, kmax=kf)
+    st = DeviceState(n, dtype)
+    st.init_zero()
+    npass = st.apply_planned(blocks)
+    assert npass < len(blocks)
+    o = orc.run_gatelist(n, ops)
+    assert _relerr(st.buf[0].cpu().numpy(), o.state()) < TOL[dtype]
+    tc.set_dtype("complex64")
