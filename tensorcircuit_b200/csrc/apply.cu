@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) dense_kernel(const __grid_constant__ Dens
     constexpr int D = 1 << K;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     C* tile = reinterpret_cast<C*>(smem_raw);
-    __shared__ uint64_t rowoff[32];
+    __shared__ uint64_t rowoff[256];
 
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(256) dense_kernel(const __grid_constant__ Dens
     cp_async_wait_all();
     __syncthreads();
 
+    // (the generic group loop is already at the HBM roofline for k <= 3 here: 40 registers,
+    // 4 CTAs / SM; the unrolled fast path of the pass kernels would cost occupancy)
     if (BATCHED) {
         apply_block_on_tile<C, K>(tile, p.gm, tid, nthr, p.tb,
                                   [&](int i, int j) { return bm[i * D + j]; });
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(256) pass_kernel(const __grid_constant__ PassP
     extern __shared__ __align__(128) unsigned char smem_raw[];
     C* tile = reinterpret_cast<C*>(smem_raw);
     C* bm = tile + (1u << p.g.T);
-    __shared__ uint64_t rowoff[32];
+    __shared__ uint64_t rowoff[256];
 
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
@@ -202,16 +204,16 @@ __global__ void __launch_bounds__(256) pass_kernel(const __grid_constant__ PassP
         const C* m = bm + op.moff;
         switch (op.k) {
             case 1:
-                apply_block_on_tile<C, 1>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return m[i * 2 + j]; });
+                apply_block_dispatch<C,1>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return m[i * 2 + j]; });
                 break;
             case 2:
-                apply_block_on_tile<C, 2>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return m[i * 4 + j]; });
+                apply_block_dispatch<C,2>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return m[i * 4 + j]; });
                 break;
             case 3:
-                apply_block_on_tile<C, 3>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return m[i * 8 + j]; });
+                apply_block_dispatch<C,3>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return m[i * 8 + j]; });
                 break;
             default:
-                apply_block_on_tile<C, 4>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return m[i * 16 + j]; });
+                apply_block_dispatch<C,4>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return m[i * 16 + j]; });
                 break;
         }
         __syncthreads();
@@ -286,6 +288,7 @@ struct CPassParams {
     TileGeom g;
     int tb;
     int nops;
+    int mat_total;  // complex elements used in m[]
     PassOp op[TCB200_MAX_PASS_OPS];
     typename CT<Real>::type m[CPASS_MAT_BYTES / sizeof(typename CT<Real>::type)];
 };
@@ -295,13 +298,19 @@ __global__ void __launch_bounds__(256) cpass_kernel(const __grid_constant__ CPas
     using C = typename CT<Real>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     C* tile = reinterpret_cast<C*>(smem_raw);
-    __shared__ uint64_t rowoff[32];
+    __shared__ uint64_t rowoff[256];
 
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
     if (tid < (1 << p.g.h)) rowoff[tid] = row_offset(p.g, tid);
     C* vec = p.state + ((uint64_t)blockIdx.y << p.g.n);
     const uint64_t base = tile_base(p.g, blockIdx.x);
+    // The constant bank is only the transport of the matrices: an index that depends on the
+    // op counter would make every FMA operand a register-indexed LDC.  Copy them once per CTA
+    // behind the tile; 1- and 2-bit blocks then keep their matrix in registers for all the
+    // groups of a thread, wider blocks read it with broadcast LDS.
+    C* bm = tile + (1u << p.g.T);
+    for (int i = tid; i < p.mat_total; i += nthr) bm[i] = p.m[i];
     __syncthreads();
     stage_in<C, true>(p.g, vec, base, tile, rowoff, tid, nthr);
     cp_async_wait_all();
@@ -309,19 +318,27 @@ __global__ void __launch_bounds__(256) cpass_kernel(const __grid_constant__ CPas
 
     for (int o = 0; o < p.nops; ++o) {
         const PassOp& op = p.op[o];
-        const int mo = op.moff;
+        const C* m = bm + op.moff;
         switch (op.k) {
-            case 1:
-                apply_block_on_tile<C, 1>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return p.m[mo + i * 2 + j]; });
+            case 1: {
+                C r[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r[i] = m[i];
+                apply_block_dispatch<C,1>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return r[i * 2 + j]; });
                 break;
-            case 2:
-                apply_block_on_tile<C, 2>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return p.m[mo + i * 4 + j]; });
+            }
+            case 2: {
+                C r[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = m[i];
+                apply_block_dispatch<C,2>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return r[i * 4 + j]; });
                 break;
+            }
             case 3:
-                apply_block_on_tile<C, 3>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return p.m[mo + i * 8 + j]; });
+                apply_block_dispatch<C,3>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return m[i * 8 + j]; });
                 break;
             default:
-                apply_block_on_tile<C, 4>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return p.m[mo + i * 16 + j]; });
+                apply_block_dispatch<C,4>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return m[i * 16 + j]; });
                 break;
         }
         __syncthreads();
@@ -368,11 +385,12 @@ static int launch_cpass(void* state, int nbits, int nops, const int* ops_k, cons
         b += k;
         if (k < kmin) kmin = k;
     }
+    q.mat_total = moff;
     q.tb = pick_threads(q.g.T, kmin, APU);
     const uint64_t ntiles = 1ull << (nbits - q.g.T);
     if (ntiles > 0x7fffffffull) return fail(TCB200_ERR_UNSUPPORTED, "state too large for one grid");
     if (batch < 1 || batch > 65535) return fail(TCB200_ERR_ARG, "batch=%lld out of range", (long long)batch);
-    size_t smem = ((size_t)sizeof(C) << q.g.T);
+    size_t smem = ((size_t)sizeof(C) << q.g.T) + sizeof(C) * (size_t)moff;
     if (smem < 16) smem = 16;
     static bool attr = false;
     if (!attr) {

@@ -283,6 +283,59 @@ TCB_HD void apply_block_on_tile(C* tile, const GroupMap& gm, int tid, int nthr, 
     }
 }
 
+// Fast path: 256 threads and exactly 2^NITLOG groups per thread (ngb == 8 + NITLOG).  The
+// thread's part of the group index is folded once; the per-iteration part walks a Gray code, so
+// each further group costs one XOR; everything is unrolled with compile-time table indices.
+template <typename C, int K, int NITLOG, bool VEC0, typename Mat>
+TCB_HD void apply_block_fast_v(C* tile, const GroupMap& gm, int tid, const Mat& mat) {
+    uint32_t b = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b ^= (0u - (((uint32_t)tid >> i) & 1u)) & gm.ntval[i];
+    uint32_t hv[NITLOG > 0 ? NITLOG : 1];
+#pragma unroll
+    for (int i = 0; i < NITLOG; ++i) hv[i] = gm.ntval[8 + i];
+    uint32_t tv[1 << K];
+#pragma unroll
+    for (int j = 0; j < (1 << K); ++j) tv[j] = gm.tval[j];
+#pragma unroll
+    for (int it = 0; it < (1 << NITLOG); ++it) {
+        if (it > 0) {
+            int z = 0;
+#pragma unroll
+            for (int q = 0; q < NITLOG; ++q)
+                if (((it >> q) & 1) && ((it & ((1 << q) - 1)) == 0)) z = q;  // count trailing zeros
+            b ^= hv[z];
+        }
+        apply_group<C, K>(tile, b, tv, VEC0, mat);
+    }
+}
+
+template <typename C, int K, int NITLOG, typename Mat>
+TCB_HD void apply_block_fast(C* tile, const GroupMap& gm, int tid, const Mat& mat) {
+    if (sizeof(C) == 8 && gm.vec0)
+        apply_block_fast_v<C, K, NITLOG, true>(tile, gm, tid, mat);
+    else
+        apply_block_fast_v<C, K, NITLOG, false>(tile, gm, tid, mat);
+}
+
+// Picks the fast path when the launch shape allows it (the production tiles: 2^12 / 2^13
+// amplitudes, 256 threads), the generic loop otherwise (small states, test tile sizes).
+template <typename C, int K, typename Mat>
+TCB_HD void apply_block_dispatch(C* tile, const GroupMap& gm, int tid, int nthr, int tb, const Mat& mat) {
+    if (nthr == 256) {
+        const int nl = gm.ngb - 8;
+        if (nl == 12 - K - 8 && 12 - K - 8 >= 0) {
+            apply_block_fast<C, K, (12 - K - 8 >= 0 ? 12 - K - 8 : 0)>(tile, gm, tid, mat);
+            return;
+        }
+        if (nl == 13 - K - 8) {
+            apply_block_fast<C, K, 13 - K - 8>(tile, gm, tid, mat);
+            return;
+        }
+    }
+    apply_block_on_tile<C, K>(tile, gm, tid, nthr, tb, mat);
+}
+
 // ---- host helpers (plan.cpp part of abi.cu) ------------------------------------------------
 // Choose the tile for a set of ascending target bits: gathers exactly the targets that do not
 // fall into the contiguous low part.  Returns <0 on error.

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) expect_kernel(const __grid_constant__ Exp
     constexpr int MT = TCB200_MAX_TERMS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     C* tile = reinterpret_cast<C*>(smem_raw);
-    __shared__ uint64_t rowoff[32];
+    __shared__ uint64_t rowoff[256];
     __shared__ double red[8][MT][2];
 
     const int tid = threadIdx.x;

@@ -36,7 +36,7 @@ int emu_dense_t(void* state, int nbits, const int* bits, const double* mat) {
     }
     const size_t tile_elems = (size_t)1 << g.T;
     C* tile = static_cast<C*>(aligned_alloc(128, tile_elems * sizeof(C) < 128 ? 128 : tile_elems * sizeof(C)));
-    uint64_t rowoff[32];
+    uint64_t rowoff[256];
     for (int r = 0; r < (1 << g.h); ++r) rowoff[r] = row_offset(g, r);
     C* vec = static_cast<C*>(state);
     const uint64_t ntiles = 1ull << (nbits - g.T);
@@ -44,7 +44,7 @@ int emu_dense_t(void* state, int nbits, const int* bits, const double* mat) {
         const uint64_t base = tile_base(g, t);
         for (int tid = 0; tid < nthr; ++tid) stage_in<C, true>(g, vec, base, tile, rowoff, tid, nthr);
         for (int tid = 0; tid < nthr; ++tid)
-            apply_block_on_tile<C, K>(tile, gm, tid, nthr, tb, [&](int i, int j) { return m[i * D + j]; });
+            apply_block_dispatch<C,K>(tile, gm, tid, nthr, tb, [&](int i, int j) { return m[i * D + j]; });
         for (int tid = 0; tid < nthr; ++tid) stage_out<C, true>(g, vec, base, tile, rowoff, tid, nthr);
     }
     free(tile);
@@ -95,7 +95,7 @@ int emu_pass_t(void* state, int nbits, int nops, const int* ops_k, const int* op
     const int nthr = 1 << tb;
     const size_t tile_elems = (size_t)1 << g.T;
     C* tile = static_cast<C*>(aligned_alloc(128, tile_elems * sizeof(C) < 128 ? 128 : tile_elems * sizeof(C)));
-    uint64_t rowoff[32];
+    uint64_t rowoff[256];
     for (int r = 0; r < (1 << g.h); ++r) rowoff[r] = row_offset(g, r);
     C* vec = static_cast<C*>(state);
     const uint64_t ntiles = 1ull << (nbits - g.T);
@@ -106,10 +106,10 @@ int emu_pass_t(void* state, int nbits, int nops, const int* ops_k, const int* op
             const C* m = ms[o].data();
             for (int tid = 0; tid < nthr; ++tid) {
                 switch (ops_k[o]) {
-                    case 1: apply_block_on_tile<C, 1>(tile, gms[o], tid, nthr, tb, [&](int i, int j) { return m[i * 2 + j]; }); break;
-                    case 2: apply_block_on_tile<C, 2>(tile, gms[o], tid, nthr, tb, [&](int i, int j) { return m[i * 4 + j]; }); break;
-                    case 3: apply_block_on_tile<C, 3>(tile, gms[o], tid, nthr, tb, [&](int i, int j) { return m[i * 8 + j]; }); break;
-                    default: apply_block_on_tile<C, 4>(tile, gms[o], tid, nthr, tb, [&](int i, int j) { return m[i * 16 + j]; }); break;
+                    case 1: apply_block_dispatch<C,1>(tile, gms[o], tid, nthr, tb, [&](int i, int j) { return m[i * 2 + j]; }); break;
+                    case 2: apply_block_dispatch<C,2>(tile, gms[o], tid, nthr, tb, [&](int i, int j) { return m[i * 4 + j]; }); break;
+                    case 3: apply_block_dispatch<C,3>(tile, gms[o], tid, nthr, tb, [&](int i, int j) { return m[i * 8 + j]; }); break;
+                    default: apply_block_dispatch<C,4>(tile, gms[o], tid, nthr, tb, [&](int i, int j) { return m[i * 16 + j]; }); break;
                 }
             }
         }
@@ -129,7 +129,7 @@ int emu_expect_t(const void* state, int nbits, int nterms, const uint64_t* flip,
     if (rc) return rc;
     const size_t tile_elems = (size_t)1 << g.T;
     C* tile = static_cast<C*>(aligned_alloc(128, tile_elems * sizeof(C) < 128 ? 128 : tile_elems * sizeof(C)));
-    uint64_t rowoff[32];
+    uint64_t rowoff[256];
     for (int r = 0; r < (1 << g.h); ++r) rowoff[r] = row_offset(g, r);
     const C* vec = static_cast<const C*>(state);
     const uint64_t ntiles = 1ull << (nbits - g.T);

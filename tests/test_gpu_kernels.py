@@ -347,3 +347,59 @@ def test_apply_planned_vs_oracle(dtype, kf):
     o = orc.run_gatelist(n, ops)
     assert _relerr(st.buf[0].cpu().numpy(), o.state()) < TOL[dtype]
     tc.set_dtype("complex64")
+
+
+def test_config2_full_size_n28():
+    """Config 2 at BASELINE's size (n = 28, 56 TFIM strings): complex64 against the engine's own
+    complex128 run (the oracle cannot hold 2^28 here), plus norm and Hermiticity properties."""
+    from tensorcircuit_b200 import recipes
+
+    n = 28
+    params = np.random.default_rng(1).uniform(0, 2 * np.pi, [8, n])
+    ops = recipes.tfim_vqe_circuit(n, params)
+    terms = recipes.tfim_terms(n)
+    pss = [ps for _, ps in terms]
+    vals = {}
+    for dtype in ("complex64", "complex128"):
+        tc.set_dtype(dtype)
+        c = recipes.build(tc.Circuit(n), ops)
+        v = np.asarray(c.expectation_ps_many(pss))
+        assert abs(c._ensure_state().norm2()[0] - 1.0) < (1e-5 if dtype == "complex64" else 1e-11)
+        assert np.max(np.abs(v.imag)) < (1e-5 if dtype == "complex64" else 1e-11)
+        vals[dtype] = v.real
+        del c
+    tc.set_dtype("complex64")
+    e64 = sum(w * v for (w, _), v in zip(terms, vals["complex64"]))
+    e128 = sum(w * v for (w, _), v in zip(terms, vals["complex128"]))
+    assert np.max(np.abs(vals["complex64"] - vals["complex128"])) < 1e-5
+    assert abs(e64 - e128) / max(abs(e128), 1e-3 * len(terms)) < 1e-5
+
+
+def test_config3_full_size_vmap_1024x20():
+    """Config 3 at BASELINE's size: vmap over 1024 parameter sets of a 20-qubit HEA (8 GiB batched
+    state), TFIM energy; a 12-element subsample is checked against the oracle."""
+    from tensorcircuit_b200 import recipes
+
+    n, B, depth = 20, 1024, 4
+    params = np.random.default_rng(2).uniform(0, 2 * np.pi, size=[B, depth, 2, n])
+    terms = recipes.tfim_terms(n)
+    pss = [ps for _, ps in terms]
+    ws = [w for w, _ in terms]
+
+    def energy(p):
+        c = tc.Circuit(n)
+        for l in range(depth):
+            for i in range(n):
+                c.rx(i, theta=p[l, 0, i])
+            for i in range(n - 1):
+                c.rzz(i, i + 1, theta=p[l, 1, i])
+            for i in range(n - 1):
+                c.cnot(i, i + 1)
+        return tc.templates.measurements.pauli_sum_expectation(c, pss, ws)
+
+    got = tc.backend.vmap(energy)(params)
+    assert got.shape == (B,)
+    for b in np.random.default_rng(0).choice(B, size=12, replace=False):
+        o = orc.run_gatelist(n, orc.hea_circuit(n, params[b]))
+        want = sum(w * o.expectation_ps(ps=ps).real for w, ps in terms)
+        assert abs(got[b] - want) / max(abs(want), 1e-3 * len(terms)) < 1e-5, b
