@@ -139,8 +139,26 @@ int tcb200_apply_pass_host(void* state, int nbits, int dtype, int nops, const in
                            const int* ops_bits, const double* ops_mats, int n_hi,
                            const int* tile_hi, int64_t batch, void* stream);
 
+/*
+ * Register-tile pass: the staged pass above, with one more level of blocking.  Each of the
+ * `nrt` (<= TCB200_MAX_PASS_OPS) register tiles is a set of <= 4 bits inside the shared-memory
+ * tile; a thread loads the 2^kt amplitudes of a group once, applies the tile's `rt_nsub` gates
+ * (1 or 2 bits each, all bits inside the register tile) back to back in registers, and stores
+ * the group once -- one shared-memory round trip per register tile instead of one per gate.
+ *
+ *   rt_k[nrt], rt_bits[sum rt_k]   HOST: bits of each register tile, ascending
+ *   rt_nsub[nrt]                    HOST: gates per register tile, applied in order
+ *   sub_k[], sub_bits[sum sub_k]    HOST: per gate, its ascending bits (subset of its tile)
+ *   sub_mats                        HOST complex128, concatenated 4^k entries per gate
+ *                                   (at most 12 KiB in the state's dtype, 96 gates per pass)
+ */
+int tcb200_apply_rpass_host(void* state, int nbits, int dtype, int nrt, const int* rt_k,
+                            const int* rt_bits, const int* rt_nsub, const int* sub_k,
+                            const int* sub_bits, const double* sub_mats, int n_hi,
+                            const int* tile_hi, int64_t batch, void* stream);
+
 /* Geometry the pass planner needs: log2 of the tile size (amplitudes) used by
- * tcb200_apply_pass / tcb200_apply_pass_host for `dtype`. */
+ * tcb200_apply_pass / tcb200_apply_pass_host / tcb200_apply_rpass_host for `dtype`. */
 int tcb200_pass_tile_bits(int dtype);
 
 /*

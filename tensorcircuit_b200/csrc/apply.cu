@@ -15,6 +15,7 @@
 //
 // CUDA cores only: the path is HBM-bound (16 B of traffic per complex64 amplitude against
 // 8*2^K flop), see DESIGN.md.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -405,6 +406,182 @@ static int launch_cpass(void* state, int nbits, int nops, const int* ops_k, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// register-tile pass: per shared-memory round trip a *sequence* of 1-/2-bit gates inside a
+// <= 4-bit register tile (common.cuh: rtile_run)
+// ------------------------------------------------------------------------------------------------
+constexpr int RPASS_MAX_SUB = 96;
+
+template <typename Real>
+struct RPassParams {
+    typename CT<Real>::type* state;
+    TileGeom g;
+    int tb;
+    int nrt;
+    int mat_total;
+    RTile rt[TCB200_MAX_PASS_OPS];
+    RSub sub[RPASS_MAX_SUB];
+    typename CT<Real>::type m[CPASS_MAT_BYTES / sizeof(typename CT<Real>::type)];
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(256) rpass_kernel(const __grid_constant__ RPassParams<Real> p) {
+    using C = typename CT<Real>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    C* tile = reinterpret_cast<C*>(smem_raw);
+    __shared__ uint64_t rowoff[256];
+    __shared__ RSub subs[RPASS_MAX_SUB];
+
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    if (tid < (1 << p.g.h)) rowoff[tid] = row_offset(p.g, tid);
+    C* vec = p.state + ((uint64_t)blockIdx.y << p.g.n);
+    const uint64_t base = tile_base(p.g, blockIdx.x);
+    C* bm = tile + (1u << p.g.T);
+    for (int i = tid; i < p.mat_total; i += nthr) bm[i] = p.m[i];
+    for (int i = tid; i < RPASS_MAX_SUB; i += nthr) subs[i] = p.sub[i];
+    __syncthreads();
+    stage_in<C, true>(p.g, vec, base, tile, rowoff, tid, nthr);
+    cp_async_wait_all();
+    __syncthreads();
+    for (int o = 0; o < p.nrt; ++o) {
+        rtile_run<C>(tile, p.rt[o], subs, bm, tid, nthr, p.tb);
+        __syncthreads();
+    }
+    stage_out<C, true>(p.g, vec, base, tile, rowoff, tid, nthr);
+}
+
+// host side: the parameter block of one register-tile pass
+template <typename Real>
+static int fill_rpass(RPassParams<Real>& q, void* state, int nbits, int nrt, const int* rt_k, const int* rt_bits,
+                      const int* rt_nsub, const int* sub_k, const int* sub_bits, const double* sub_mats, int n_hi,
+                      const int* tile_hi) {
+    using C = typename CT<Real>::type;
+    constexpr int APU = CT<Real>::APU;
+    constexpr int MAXM = CPASS_MAT_BYTES / (int)sizeof(C);
+    q.state = static_cast<C*>(state);
+    const int tile_bits = pass_tile_bits(sizeof(Real) == 4 ? TCB200_C64 : TCB200_C128);
+    int rc = make_geom_hi(nbits, tile_bits, nbits <= tile_bits ? 0 : n_hi, tile_hi, &q.g);
+    if (rc) return rc;
+    q.nrt = nrt;
+    int moff = 0, nsub_tot = 0, kmin = 99;
+    const int* rb = rt_bits;
+    const int* sb = sub_bits;
+    const double* mp = sub_mats;
+    const int* sk = sub_k;
+    for (int o = 0; o < nrt; ++o) {
+        const int kt = rt_k[o];
+        if (kt < 1 || kt > 4) return fail(TCB200_ERR_UNSUPPORTED, "register tile of %d bits (max 4)", kt);
+        for (int i = 0; i < kt; ++i)
+            if (rb[i] < 0 || rb[i] >= nbits) return fail(TCB200_ERR_ARG, "bit %d out of range", rb[i]);
+        q.rt[o].kt = kt;
+        q.rt[o].nsub = rt_nsub[o];
+        q.rt[o].sub0 = nsub_tot;
+        rc = make_group_map(q.g, APU, kt, rb, &q.rt[o].gm);
+        if (rc) return rc;
+        for (int s = 0; s < rt_nsub[o]; ++s) {
+            if (nsub_tot >= RPASS_MAX_SUB) return fail(TCB200_ERR_UNSUPPORTED, "more than %d gates in one pass", RPASS_MAX_SUB);
+            const int k = *sk++;
+            if (k != 1 && k != 2) return fail(TCB200_ERR_UNSUPPORTED, "gate of %d bits inside a register tile", k);
+            int pos[2] = {0, 0};
+            for (int i = 0; i < k; ++i) {
+                int f = -1;
+                for (int j = 0; j < kt; ++j)
+                    if (rb[j] == sb[i]) f = j;
+                if (f < 0) return fail(TCB200_ERR_ARG, "gate bit %d is not in its register tile", sb[i]);
+                pos[i] = f;
+            }
+            if (k == 2 && pos[1] <= pos[0]) return fail(TCB200_ERR_ARG, "gate bits must be ascending");
+            const int sz = 1 << (2 * k);
+            if (moff + sz > MAXM) return fail(TCB200_ERR_UNSUPPORTED, "pass matrices exceed %d bytes", CPASS_MAT_BYTES);
+            RSub& r = q.sub[nsub_tot++];
+            r.k = k;
+            r.p0 = pos[0];
+            r.p1 = pos[1];
+            r.moff = moff;
+            for (int i = 0; i < sz; ++i) {
+                q.m[moff + i].x = (Real)mp[2 * i];
+                q.m[moff + i].y = (Real)mp[2 * i + 1];
+            }
+            moff += sz;
+            mp += 2 * sz;
+            sb += k;
+        }
+        rb += kt;
+        if (kt < kmin) kmin = kt;
+    }
+    q.mat_total = moff;
+    q.tb = pick_threads(q.g.T, kmin, APU);
+    return 0;
+}
+
+template <typename Real>
+static int launch_rpass(void* state, int nbits, int nrt, const int* rt_k, const int* rt_bits, const int* rt_nsub,
+                        const int* sub_k, const int* sub_bits, const double* sub_mats, int n_hi, const int* tile_hi,
+                        int64_t batch, cudaStream_t st) {
+    using C = typename CT<Real>::type;
+    static thread_local RPassParams<Real>* tp = nullptr;
+    if (!tp) tp = new RPassParams<Real>();
+    RPassParams<Real>& q = *tp;
+    int rc = fill_rpass<Real>(q, state, nbits, nrt, rt_k, rt_bits, rt_nsub, sub_k, sub_bits, sub_mats, n_hi, tile_hi);
+    if (rc) return rc;
+    const uint64_t ntiles = 1ull << (nbits - q.g.T);
+    if (ntiles > 0x7fffffffull) return fail(TCB200_ERR_UNSUPPORTED, "state too large for one grid");
+    if (batch < 1 || batch > 65535) return fail(TCB200_ERR_ARG, "batch=%lld out of range", (long long)batch);
+    size_t smem = ((size_t)sizeof(C) << q.g.T) + sizeof(C) * (size_t)q.mat_total;
+    if (smem < 16) smem = 16;
+    static bool attr = false;
+    if (!attr) {
+        TCB_CUDA(cudaFuncSetAttribute(rpass_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    dim3 grid((unsigned)ntiles, (unsigned)batch);
+    dim3 block(1u << q.tb);
+    rpass_kernel<Real><<<grid, block, smem, st>>>(q);
+    TCB_LAUNCH_CHECK("rpass_kernel");
+    return 0;
+}
+
+#ifdef TCB200_EMU
+// tests/emu only (never compiled into the product library): run the register-tile pass on the
+// CPU with the same parameter block and the same __host__ __device__ bodies as rpass_kernel.
+template <typename Real>
+static int emu_rpass(void* state, int nbits, int nrt, const int* rt_k, const int* rt_bits, const int* rt_nsub,
+                     const int* sub_k, const int* sub_bits, const double* sub_mats, int n_hi, const int* tile_hi) {
+    using C = typename CT<Real>::type;
+    RPassParams<Real>* q = new RPassParams<Real>();
+    int rc = fill_rpass<Real>(*q, state, nbits, nrt, rt_k, rt_bits, rt_nsub, sub_k, sub_bits, sub_mats, n_hi, tile_hi);
+    if (rc) { delete q; return rc; }
+    const int nthr = 1 << q->tb;
+    const size_t elems = ((size_t)1 << q->g.T) + q->mat_total + 16;
+    C* tile = static_cast<C*>(aligned_alloc(128, ((elems * sizeof(C) + 127) / 128) * 128));
+    C* bm = tile + ((size_t)1 << q->g.T);
+    for (int i = 0; i < q->mat_total; ++i) bm[i] = q->m[i];
+    uint64_t rowoff[256];
+    for (int r = 0; r < (1 << q->g.h); ++r) rowoff[r] = row_offset(q->g, r);
+    C* vec = static_cast<C*>(state);
+    const uint64_t ntiles = 1ull << (nbits - q->g.T);
+    for (uint64_t t = 0; t < ntiles; ++t) {
+        const uint64_t base = tile_base(q->g, t);
+        for (int tid = 0; tid < nthr; ++tid) stage_in<C, true>(q->g, vec, base, tile, rowoff, tid, nthr);
+        for (int o = 0; o < q->nrt; ++o)
+            for (int tid = 0; tid < nthr; ++tid) rtile_run<C>(tile, q->rt[o], q->sub, bm, tid, nthr, q->tb);
+        for (int tid = 0; tid < nthr; ++tid) stage_out<C, true>(q->g, vec, base, tile, rowoff, tid, nthr);
+    }
+    free(tile);
+    delete q;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int emu_apply_rpass(void* state, int nbits, int dtype, int nrt, const int* rt_k,
+                                                                       const int* rt_bits, const int* rt_nsub, const int* sub_k,
+                                                                       const int* sub_bits, const double* sub_mats, int n_hi,
+                                                                       const int* tile_hi) {
+    if (dtype == TCB200_C64) return emu_rpass<float>(state, nbits, nrt, rt_k, rt_bits, rt_nsub, sub_k, sub_bits, sub_mats, n_hi, tile_hi);
+    return emu_rpass<double>(state, nbits, nrt, rt_k, rt_bits, rt_nsub, sub_k, sub_bits, sub_mats, n_hi, tile_hi);
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
 // diagonal block
 // ------------------------------------------------------------------------------------------------
 struct DiagParams {
@@ -497,6 +674,20 @@ int tcb200_apply_pass_host(void* state, int nbits, int dtype, int nops, const in
     if (dtype == TCB200_C64)
         return launch_cpass<float>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, batch, st);
     return launch_cpass<double>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, batch, st);
+}
+
+int tcb200_apply_rpass_host(void* state, int nbits, int dtype, int nrt, const int* rt_k,
+                            const int* rt_bits, const int* rt_nsub, const int* sub_k,
+                            const int* sub_bits, const double* sub_mats, int n_hi,
+                            const int* tile_hi, int64_t batch, void* stream) {
+    if (!state || !rt_k || !rt_bits || !rt_nsub || !sub_k || !sub_bits || !sub_mats) return fail(TCB200_ERR_ARG, "NULL argument");
+    if (dtype != TCB200_C64 && dtype != TCB200_C128) return fail(TCB200_ERR_ARG, "bad dtype %d", dtype);
+    if (nrt < 1 || nrt > TCB200_MAX_PASS_OPS) return fail(TCB200_ERR_ARG, "nrt=%d out of range", nrt);
+    if (nbits < 1 || nbits > 40) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == TCB200_C64)
+        return launch_rpass<float>(state, nbits, nrt, rt_k, rt_bits, rt_nsub, sub_k, sub_bits, sub_mats, n_hi, tile_hi, batch, st);
+    return launch_rpass<double>(state, nbits, nrt, rt_k, rt_bits, rt_nsub, sub_k, sub_bits, sub_mats, n_hi, tile_hi, batch, st);
 }
 
 int tcb200_apply_diag(void* state, int nbits, int dtype, int k, const int* bits,

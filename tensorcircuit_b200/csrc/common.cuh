@@ -336,6 +336,176 @@ TCB_HD void apply_block_dispatch(C* tile, const GroupMap& gm, int tid, int nthr,
     apply_block_on_tile<C, K>(tile, gm, tid, nthr, tb, mat);
 }
 
+// ---- register tiles: several small gates per shared-memory round trip -----------------------
+// A register tile is a set of KT <= 4 tile-local bits.  A thread loads the 2^KT amplitudes of a
+// group once, applies a *sequence* of 1- and 2-bit gates that live inside those bits entirely
+// in registers, and stores the group once.  Compared with one shared-memory round trip per
+// gate this divides the LDS/STS traffic and the addressing overhead by the number of gates in
+// the tile, which is what a staged pass is bound by once the FP32 pipe is busy.
+struct RSub {
+    int k;     // 1 or 2
+    int p0;    // position (0..KT-1) of matrix index bit 0 inside the register tile
+    int p1;    // position of matrix index bit 1 (k == 2), p1 > p0
+    int moff;  // offset of the 2^k x 2^k matrix in the pass blob (complex elements, even)
+};
+
+struct RTile {
+    int kt;    // register-tile bits (1..4)
+    int nsub;  // gates applied inside the tile
+    int sub0;  // index of the first RSub
+    GroupMap gm;
+};
+
+// one 2-bit gate on positions (P0, P1) of the 2^KT register array
+template <typename C, int KT, int P0, int P1>
+TCB_HD void rsub2(C* v, const C* m) {
+    C mr[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mr[i] = m[i];
+#pragma unroll
+    for (int r = 0; r < (1 << (KT - 2)); ++r) {
+        // spread r over the positions other than P0, P1
+        int base = 0, rb = 0;
+#pragma unroll
+        for (int b = 0; b < KT; ++b)
+            if (b != P0 && b != P1) {
+                base |= ((r >> rb) & 1) << b;
+                ++rb;
+            }
+        const int i0 = base, i1 = base | (1 << P0), i2 = base | (1 << P1), i3 = base | (1 << P0) | (1 << P1);
+        const C a0 = v[i0], a1 = v[i1], a2 = v[i2], a3 = v[i3];
+        C o;
+        o = cmul(mr[0], a0); cfma(o, mr[1], a1); cfma(o, mr[2], a2); cfma(o, mr[3], a3); v[i0] = o;
+        o = cmul(mr[4], a0); cfma(o, mr[5], a1); cfma(o, mr[6], a2); cfma(o, mr[7], a3); v[i1] = o;
+        o = cmul(mr[8], a0); cfma(o, mr[9], a1); cfma(o, mr[10], a2); cfma(o, mr[11], a3); v[i2] = o;
+        o = cmul(mr[12], a0); cfma(o, mr[13], a1); cfma(o, mr[14], a2); cfma(o, mr[15], a3); v[i3] = o;
+    }
+}
+
+// one 1-bit gate on position P0
+template <typename C, int KT, int P0>
+TCB_HD void rsub1(C* v, const C* m) {
+    const C m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
+#pragma unroll
+    for (int r = 0; r < (1 << (KT - 1)); ++r) {
+        const int lo = r & ((1 << P0) - 1);
+        const int i0 = ((r >> P0) << (P0 + 1)) | lo, i1 = i0 | (1 << P0);
+        const C a0 = v[i0], a1 = v[i1];
+        C o;
+        o = cmul(m0, a0); cfma(o, m1, a1); v[i0] = o;
+        o = cmul(m2, a0); cfma(o, m3, a1); v[i1] = o;
+    }
+}
+
+template <typename C, int KT>
+TCB_HD void rsub_dispatch(C* v, const RSub& s, const C* bm) {
+    const C* m = bm + s.moff;
+    if (s.k == 1) {
+        switch (s.p0) {
+            case 0: rsub1<C, KT, 0>(v, m); break;
+            case 1: if constexpr (KT > 1) rsub1<C, KT, 1>(v, m); break;
+            case 2: if constexpr (KT > 2) rsub1<C, KT, 2>(v, m); break;
+            default: if constexpr (KT > 3) rsub1<C, KT, 3>(v, m); break;
+        }
+        return;
+    }
+    switch (s.p0 * 4 + s.p1) {
+        case 1: if constexpr (KT > 1) rsub2<C, KT, 0, 1>(v, m); break;
+        case 2: if constexpr (KT > 2) rsub2<C, KT, 0, 2>(v, m); break;
+        case 3: if constexpr (KT > 3) rsub2<C, KT, 0, 3>(v, m); break;
+        case 6: if constexpr (KT > 2) rsub2<C, KT, 1, 2>(v, m); break;
+        case 7: if constexpr (KT > 3) rsub2<C, KT, 1, 3>(v, m); break;
+        default: if constexpr (KT > 3) rsub2<C, KT, 2, 3>(v, m); break;  // 11
+    }
+}
+
+// load one group, run the tile's gates in registers, store the group
+template <typename C, int KT, bool VEC0>
+TCB_HD void rtile_group(C* tile, uint32_t base, const uint32_t* tv, const RTile& rt, const RSub* subs, const C* bm) {
+    constexpr int D = 1 << KT;
+    C v[D];
+    if (VEC0) {
+#pragma unroll
+        for (int j = 0; j < D; j += 2) {
+            const Unit16 q = *reinterpret_cast<const Unit16*>(tile + (base ^ tv[j]));
+            const C* qc = reinterpret_cast<const C*>(&q);
+            v[j] = qc[0];
+            v[(j + 1) % D] = qc[1 % (16 / (int)sizeof(C))];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < D; ++j) v[j] = tile[base ^ tv[j]];
+    }
+    for (int s = 0; s < rt.nsub; ++s) rsub_dispatch<C, KT>(v, subs[rt.sub0 + s], bm);
+    if (VEC0) {
+#pragma unroll
+        for (int j = 0; j < D; j += 2) {
+            Unit16 q;
+            C* qc = reinterpret_cast<C*>(&q);
+            qc[0] = v[j];
+            qc[1 % (16 / (int)sizeof(C))] = v[(j + 1) % D];
+            *reinterpret_cast<Unit16*>(tile + (base ^ tv[j])) = q;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < D; ++j) tile[base ^ tv[j]] = v[j];
+    }
+}
+
+template <typename C, int KT, bool VEC0>
+TCB_HD void rtile_run_v(C* tile, const RTile& rt, const RSub* subs, const C* bm, int tid, int nthr, int tb) {
+    const GroupMap& gm = rt.gm;
+    const uint32_t ngroups = 1u << gm.ngb;
+    if ((uint32_t)tid >= ngroups) return;
+    uint32_t tv[1 << KT];
+#pragma unroll
+    for (int j = 0; j < (1 << KT); ++j) tv[j] = gm.tval[j];
+    uint32_t b = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b ^= (0u - (((uint32_t)tid >> i) & 1u)) & gm.ntval[i];
+    if (nthr == 256) {
+        // remaining group bits in Gray-code order: one XOR per further group
+        const uint32_t nit = ngroups >> 8;
+        for (uint32_t it = 0; it < (nit ? nit : 1u); ++it) {
+            if (it > 0) {
+                int z = 0;
+                while (!((it >> z) & 1u)) ++z;
+                b ^= gm.ntval[8 + z];
+            }
+            rtile_group<C, KT, VEC0>(tile, b, tv, rt, subs, bm);
+        }
+    } else {
+        for (uint32_t it = 0; ((it << tb) | (uint32_t)tid) < ngroups; ++it) {
+            const uint32_t g = (it << tb) | (uint32_t)tid;
+            uint32_t bb = 0;
+            for (int i = 0; i < gm.ngb; ++i) bb ^= (0u - ((g >> i) & 1u)) & gm.ntval[i];
+            rtile_group<C, KT, VEC0>(tile, bb, tv, rt, subs, bm);
+        }
+    }
+}
+
+template <typename C>
+TCB_HD void rtile_run(C* tile, const RTile& rt, const RSub* subs, const C* bm, int tid, int nthr, int tb) {
+    const bool vec0 = sizeof(C) == 8 && rt.gm.vec0 != 0;
+    switch (rt.kt) {
+        case 1:
+            rtile_run_v<C, 1, false>(tile, rt, subs, bm, tid, nthr, tb);
+            break;
+        case 2:
+            if (vec0) rtile_run_v<C, 2, true>(tile, rt, subs, bm, tid, nthr, tb);
+            else rtile_run_v<C, 2, false>(tile, rt, subs, bm, tid, nthr, tb);
+            break;
+        case 3:
+            if (vec0) rtile_run_v<C, 3, true>(tile, rt, subs, bm, tid, nthr, tb);
+            else rtile_run_v<C, 3, false>(tile, rt, subs, bm, tid, nthr, tb);
+            break;
+        default:
+            if (vec0) rtile_run_v<C, 4, true>(tile, rt, subs, bm, tid, nthr, tb);
+            else rtile_run_v<C, 4, false>(tile, rt, subs, bm, tid, nthr, tb);
+            break;
+    }
+}
+
 // ---- host helpers (plan.cpp part of abi.cu) ------------------------------------------------
 // Choose the tile for a set of ascending target bits: gathers exactly the targets that do not
 // fall into the contiguous low part.  Returns <0 on error.

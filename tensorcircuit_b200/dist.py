@@ -159,6 +159,26 @@ class DistState:
         self.local.apply_block(lb)
         self.stats["local_passes"] += 1
 
+    def _run_local_batch(self, batch: Sequence[Block]) -> None:
+        """Blocks that can all run before the next remap: staged multi-block passes on the
+        shard when the local engine plans them, one pass per block otherwise."""
+        if not batch:
+            return
+        fixed = []
+        for lb in batch:
+            if len(lb.bits) == 0:  # pure rank phase: fold into a 1-bit diagonal block
+                ph = complex(np.asarray(lb.matrix).reshape(-1)[0])
+                lb = Block(qubits=(self.nloc - 1,), bits=(0,), matrix=np.eye(2, dtype=np.complex128) * ph, batched=False, ngates=lb.ngates)
+            fixed.append(lb)
+        if self.use_passes and hasattr(self.local, "apply_planned"):
+            self.stats["local_passes"] += int(self.local.apply_planned(fixed))
+        else:
+            for lb in fixed:
+                self.local.apply_block(lb)
+            self.stats["local_passes"] += len(fixed)
+
+    use_passes = True
+
     def _swap_local_bits(self, pa: int, pb: int) -> None:
         """Exchange two physical local bits (one local pass) and update the map."""
         lo, hi = sorted((pa, pb))
@@ -244,13 +264,14 @@ class DistState:
         while done < nb:
             progressed = False
             again = True
+            batch: List[Block] = []  # everything executable before the next remap, in order
             while again:
                 again = False
                 for i in list(ready):
                     lb = self._try_local(blocks[i])
                     if lb is None:
                         continue
-                    self._run_local(lb)
+                    batch.append(lb)
                     ready.remove(i)
                     done += 1
                     progressed = again = True
@@ -259,6 +280,7 @@ class DistState:
                         if indeg[s] == 0:
                             ready.append(s)
                     ready.sort()
+            self._run_local_batch(batch)
             if done == nb:
                 break
             if not progressed:

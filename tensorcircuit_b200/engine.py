@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import check, lib
-from .fusion import Block, plan_passes, tile_hi_fixpoint  # noqa: F401
+from .fusion import Block, plan_passes, plan_regtiles, tile_hi_fixpoint  # noqa: F401
 
 _TORCH_C = {"complex64": torch.complex64, "complex128": torch.complex128}
 _DT = {"complex64": _lib.C64, "complex128": _lib.C128}
@@ -149,15 +149,45 @@ class DeviceState:
         mat_elems = (12 * 1024) // self.amp_bytes
         passes = plan_passes([b.bits for b in blocks], self.nbits, T, max_hi=self.pass_max_hi,
                              max_ops=_lib.MAX_PASS_OPS, max_mat_elems=mat_elems, max_pass_k=_lib.MAX_PASS_K)
+        nlaunch = 0
         for p in passes:
             blks = [blocks[i] for i in p.block_ids]
             if len(blks) == 1:
                 self.apply_block(blks[0])
+                nlaunch += 1
             elif any(b.batched for b in blks):
                 self.apply_pass(blks, p.tile_hi)
+                nlaunch += 1
+            elif self.use_regtiles and all(len(b.bits) <= 2 for b in blks):
+                nlaunch += self.apply_rpass_host(blocks, p.block_ids, p.tile_hi)
             else:
                 self.apply_pass_host(blks, p.tile_hi)
-        return len(passes)
+                nlaunch += 1
+        return nlaunch
+
+    use_regtiles = os.environ.get("TCB200_REGTILES", "1") != "0"
+
+    def apply_rpass_host(self, blocks: Sequence[Block], ids: Sequence[int], tile_hi: Sequence[int]) -> int:
+        """One staged pass whose blocks are clustered into register tiles (fusion.plan_regtiles)."""
+        kt_max = 4 if self.dtype == "complex64" else 3
+        tiles = plan_regtiles([b.bits for b in blocks], list(ids), max_bits=kt_max)
+        hi = np.asarray(list(tile_hi) if len(tile_hi) else [0], dtype=np.int32)
+        launches = 0
+        for c0 in range(0, len(tiles), _lib.MAX_PASS_OPS):
+            chunk = tiles[c0 : c0 + _lib.MAX_PASS_OPS]
+            rt_k = np.asarray([len(t.bits) for t in chunk], dtype=np.int32)
+            rt_bits = np.asarray([x for t in chunk for x in t.bits], dtype=np.int32)
+            rt_nsub = np.asarray([len(t.block_ids) for t in chunk], dtype=np.int32)
+            sub_k = np.asarray([len(blocks[i].bits) for t in chunk for i in t.block_ids], dtype=np.int32)
+            sub_bits = np.asarray([x for t in chunk for i in t.block_ids for x in blocks[i].bits], dtype=np.int32)
+            mats = np.ascontiguousarray(np.concatenate([np.asarray(blocks[i].matrix, dtype=np.complex128).reshape(-1) for t in chunk for i in t.block_ids]))
+            check(lib.tcb200_apply_rpass_host(_ptr(self.buf), self.nbits, self.dt, len(chunk), _lib.iptr(rt_k), _lib.iptr(rt_bits), _lib.iptr(rt_nsub),
+                                              _lib.iptr(sub_k), _lib.iptr(sub_bits), _lib.dptr(mats.view(np.float64)), len(tile_hi), _lib.iptr(hi),
+                                              self.batch, _stream()))
+            STATS["apply_launches"] += 1
+            STATS["apply_bytes"] += 2 * self.amp_bytes * (self.batch << self.nbits)
+            launches += 1
+        return launches
 
     def apply_pass_host(self, blocks: Sequence[Block], tile_hi: Sequence[int]) -> None:
         """Several shared-matrix blocks in one staged pass, matrices in the constant bank."""

@@ -197,6 +197,50 @@ class Pass:
     tile_hi: List[int]
 
 
+@dataclass
+class RegTile:
+    """<= 4 tile-local bits and the blocks (1 or 2 bits each, all inside those bits) applied to
+    them back to back in registers: one shared-memory round trip for all of them."""
+
+    bits: Tuple[int, ...]
+    block_ids: List[int]
+
+
+def plan_regtiles(block_bits: Sequence[Tuple[int, ...]], ids: Sequence[int], max_bits: int = 4,
+                  max_gates: int = 12) -> List[RegTile]:
+    """Cluster the blocks of one pass (``ids`` in execution order) into register tiles.
+
+    A block may join the open register tile when every earlier block of the pass that shares a
+    bit with it is already placed (dependencies), and the union of bits stays within
+    ``max_bits``; blocks on the same qubits therefore pile up in one tile."""
+    n = len(ids)
+    bsets = [set(block_bits[i]) for i in ids]
+    placed = [False] * n
+    tiles: List[RegTile] = []
+    left = n
+    while left:
+        bits: set = set()
+        members: List[int] = []
+        progressed = True
+        while progressed and len(members) < max_gates:
+            progressed = False
+            for i in range(n):
+                if placed[i]:
+                    continue
+                if any((not placed[j]) and (bsets[j] & bsets[i]) for j in range(i)):
+                    continue  # an earlier block on a shared bit is still pending
+                if len(bits | bsets[i]) > max_bits:
+                    continue
+                bits |= bsets[i]
+                members.append(i)
+                placed[i] = True
+                left -= 1
+                progressed = True
+                break
+        tiles.append(RegTile(bits=tuple(sorted(bits)), block_ids=[ids[i] for i in members]))
+    return tiles
+
+
 _PASS_CACHE: Dict[Any, List[Pass]] = {}
 
 

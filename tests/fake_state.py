@@ -84,6 +84,24 @@ class FakeState:
                 for b in blks:
                     self.apply_block(b)
                 continue
+            if all(len(b.bits) <= 2 for b in blks):  # register-tile pass, as DeviceState.apply_rpass_host
+                from tensorcircuit_b200.fusion import plan_regtiles
+
+                tiles = plan_regtiles([b.bits for b in blocks], list(p.block_ids), max_bits=4 if self.dt == 0 else 3)
+                assert sorted(i for t in tiles for i in t.block_ids) == sorted(p.block_ids)
+                rt_k = [len(t.bits) for t in tiles]
+                rt_bits = [x for t in tiles for x in t.bits]
+                rt_nsub = [len(t.block_ids) for t in tiles]
+                sub_k = [len(blocks[i].bits) for t in tiles for i in t.block_ids]
+                sub_bits = [x for t in tiles for i in t.block_ids for x in blocks[i].bits]
+                mats = np.ascontiguousarray(np.concatenate([np.asarray(blocks[i].matrix, dtype=np.complex128).reshape(-1) for t in tiles for i in t.block_ids]))
+                for r in range(self.batch):
+                    rc = self._lib.emu_apply_rpass(self.np[r].ctypes.data_as(ctypes.c_void_p), self.nbits, self.dt, len(tiles), _ip(rt_k), _ip(rt_bits), _ip(rt_nsub),
+                                                   _ip(sub_k), _ip(sub_bits), mats.view(np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                   len(p.tile_hi), _ip(p.tile_hi if p.tile_hi else [0]))
+                    assert rc == 0, self._lib.emu_last_error()
+                engine.STATS["apply_launches"] += 1
+                continue
             ks = [len(b.bits) for b in blks]
             bits = [x for b in blks for x in b.bits]
             mats = np.ascontiguousarray(np.concatenate([np.asarray(b.matrix, dtype=np.complex128).reshape(-1) for b in blks]))

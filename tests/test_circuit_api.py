@@ -588,6 +588,21 @@ def test_vmap_hea_energy(eng):
 
 
 # ---- pass planner --------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [("complex64", 1e-5), ("complex128", 1e-11)])
+def test_planned_passes_production_tile(eng, dtype, tol):
+    """Default 64 KiB pass tile, 256 threads, several tiles: the unrolled / Gray-code paths of
+    the pass kernels (register tiles included) against the oracle."""
+    tc.set_dtype(dtype)
+    n = 15
+    ops = orc.random_circuit(n, 3, seed=9)
+    ops += [("toffoli", (0, 7, 14), {}), ("rzz", (3, 11), {"theta": 0.4}), ("h", (14,), {}), ("cz", (13, 14), {})]
+    c = _run_gatelist(n, ops)
+    o = orc.run_gatelist(n, ops)
+    assert np.linalg.norm(A(c.state()) - o.state()) / np.linalg.norm(o.state()) < tol
+    tc.set_dtype("complex64")
+
+
+
 @pytest.mark.parametrize("kf", [2, 3, 4])
 def test_planned_passes_small_tiles(eng, kf, monkeypatch):
     """Multi-block staged passes with a tiny tile (many passes, gathered high bits) == oracle."""

@@ -21,13 +21,16 @@ EMU_LIB = os.path.join(EMU_DIR, "_build", "libtcb200emu.so")
 
 
 def _build_emu():
-    srcs = [os.path.join(EMU_DIR, "emu.cu"), os.path.join(ROOT, "tensorcircuit_b200", "csrc", "abi.cu")]
+    # apply.cu is compiled with -DTCB200_EMU only here: that adds the CPU execution of the
+    # register-tile pass (same parameter block and device functions as rpass_kernel)
+    srcs = [os.path.join(EMU_DIR, "emu.cu"), os.path.join(ROOT, "tensorcircuit_b200", "csrc", "abi.cu"),
+            os.path.join(ROOT, "tensorcircuit_b200", "csrc", "apply.cu")]
     deps = srcs + [os.path.join(ROOT, "tensorcircuit_b200", "csrc", "common.cuh"), os.path.join(ROOT, "include", "tcb200.h")]
     if os.path.exists(EMU_LIB) and all(os.path.getmtime(EMU_LIB) > os.path.getmtime(d) for d in deps):
         return
     os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
     nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc"
-    cmd = [nvcc, "-O1", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
+    cmd = [nvcc, "-O1", "-std=c++17", "-DTCB200_EMU", "-shared", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
            "-I", os.path.join(ROOT, "tensorcircuit_b200", "csrc"), "-gencode", "arch=compute_100a,code=sm_100a"] + srcs + ["-o", EMU_LIB, "-lcudart"]
     subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
 
