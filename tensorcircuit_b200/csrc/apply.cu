@@ -470,7 +470,8 @@ static int fill_rpass(RPassParams<Real>& q, void* state, int nbits, int nrt, con
     const int* sk = sub_k;
     for (int o = 0; o < nrt; ++o) {
         const int kt = rt_k[o];
-        if (kt < 1 || kt > 4) return fail(TCB200_ERR_UNSUPPORTED, "register tile of %d bits (max 4)", kt);
+        if (kt < 1 || kt > (sizeof(Real) == 4 ? 4 : 3))
+            return fail(TCB200_ERR_UNSUPPORTED, "register tile of %d bits (max 4 for complex64, 3 for complex128)", kt);
         for (int i = 0; i < kt; ++i)
             if (rb[i] < 0 || rb[i] >= nbits) return fail(TCB200_ERR_ARG, "bit %d out of range", rb[i]);
         q.rt[o].kt = kt;

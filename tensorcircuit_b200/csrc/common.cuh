@@ -500,8 +500,12 @@ TCB_HD void rtile_run(C* tile, const RTile& rt, const RSub* subs, const C* bm, i
             else rtile_run_v<C, 3, false>(tile, rt, subs, bm, tid, nthr, tb);
             break;
         default:
-            if (vec0) rtile_run_v<C, 4, true>(tile, rt, subs, bm, tid, nthr, tb);
-            else rtile_run_v<C, 4, false>(tile, rt, subs, bm, tid, nthr, tb);
+            // 4-bit register tiles only for complex64 (16 amplitudes = 32 registers); for
+            // complex128 the host plans <= 3 bits and abi checks it
+            if constexpr (sizeof(C) == 8) {
+                if (vec0) rtile_run_v<C, 4, true>(tile, rt, subs, bm, tid, nthr, tb);
+                else rtile_run_v<C, 4, false>(tile, rt, subs, bm, tid, nthr, tb);
+            }
             break;
     }
 }

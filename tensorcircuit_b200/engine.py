@@ -165,7 +165,11 @@ class DeviceState:
                 nlaunch += 1
         return nlaunch
 
-    use_regtiles = os.environ.get("TCB200_REGTILES", "1") != "0"
+    # Register tiles (several gates per shared-memory round trip) pay off when many gates pile up
+    # on the same <= 4 qubits inside a pass (nearest-neighbour ladders); on the random-matching
+    # benchmark circuit a pass holds ~2 gates per tile and the generic dispatch costs more than it
+    # saves (measured: profiles/README.md), so the plain multi-block pass is the default.
+    use_regtiles = os.environ.get("TCB200_REGTILES", "0") != "0"
 
     def apply_rpass_host(self, blocks: Sequence[Block], ids: Sequence[int], tile_hi: Sequence[int]) -> int:
         """One staged pass whose blocks are clustered into register tiles (fusion.plan_regtiles)."""

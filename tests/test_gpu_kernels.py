@@ -328,11 +328,12 @@ def test_config2_tfim_energy_n20():
 
 
 @pytest.mark.parametrize("dtype", ["complex64", "complex128"])
-@pytest.mark.parametrize("kf", [2, 3])
-def test_apply_planned_vs_oracle(dtype, kf):
-    """Pass planner + constant-bank multi-block pass kernel on a 21-qubit circuit."""
+@pytest.mark.parametrize("kf,regtiles", [(2, False), (2, True), (3, False)])
+def test_apply_planned_vs_oracle(dtype, kf, regtiles, monkeypatch):
+    """Pass planner + multi-block pass kernels (plain and register-tile) on a 21-qubit circuit."""
     from tensorcircuit_b200.fusion import fuse
 
+    monkeypatch.setattr(DeviceState, "use_regtiles", regtiles)
     n = 21
     ops = orc.random_circuit(n, 4, seed=11)
     tc.set_dtype(dtype)
