@@ -352,7 +352,8 @@ def run_ours(args):
         "gate_phase_ms_per_step": apply_ms / args.steps,
         "roofline": {"bound": "hbm", "kernel": "rpass_kernel (staged multi-block pass, register tiles)" if use_passes else "dense_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "bytes_per_launch": bytes_per_launch,
-                     "launch_ms": launch_ms, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
+                     "launch_ms": launch_ms, "traffic": (bytes_per_launch * traffic["dram_bytes_per_algorithmic_byte"]) if traffic and "dram_bytes_per_algorithmic_byte" in traffic else None,
+                     "traffic_source": (traffic or {}).get("source"),
                      "fp32_fma_per_amp_per_launch": sum(4 * 2 ** len(b.bits) for b in blocks) / max(1, npass),
                      "note": "a staged pass holding several blocks is FP32-FMA-bound, not HBM-bound: see roofline_single_block for the one-block-per-pass kernel"},
         "roofline_single_block": dict(probe, bound="hbm", kernel="dense_kernel", peak=peak, unit="GB/s"),
