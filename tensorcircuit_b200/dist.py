@@ -215,19 +215,42 @@ class DistState:
         self.stats["remap_bytes"] += self.shard_bytes - self.shard_bytes // self.G
 
     def _remap_chunked(self, src: torch.Tensor) -> None:
-        G = self.G
+        """In-place exchange through a bounded staging buffer (shards too large to double
+        buffer).  The rank's own chunk never moves; the peer chunks go slice by slice through two
+        staging sets so that packing slice i+1 and unpacking slice i-1 (device copies, HBM-bound)
+        overlap the all-to-all of slice i (NVLink-bound)."""
+        G, r = self.G, self.rank
         chunk = src.shape[0] // G  # amplitudes per peer chunk
-        rowb = self.amp_bytes
-        per = max(1, min(chunk, self.staging_bytes // (2 * G * rowb)))
-        # largest power of two <= per (chunk is a power of two)
-        per = 1 << (per.bit_length() - 1)
-        if self._stage is None or self._stage.shape[1] != G * per:
-            self._stage = torch.empty((2, G * per, 2), dtype=src.dtype, device=src.device)
-        send, recv = self._stage[0], self._stage[1]
-        for s in range(0, chunk, per):
-            self._copy_rows(send, per, src[s:], chunk, per, G)       # pack: row c <- chunk c, slice s
-            dist.all_to_all_single(recv, send, group=self.group)
-            self._copy_rows(src[s:], chunk, recv, per, per, G)       # unpack into the same slots
+        nset = 2
+        per = max(1, min(chunk, self.staging_bytes // (2 * nset * (G - 1) * self.amp_bytes)))
+        per = 1 << (per.bit_length() - 1)  # chunk is a power of two
+        rows = (G - 1) * per
+        if self._stage is None or tuple(self._stage.shape[:3]) != (nset, 2, rows):
+            self._stage = torch.empty((nset, 2, rows, 2), dtype=src.dtype, device=src.device)
+        peers = [c for c in range(G) if c != r]
+        splits = [per] * G
+        splits[r] = 0
+        slices = list(range(0, chunk, per))
+        works: List[Any] = [None] * nset
+
+        def unpack(i: int) -> None:
+            k = i % nset
+            works[k].wait()
+            recv = self._stage[k, 1]
+            for j, c in enumerate(peers):
+                self._copy_rows(src[c * chunk + slices[i]:], per, recv[j * per:], per, per, 1)
+
+        for i, s in enumerate(slices):
+            k = i % nset
+            if i >= nset:
+                unpack(i - nset)  # frees staging set k
+            send = self._stage[k, 0]
+            for j, c in enumerate(peers):
+                self._copy_rows(send[j * per:], per, src[c * chunk + s:], per, per, 1)
+            works[k] = dist.all_to_all_single(self._stage[k, 1], send, output_split_sizes=splits, input_split_sizes=splits,
+                                              group=self.group, async_op=True)
+        for i in range(max(0, len(slices) - nset), len(slices)):
+            unpack(i)
 
     def _copy_rows(self, dst: torch.Tensor, dst_pitch: int, src: torch.Tensor, src_pitch: int, row: int, nrows: int) -> None:
         """copy nrows runs of `row` amplitudes; pitches in amplitudes"""
