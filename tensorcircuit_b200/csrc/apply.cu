@@ -424,7 +424,7 @@ struct RPassParams {
 };
 
 template <typename Real>
-__global__ void __launch_bounds__(256) rpass_kernel(const __grid_constant__ RPassParams<Real> p) {
+__global__ void __launch_bounds__(256, 3) rpass_kernel(const __grid_constant__ RPassParams<Real> p) {
     using C = typename CT<Real>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     C* tile = reinterpret_cast<C*>(smem_raw);

@@ -358,10 +358,19 @@ struct RTile {
 
 // one 2-bit gate on positions (P0, P1) of the 2^KT register array
 template <typename C, int KT, int P0, int P1>
+TCB_HD void rsub2r(C* v, const C* mr);
+
+template <typename C, int KT, int P0, int P1>
 TCB_HD void rsub2(C* v, const C* m) {
     C mr[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) mr[i] = m[i];
+    rsub2r<C, KT, P0, P1>(v, mr);
+}
+
+// same with the matrix already in registers
+template <typename C, int KT, int P0, int P1>
+TCB_HD void rsub2r(C* v, const C* mr) {
 #pragma unroll
     for (int r = 0; r < (1 << (KT - 2)); ++r) {
         // spread r over the positions other than P0, P1
@@ -484,9 +493,112 @@ TCB_HD void rtile_run_v(C* tile, const RTile& rt, const RSub* subs, const C* bm,
     }
 }
 
+// Pair path: a 4-bit register tile holding exactly two 2-bit gates on disjoint positions
+// (P0,P1) and the complementary pair.  Both matrices are loaded once per thread, each group of
+// 16 amplitudes makes one shared-memory round trip for 32 FMA per amplitude -- twice the
+// arithmetic intensity of running the two gates as separate blocks.
+template <typename C, int P0, int P1, bool VEC0>
+TCB_HD void rpair_run(C* tile, const RTile& rt, const C* mA, const C* mB, int tid) {
+    constexpr int Q0 = (P0 != 0 && P1 != 0) ? 0 : ((P0 != 1 && P1 != 1) ? 1 : 2);
+    constexpr int Q1 = (P0 != 3 && P1 != 3) ? 3 : ((P0 != 2 && P1 != 2) ? 2 : 1);
+    const GroupMap& gm = rt.gm;
+    C ra[16], rb[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        ra[i] = mA[i];
+        rb[i] = mB[i];
+    }
+    uint32_t tv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) tv[j] = gm.tval[j];
+    uint32_t b = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b ^= (0u - (((uint32_t)tid >> i) & 1u)) & gm.ntval[i];
+    const uint32_t nit = (1u << gm.ngb) >> 8;
+    for (uint32_t it = 0; it < nit; ++it) {
+        if (it > 0) {
+            int z = 0;
+            while (!((it >> z) & 1u)) ++z;
+            b ^= gm.ntval[8 + z];
+        }
+        C v[16];
+        if (VEC0) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const Unit16 q = *reinterpret_cast<const Unit16*>(tile + (b ^ tv[j]));
+                const C* qc = reinterpret_cast<const C*>(&q);
+                v[j] = qc[0];
+                v[j + 1] = qc[1 % (16 / (int)sizeof(C))];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = tile[b ^ tv[j]];
+        }
+        rsub2r<C, 4, P0, P1>(v, ra);
+        rsub2r<C, 4, Q0, Q1>(v, rb);
+        if (VEC0) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                Unit16 q;
+                C* qc = reinterpret_cast<C*>(&q);
+                qc[0] = v[j];
+                qc[1 % (16 / (int)sizeof(C))] = v[j + 1];
+                *reinterpret_cast<Unit16*>(tile + (b ^ tv[j])) = q;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) tile[b ^ tv[j]] = v[j];
+        }
+    }
+}
+
+template <typename C, int P0, int P1>
+TCB_HD void rpair_dispatch(C* tile, const RTile& rt, const C* mA, const C* mB, int tid) {
+    if (sizeof(C) == 8 && rt.gm.vec0)
+        rpair_run<C, P0, P1, true>(tile, rt, mA, mB, tid);
+    else
+        rpair_run<C, P0, P1, false>(tile, rt, mA, mB, tid);
+}
+
 template <typename C>
 TCB_HD void rtile_run(C* tile, const RTile& rt, const RSub* subs, const C* bm, int tid, int nthr, int tb) {
     const bool vec0 = sizeof(C) == 8 && rt.gm.vec0 != 0;
+    const RSub s0 = subs[rt.sub0];
+    if (rt.nsub == 1 && rt.kt == s0.k) {
+        // one gate covering the whole tile: the plain block path (matrix in registers)
+        const C* m = bm + s0.moff;
+        if (s0.k == 1) {
+            C r[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[i] = m[i];
+            apply_block_dispatch<C, 1>(tile, rt.gm, tid, nthr, tb, [&](int i, int j) { return r[i * 2 + j]; });
+        } else {
+            C r[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = m[i];
+            apply_block_dispatch<C, 2>(tile, rt.gm, tid, nthr, tb, [&](int i, int j) { return r[i * 4 + j]; });
+        }
+        return;
+    }
+    if constexpr (sizeof(C) == 8) {
+        if (rt.kt == 4 && rt.nsub == 2 && nthr == 256 && rt.gm.ngb >= 8) {
+            const RSub s1 = subs[rt.sub0 + 1];
+            const int ma = (1 << s0.p0) | (1 << s0.p1), mb = (1 << s1.p0) | (1 << s1.p1);
+            if (s0.k == 2 && s1.k == 2 && (ma & mb) == 0) {
+                const C* mA = bm + s0.moff;
+                const C* mB = bm + s1.moff;
+                switch (s0.p0 * 4 + s0.p1) {
+                    case 1: rpair_dispatch<C, 0, 1>(tile, rt, mA, mB, tid); break;
+                    case 2: rpair_dispatch<C, 0, 2>(tile, rt, mA, mB, tid); break;
+                    case 3: rpair_dispatch<C, 0, 3>(tile, rt, mA, mB, tid); break;
+                    case 6: rpair_dispatch<C, 1, 2>(tile, rt, mA, mB, tid); break;
+                    case 7: rpair_dispatch<C, 1, 3>(tile, rt, mA, mB, tid); break;
+                    default: rpair_dispatch<C, 2, 3>(tile, rt, mA, mB, tid); break;
+                }
+                return;
+            }
+        }
+    }
     switch (rt.kt) {
         case 1:
             rtile_run_v<C, 1, false>(tile, rt, subs, bm, tid, nthr, tb);

@@ -171,10 +171,13 @@ class DeviceState:
     # saves (measured: profiles/README.md), so the plain multi-block pass is the default.
     use_regtiles = os.environ.get("TCB200_REGTILES", "0") != "0"
 
+    # 2 = pair mode: two disjoint 2-bit gates per 4-bit register tile (the specialised path)
+    regtile_max_gates = int(os.environ.get("TCB200_REGTILE_GATES", "2"))
+
     def apply_rpass_host(self, blocks: Sequence[Block], ids: Sequence[int], tile_hi: Sequence[int]) -> int:
         """One staged pass whose blocks are clustered into register tiles (fusion.plan_regtiles)."""
         kt_max = 4 if self.dtype == "complex64" else 3
-        tiles = plan_regtiles([b.bits for b in blocks], list(ids), max_bits=kt_max)
+        tiles = plan_regtiles([b.bits for b in blocks], list(ids), max_bits=kt_max, max_gates=self.regtile_max_gates)
         hi = np.asarray(list(tile_hi) if len(tile_hi) else [0], dtype=np.int32)
         launches = 0
         for c0 in range(0, len(tiles), _lib.MAX_PASS_OPS):

@@ -67,6 +67,7 @@ class FakeState:
             self.apply_block(b)
 
     pass_max_hi = 6
+    regtile_max_gates = 2  # pair mode, as the engine; tests override it to cover the generic path
 
     def apply_planned(self, blocks):
         """Same planner as DeviceState.apply_planned; passes run through the emulated pass kernel."""
@@ -87,7 +88,8 @@ class FakeState:
             if all(len(b.bits) <= 2 for b in blks):  # register-tile pass, as DeviceState.apply_rpass_host
                 from tensorcircuit_b200.fusion import plan_regtiles
 
-                tiles = plan_regtiles([b.bits for b in blocks], list(p.block_ids), max_bits=4 if self.dt == 0 else 3)
+                tiles = plan_regtiles([b.bits for b in blocks], list(p.block_ids), max_bits=4 if self.dt == 0 else 3,
+                                      max_gates=self.regtile_max_gates)
                 assert sorted(i for t in tiles for i in t.block_ids) == sorted(p.block_ids)
                 rt_k = [len(t.bits) for t in tiles]
                 rt_bits = [x for t in tiles for x in t.bits]

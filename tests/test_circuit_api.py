@@ -588,10 +588,14 @@ def test_vmap_hea_energy(eng):
 
 
 # ---- pass planner --------------------------------------------------------------------------------
+@pytest.mark.parametrize("rt_gates", [2, 12])
 @pytest.mark.parametrize("dtype,tol", [("complex64", 1e-5), ("complex128", 1e-11)])
-def test_planned_passes_production_tile(eng, dtype, tol):
+def test_planned_passes_production_tile(eng, dtype, tol, rt_gates, monkeypatch):
     """Default 64 KiB pass tile, 256 threads, several tiles: the unrolled / Gray-code paths of
-    the pass kernels (register tiles included) against the oracle."""
+    the pass kernels (register tiles in pair mode and in generic mode) against the oracle."""
+    st_cls = tc.engine.DeviceState
+    monkeypatch.setattr(st_cls, "regtile_max_gates", rt_gates)
+    monkeypatch.setattr(st_cls, "use_regtiles", True, raising=False)
     tc.set_dtype(dtype)
     n = 15
     ops = orc.random_circuit(n, 3, seed=9)
