@@ -329,8 +329,9 @@ def run_ours(args):
         c = recipes.build(tc.Circuit(n), ops)
         c.use_passes = use_passes
         s = c.sample(batch=shots, allow_state=True, status=u_host, format="sample_int")
-        del c
-        gc.collect()
+        del c  # refcount drop returns the 2^n buffer to the caching allocator for the next step
+        if torch.cuda.memory_allocated() > (8 << n) // 2:  # never reached unless a cycle kept it alive
+            gc.collect()
         return s
 
     s_api = api_step()  # warm-up (also allocates the state once; the allocator then reuses it)

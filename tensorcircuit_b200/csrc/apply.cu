@@ -204,12 +204,20 @@ __global__ void __launch_bounds__(256) pass_kernel(const __grid_constant__ PassP
         const PassOp& op = p.op[o];
         const C* m = bm + op.moff;
         switch (op.k) {
-            case 1:
-                apply_block_dispatch<C,1>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return m[i * 2 + j]; });
+            case 1: {  // narrow blocks: matrix in registers for all the groups of the thread
+                C r[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r[i] = m[i];
+                apply_block_dispatch<C,1>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return r[i * 2 + j]; });
                 break;
-            case 2:
-                apply_block_dispatch<C,2>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return m[i * 4 + j]; });
+            }
+            case 2: {
+                C r[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = m[i];
+                apply_block_dispatch<C,2>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return r[i * 4 + j]; });
                 break;
+            }
             case 3:
                 apply_block_dispatch<C,3>(tile, op.gm, tid, nthr, p.tb, [&](int i, int j) { return m[i * 8 + j]; });
                 break;

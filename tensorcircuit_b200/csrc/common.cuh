@@ -662,6 +662,42 @@ TCB_HD void expect_tile_term(const C* tile, uint32_t tsz, uint32_t fl, uint32_t 
     *out_im = pi;
 }
 
+// All terms of a launch on one staged tile: every amplitude of the thread is loaded once and
+// reused by all terms; Z-type terms (no flip) need no partner load at all.
+template <typename C, typename R, int MT>
+TCB_HD void expect_tile_terms(const C* tile, uint32_t tsz, int nterms, const uint32_t* fl, const uint32_t* sl,
+                              int tid, int nthr, R* pr, R* pi) {
+#pragma unroll
+    for (int t = 0; t < MT; ++t) pr[t] = pi[t] = 0;
+    for (uint32_t e = tid; e < tsz; e += nthr) {
+        const C a = tile[e];
+        const R p = a.x * a.x + a.y * a.y;
+#pragma unroll
+        for (int t = 0; t < MT; ++t) {
+            if (t < nterms) {
+                R re = p, im = 0;
+                if (fl[t] != 0) {
+                    const C b = tile[e ^ fl[t]];
+                    re = a.x * b.x + a.y * b.y;
+                    im = a.x * b.y - a.y * b.x;
+                }
+                uint32_t par = e & sl[t];
+                par ^= par >> 16;
+                par ^= par >> 8;
+                par ^= par >> 4;
+                par ^= par >> 2;
+                par ^= par >> 1;
+                if (par & 1u) {
+                    re = -re;
+                    im = -im;
+                }
+                pr[t] += re;
+                pi[t] += im;
+            }
+        }
+    }
+}
+
 TCB_HD bool parity64(uint64_t x) {
     x ^= x >> 32;
     x ^= x >> 16;

@@ -55,14 +55,16 @@ __global__ void __launch_bounds__(256) expect_kernel(const __grid_constant__ Exp
         stage_in<C, false>(p.g, vec, base, tile, rowoff, tid, nthr);
         cp_async_wait_all();
         __syncthreads();
+        {
+            Real pr[MT], pi[MT];
+            expect_tile_terms<C, Real, MT>(tile, tsz, p.nterms, p.flip_l, p.sign_l, tid, nthr, pr, pi);
 #pragma unroll
-        for (int t = 0; t < MT; ++t) {
-            if (t < p.nterms) {
-                Real pr, pi;
-                expect_tile_term<C, Real>(tile, tsz, p.flip_l[t], p.sign_l[t], tid, nthr, &pr, &pi);
-                const bool neg = parity64(base & p.sign_hi[t]);
-                acc_re[t] += neg ? -(double)pr : (double)pr;
-                acc_im[t] += neg ? -(double)pi : (double)pi;
+            for (int t = 0; t < MT; ++t) {
+                if (t < p.nterms) {
+                    const bool neg = parity64(base & p.sign_hi[t]);
+                    acc_re[t] += neg ? -(double)pr[t] : (double)pr[t];
+                    acc_im[t] += neg ? -(double)pi[t] : (double)pi[t];
+                }
             }
         }
         __syncthreads();  // tile is overwritten by the next iteration

@@ -68,19 +68,35 @@ def embed_apply(block_m: np.ndarray, block_qubits: Sequence[int], g: np.ndarray,
         t = np.tensordot(gt, t, axes=(list(range(kg, 2 * kg)), pos))
         t = np.moveaxis(t, list(range(kg)), pos)
         return np.ascontiguousarray(t).reshape(D, D)
-    B = block_m.shape[0] if block_m.ndim == 3 else g.shape[0]
-    bm = np.broadcast_to(block_m, (B, D, D)) if block_m.ndim == 2 else block_m
-    gm = np.broadcast_to(g, (B,) + g.shape[-2:]) if g.ndim == 2 else g
-    # einsum with explicit letters: batch z, row legs, column c
-    letters = "abcdefgh"
-    row = list(letters[:k])
-    out = list(row)
-    new = "ijklm"[:kg]
+    # batched (vmap): embed the gate into the block's index space by fancy indexing and use
+    # one batched matmul -- an order of magnitude cheaper on the host than an einsum per gate
+    og, same_rest = _embed_index(k, tuple(pos))
+    full = g[..., og[:, None], og[None, :]] * same_rest
+    return np.matmul(full, block_m)
+
+
+_EMBED_CACHE: Dict[Any, Tuple[np.ndarray, np.ndarray]] = {}
+
+
+def _embed_index(k: int, pos: Tuple[int, ...]) -> Tuple[np.ndarray, np.ndarray]:
+    """For a block of k qubits (big-endian index over its ascending qubit list) and a gate on the
+    block positions ``pos`` (gate order): the gate index of every block index, and the mask of
+    index pairs that agree on all other positions."""
+    hit = _EMBED_CACHE.get((k, pos))
+    if hit is not None:
+        return hit
+    D = 1 << k
+    kg = len(pos)
+    idx = np.arange(D)
+    og = np.zeros(D, dtype=np.int64)
+    rest = idx.copy()
     for a, p in enumerate(pos):
-        out[p] = new[a]
-    expr = "z%s%s,z%sy->z%sy" % (new, "".join(row[p] for p in pos), "".join(row), "".join(out))
-    t = np.einsum(expr, gm.reshape([B] + [2] * (2 * kg)), bm.reshape([B] + [2] * k + [D]), optimize=False)
-    return np.ascontiguousarray(t).reshape(B, D, D)
+        bit = (idx >> (k - 1 - p)) & 1
+        og |= bit << (kg - 1 - a)
+        rest &= ~(1 << (k - 1 - p))
+    same = (rest[:, None] == rest[None, :]).astype(np.complex128)
+    _EMBED_CACHE[(k, pos)] = (og, same)
+    return og, same
 
 
 def _raw(m: Any) -> np.ndarray:

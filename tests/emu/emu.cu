@@ -153,11 +153,13 @@ int emu_expect_t(const void* state, int nbits, int nterms, const uint64_t* flip,
             const uint64_t base = tile_base(g, tl);
             for (int tid = 0; tid < nthr; ++tid) stage_in<C, false>(g, vec, base, tile, rowoff, tid, nthr);
             for (int tid = 0; tid < nthr; ++tid) {
-                Real pr, pi;
-                expect_tile_term<C, Real>(tile, (uint32_t)tile_elems, fl, sl, tid, nthr, &pr, &pi);
+                // the kernel's multi-term body, run here with this term in slot 0
+                Real pr[TCB200_MAX_TERMS], pi[TCB200_MAX_TERMS];
+                const uint32_t fla[TCB200_MAX_TERMS] = {fl}, sla[TCB200_MAX_TERMS] = {sl};
+                expect_tile_terms<C, Real, TCB200_MAX_TERMS>(tile, (uint32_t)tile_elems, 1, fla, sla, tid, nthr, pr, pi);
                 const bool neg = parity64(base & shi);
-                re += neg ? -(double)pr : (double)pr;
-                im += neg ? -(double)pi : (double)pi;
+                re += neg ? -(double)pr[0] : (double)pr[0];
+                im += neg ? -(double)pi[0] : (double)pi[0];
             }
         }
         double ore = re, oim = im;
