@@ -351,7 +351,7 @@ def run_ours(args):
         "config": dict(workload_config(1, n, args.depth, shots), recorded_gates=ngates, fused_passes=npass, block_width_histogram=khist, fusion_kmax=tc.Circuit.fusion_kmax),
         "fused_pass_updates_per_s": args.steps * npass * float(2**n) / (apply_ms * 1e-3),
         "gate_phase_ms_per_step": apply_ms / args.steps,
-        "roofline": {"bound": "hbm", "kernel": "rpass_kernel (staged multi-block pass, register tiles)" if use_passes else "dense_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "roofline": {"bound": "hbm", "kernel": (("rpass_kernel (staged multi-block pass, register tiles)" if engine.DeviceState.use_regtiles else "cpass_kernel (staged multi-block pass)") if use_passes else "dense_kernel"), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "bytes_per_launch": bytes_per_launch,
                      "launch_ms": launch_ms, "traffic": (bytes_per_launch * traffic["dram_bytes_per_algorithmic_byte"]) if traffic and "dram_bytes_per_algorithmic_byte" in traffic else None,
                      "traffic_source": (traffic or {}).get("source"),

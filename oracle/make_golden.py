@@ -1,0 +1,122 @@
+"""Generate tests/golden/ref_fixtures.npz by running the REFERENCE's own code.
+
+Run in the build container (needs /root/reference):  python oracle/make_golden.py
+
+The reference's hot-path modules (gates.py, abstractcircuit.py, basecircuit.py, circuit.py,
+quantum.py, backends/abstract_backend.py + numpy_backend.py, cons.py contractor) execute
+unmodified from /root/reference through oracle/ref_loader.py; only their un-vendored
+third-party dependency (tensornetwork / opt_einsum / graphviz) is replaced by the stand-ins in
+oracle/refshim/.  The fixtures pin, with outputs of the reference itself:
+  * amplitudes of BASELINE config 1 (10-qubit HEA) in complex64 and complex128, and of the
+    config-4 random-circuit recipe at n = 9, and of a circuit that uses every gate name;
+  * expectation_ps of the TFIM strings + random strings, and expectation of general operators;
+  * sample(allow_state=True, status=u) indices -- the one quantity no reference test pins;
+  * sample formats and numpy-backend vmap values.
+"""
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import tc_oracle as orc  # noqa: E402  (only for the shared circuit recipes)
+from oracle.ref_loader import load_reference  # noqa: E402
+
+
+def build(tc, n, ops, **kw):
+    c = tc.Circuit(n, **kw)
+    for name, q, p in ops:
+        getattr(c, name)(*q, **p)
+    return c
+
+
+ALL_GATES = [
+    ("h", (0,), {}), ("x", (1,), {}), ("y", (2,), {}), ("z", (3,), {}), ("t", (0,), {}), ("s", (1,), {}), ("td", (2,), {}), ("sd", (3,), {}),
+    ("wroot", (0,), {}), ("cnot", (0, 1), {}), ("cz", (1, 2), {}), ("swap", (2, 3), {}), ("cy", (3, 0), {}), ("ox", (0, 2), {}), ("oy", (1, 3), {}),
+    ("oz", (2, 0), {}), ("toffoli", (0, 1, 2), {}), ("fredkin", (3, 1, 0), {}),
+    ("r", (0,), dict(theta=0.3, alpha=1.1, phi=-0.7)), ("cr", (1, 2), dict(theta=0.3, alpha=1.1, phi=-0.7)), ("u", (3,), dict(theta=0.4, phi=0.5, lbd=-1.2)),
+    ("cu", (0, 3), dict(theta=0.4, phi=0.5, lbd=-1.2)), ("rx", (1,), dict(theta=0.6)), ("ry", (2,), dict(theta=0.7)), ("rz", (3,), dict(theta=0.8)),
+    ("phase", (0,), dict(theta=0.9)), ("rxx", (0, 1), dict(theta=0.25)), ("ryy", (1, 2), dict(theta=0.35)), ("rzz", (2, 3), dict(theta=0.45)),
+    ("cphase", (3, 1), dict(theta=0.55)), ("crx", (0, 2), dict(theta=0.65)), ("cry", (1, 3), dict(theta=0.75)), ("crz", (2, 0), dict(theta=0.85)),
+    ("orx", (3, 2), dict(theta=0.15)), ("ory", (0, 1), dict(theta=0.22)), ("orz", (1, 0), dict(theta=0.33)), ("iswap", (2, 3), dict(theta=0.4)),
+    ("cx", (3, 2), {}), ("cswap", (0, 2, 3), {}), ("ccnot", (1, 2, 0), {}), ("sdg", (1,), {}), ("tdg", (2,), {}),
+]
+
+
+def main():
+    tc = load_reference()
+    out = {}
+    # ---- config 1: 10-qubit HEA, both dtypes -------------------------------------------------
+    n = 10
+    params = np.random.default_rng(0).uniform(0, 2 * np.pi, size=[4, 2, n])
+    ops = orc.hea_circuit(n, params)
+    pss = [ps for _, ps in orc.tfim_terms(n)] + [list(r) for r in np.random.default_rng(0).integers(0, 4, size=[8, n])]
+    out["hea10_pss"] = np.array(pss)
+    for dt in ("complex64", "complex128"):
+        tc.set_dtype(dt)
+        c = build(tc, n, ops)
+        out["hea10_state_" + dt] = np.asarray(c.wavefunction())
+        out["hea10_exps_" + dt] = np.array([np.asarray(c.expectation_ps(ps=ps)) for ps in pss])
+    tc.set_dtype("complex64")
+    # ---- config 4 recipe at n = 9: amplitudes + sample(status=...) --------------------------------
+    n = 9
+    ops = orc.random_circuit(n, 6, seed=3)
+    c = build(tc, n, ops)
+    out["rand9_state"] = np.asarray(c.wavefunction())
+    u = np.random.default_rng(4).random(2000)
+    out["rand9_status"] = u
+    out["rand9_sample_int"] = np.asarray(c.sample(batch=2000, allow_state=True, status=u, format="sample_int"))
+    out["rand9_sample_bin_head"] = np.asarray(c.sample(batch=8, allow_state=True, status=u[:8], format="sample_bin"))
+    out["rand9_count_vector"] = np.asarray(c.sample(batch=2000, allow_state=True, status=u, format="count_vector"))
+    tc.set_dtype("complex128")
+    c = build(tc, n, ops)
+    out["rand9_sample_int_c128"] = np.asarray(c.sample(batch=2000, allow_state=True, status=u, format="sample_int"))
+    out["rand9_probability_c128"] = np.asarray(c.probability())
+    tc.set_dtype("complex64")
+    # ---- every gate name -----------------------------------------------------------------------
+    c = build(tc, 4, ALL_GATES)
+    out["allgates_state"] = np.asarray(c.wavefunction())
+    inp = np.random.default_rng(7).normal(size=16) + 1j * np.random.default_rng(8).normal(size=16)
+    inp /= np.linalg.norm(inp)
+    out["allgates_inputs"] = inp
+    c = build(tc, 4, ALL_GATES, inputs=inp)
+    out["allgates_state_inputs"] = np.asarray(c.wavefunction())
+    out["allgates_exp_x0z2"] = np.asarray(c.expectation_ps(x=[0], z=[2]))
+    out["allgates_exp_y1y3"] = np.asarray(c.expectation_ps(y=[1, 3]))
+    op2 = np.random.default_rng(9).normal(size=(4, 4)) + 1j * np.random.default_rng(10).normal(size=(4, 4))
+    out["allgates_op2"] = op2
+    out["allgates_exp_op2_q12"] = np.asarray(c.expectation((op2.reshape(2, 2, 2, 2).astype(np.complex64), [1, 2]), (tc.gates.z(), [0])))
+    # complex gate parameter (non-unitary), tests/test_circuit.py:343-352
+    c = tc.Circuit(2)
+    c.rx(0, theta=0.8 + 0.7j)
+    c.rzz(0, 1, theta=-0.2j)
+    out["complex_param_state"] = np.asarray(c.wavefunction())
+    # unitary-as-input form, tests/test_circuit.py:404-412
+    c = tc.Circuit(2, inputs=np.eye(4))
+    c.rx(0, theta=0.3)
+    c.cnot(0, 1)
+    out["unitary_inputs_state"] = np.asarray(c.wavefunction())
+    # ---- numpy-backend vmap values (numpy_backend.py:394-418) --------------------------------------
+    K = tc.backend
+
+    def f(theta):
+        c = tc.Circuit(3)
+        c.rx(0, theta=theta[0])
+        c.ry(1, theta=theta[1])
+        c.cnot(0, 2)
+        c.rzz(1, 2, theta=theta[2] * 0.5)
+        return K.real(c.expectation_ps(z=[2]) + 2.0 * c.expectation_ps(x=[1], z=[0]))
+
+    th = np.random.default_rng(0).uniform(0, 2, size=(5, 3))
+    out["vmap_theta"] = th
+    out["vmap_values"] = np.asarray(K.vmap(f, vectorized_argnums=0)(th))
+    path = os.path.join(ROOT, "tests", "golden", "ref_fixtures.npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s (%d arrays, %.1f KiB)" % (path, len(out), os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()

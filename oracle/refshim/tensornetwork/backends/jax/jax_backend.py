@@ -1,0 +1,8 @@
+from ..abstract_backend import AbstractBackend
+
+
+class JaxBackend(AbstractBackend):
+    """placeholder: only the numpy backend is functional in the shim"""
+
+    def __init__(self, *a, **k):
+        raise ImportError("jax backend is not available in the tensornetwork shim")

@@ -7,14 +7,20 @@ It is NOT part of the product: only ``tests/``, ``__graft_entry__.smoke()`` and 
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The engine in
 ``tensorcircuit_b200/`` never imports it and has no CPU path.
 
-Pinning status (see tests/test_oracle_golden.py, tests/golden/):
-  * conventions (bit order, gate axes, Pauli signs, gate matrices, sample formats) are pinned
-    against the golden values the reference's own test-suite holds
+Pinning status:
+  * tests/test_oracle_golden.py -- conventions (bit order, gate axes, Pauli signs, gate
+    matrices, sample formats) against the golden values the reference's own test-suite holds
     (/root/reference/tests/test_circuit.py, test_gates.py, test_quantum.py, test_miscs.py,
     test_backends.py, test_templates.py -- each golden test cites the line it transcribes);
-  * exact sample indices for given ``status`` uniforms are NOT pinned by any reference test
-    ("parity unpinned" for that one quantity): the contract restated here is the code at
-    tensorcircuit/backends/abstract_backend.py:1124-1157.
+  * tests/test_ref_fixtures.py -- against OUTPUTS OF THE REFERENCE ITSELF: tests/golden/
+    ref_fixtures.npz is produced by oracle/make_golden.py, which runs the reference's own
+    gates.py / abstractcircuit.py / basecircuit.py / circuit.py / quantum.py / backends from
+    /root/reference unmodified (only the un-vendored tensornetwork / opt_einsum / graphviz
+    imports are served by the stand-ins in oracle/refshim/).  Amplitudes (complex64 and
+    complex128), expectation_ps, general-operator expectations, every gate name, sample
+    formats, numpy-backend vmap -- and the sample indices for given ``status`` uniforms,
+    which no reference test pins: the oracle reproduces them bit for bit (float32 CDF for
+    complex64 states, float64 for complex128, abstract_backend.py:1124-1157).
 The arithmetic of the reference lives in un-vendored third-party packages
 (tensornetwork==0.4.6 per requirements/requirements-docker-v2.txt:7, opt_einsum, numpy/jax);
 their published semantics (tensordot of the shared axes, transpose on reorder_edges) are what

@@ -681,12 +681,16 @@ TCB_HD void expect_tile_terms(const C* tile, uint32_t tsz, int nterms, const uin
                     re = a.x * b.x + a.y * b.y;
                     im = a.x * b.y - a.y * b.x;
                 }
+#if defined(__CUDA_ARCH__)
+                const uint32_t par = (uint32_t)__popc(e & sl[t]);
+#else
                 uint32_t par = e & sl[t];
                 par ^= par >> 16;
                 par ^= par >> 8;
                 par ^= par >> 4;
                 par ^= par >> 2;
                 par ^= par >> 1;
+#endif
                 if (par & 1u) {
                     re = -re;
                     im = -im;

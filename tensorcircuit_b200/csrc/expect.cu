@@ -30,7 +30,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 template <typename Real>
-__global__ void __launch_bounds__(256) expect_kernel(const __grid_constant__ ExpectParams p) {
+__global__ void __launch_bounds__(256, 4) expect_kernel(const __grid_constant__ ExpectParams p) {
     using C = typename CT<Real>::type;
     constexpr int MT = TCB200_MAX_TERMS;
     extern __shared__ __align__(128) unsigned char smem_raw[];

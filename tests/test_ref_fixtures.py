@@ -1,0 +1,165 @@
+"""Golden vectors produced by the REFERENCE's own code (tests/golden/ref_fixtures.npz, generated
+by oracle/make_golden.py: reference modules run unmodified from /root/reference, their
+un-vendored tensornetwork / opt_einsum dependency replaced by oracle/refshim).
+
+They pin (i) the oracle and (ii) the engine -- on the CPU through the kernel emulation
+(``emu``) and on the GPU through the C ABI (``cuda``, ``-m gpu``).  Nothing here reads
+/root/reference at run time."""
+
+import os
+
+import numpy as np
+import pytest
+
+import tensorcircuit_b200 as tc
+from oracle import tc_oracle as orc
+
+from .test_circuit_api import eng  # noqa: F401  (fixture: emu on CPU, cuda under -m gpu)
+
+FIX = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fixtures.npz"))
+
+# the same gate list oracle/make_golden.py fed to the reference
+ALL_GATES = [
+    ("h", (0,), {}), ("x", (1,), {}), ("y", (2,), {}), ("z", (3,), {}), ("t", (0,), {}), ("s", (1,), {}), ("td", (2,), {}), ("sd", (3,), {}),
+    ("wroot", (0,), {}), ("cnot", (0, 1), {}), ("cz", (1, 2), {}), ("swap", (2, 3), {}), ("cy", (3, 0), {}), ("ox", (0, 2), {}), ("oy", (1, 3), {}),
+    ("oz", (2, 0), {}), ("toffoli", (0, 1, 2), {}), ("fredkin", (3, 1, 0), {}),
+    ("r", (0,), dict(theta=0.3, alpha=1.1, phi=-0.7)), ("cr", (1, 2), dict(theta=0.3, alpha=1.1, phi=-0.7)), ("u", (3,), dict(theta=0.4, phi=0.5, lbd=-1.2)),
+    ("cu", (0, 3), dict(theta=0.4, phi=0.5, lbd=-1.2)), ("rx", (1,), dict(theta=0.6)), ("ry", (2,), dict(theta=0.7)), ("rz", (3,), dict(theta=0.8)),
+    ("phase", (0,), dict(theta=0.9)), ("rxx", (0, 1), dict(theta=0.25)), ("ryy", (1, 2), dict(theta=0.35)), ("rzz", (2, 3), dict(theta=0.45)),
+    ("cphase", (3, 1), dict(theta=0.55)), ("crx", (0, 2), dict(theta=0.65)), ("cry", (1, 3), dict(theta=0.75)), ("crz", (2, 0), dict(theta=0.85)),
+    ("orx", (3, 2), dict(theta=0.15)), ("ory", (0, 1), dict(theta=0.22)), ("orz", (1, 0), dict(theta=0.33)), ("iswap", (2, 3), dict(theta=0.4)),
+    ("cx", (3, 2), {}), ("cswap", (0, 2, 3), {}), ("ccnot", (1, 2, 0), {}), ("sdg", (1,), {}), ("tdg", (2,), {}),
+]
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b))
+
+
+def _hea10():
+    n = 10
+    params = np.random.default_rng(0).uniform(0, 2 * np.pi, size=[4, 2, n])
+    return n, orc.hea_circuit(n, params), [list(map(int, r)) for r in FIX["hea10_pss"]]
+
+
+def _sample_ok(got, ref_idx, probs, u):
+    """identical indices, except where the uniform sits on a CDF tie (|CDF - r| tiny)"""
+    cdf = np.cumsum(np.asarray(probs, dtype=np.float64) / np.sum(probs, dtype=np.float64))
+    r = cdf[-1] * (1 - u)
+    bad = np.nonzero(np.asarray(got) != np.asarray(ref_idx))[0]
+    for i in bad:
+        lo = min(int(got[i]), int(ref_idx[i]))
+        assert abs(cdf[lo] - r[i]) < 3e-7, (i, got[i], ref_idx[i])  # float32 CDF resolution of the reference
+    return len(bad)
+
+
+# ---- the oracle against the reference's outputs -------------------------------------------------
+def test_oracle_vs_reference_outputs():
+    n, ops, pss = _hea10()
+    o = orc.run_gatelist(n, ops)
+    assert _rel(o.state(), FIX["hea10_state_complex128"]) < 1e-13
+    assert _rel(o.state(), FIX["hea10_state_complex64"]) < 2e-6
+    exps = np.array([o.expectation_ps(ps=ps) for ps in pss])
+    np.testing.assert_allclose(exps, FIX["hea10_exps_complex128"], atol=1e-13)
+    np.testing.assert_allclose(exps, FIX["hea10_exps_complex64"], atol=2e-6)
+    o = orc.run_gatelist(9, orc.random_circuit(9, 6, seed=3))
+    assert _rel(o.state(), FIX["rand9_state"]) < 2e-6
+    np.testing.assert_allclose(o.probability(), FIX["rand9_probability_c128"], atol=1e-14)
+    u = FIX["rand9_status"]
+    # complex128 reference: float64 CDF -> the oracle's rule must give identical indices
+    np.testing.assert_array_equal(orc.probability_sample(o.probability(), u), FIX["rand9_sample_int_c128"])
+    # complex64 reference: float32 CDF; identical when the oracle runs the rule in float32 on
+    # the reference's own float32 probabilities
+    p32 = (np.abs(FIX["rand9_state"]) ** 2).astype(np.float32)
+    np.testing.assert_array_equal(orc.probability_sample(p32, u, dtype=np.float32), FIX["rand9_sample_int"])
+    assert _sample_ok(orc.probability_sample(o.probability(), u), FIX["rand9_sample_int"], o.probability(), u) < 20
+    np.testing.assert_array_equal(orc.sample2all(FIX["rand9_sample_int"], 9, "count_vector"), FIX["rand9_count_vector"])
+    np.testing.assert_array_equal(orc.sample_int2bin(FIX["rand9_sample_int"][:8], 9), FIX["rand9_sample_bin_head"])
+    o = orc.run_gatelist(4, ALL_GATES)
+    assert _rel(o.state(), FIX["allgates_state"]) < 2e-6
+    o = orc.run_gatelist(4, ALL_GATES, inputs=FIX["allgates_inputs"])
+    assert _rel(o.state(), FIX["allgates_state_inputs"]) < 2e-6
+    np.testing.assert_allclose(o.expectation_ps(x=[0], z=[2]), FIX["allgates_exp_x0z2"], atol=2e-6)
+    np.testing.assert_allclose(o.expectation_ps(y=[1, 3]), FIX["allgates_exp_y1y3"], atol=2e-6)
+    np.testing.assert_allclose(o.expectation((FIX["allgates_op2"], [1, 2]), (orc.Z, [0])), FIX["allgates_exp_op2_q12"], atol=1e-5)
+    c = orc.OracleCircuit(2)
+    c.rx(0, theta=0.8 + 0.7j)
+    c.rzz(0, 1, theta=-0.2j)
+    assert _rel(c.state(), FIX["complex_param_state"]) < 2e-6
+    c = orc.OracleCircuit(2, inputs=np.eye(4))
+    c.rx(0, theta=0.3)
+    c.cnot(0, 1)
+    assert _rel(c.state(), FIX["unitary_inputs_state"]) < 2e-6
+
+
+# ---- the engine against the reference's outputs ----------------------------------------------------
+def _build(n, ops, **kw):
+    c = tc.Circuit(n, **kw)
+    for name, q, p in ops:
+        getattr(c, name)(*q, **p)
+    return c
+
+
+@pytest.mark.parametrize("dtype,tol", [("complex64", 1e-5), ("complex128", 1e-11)])
+def test_engine_config1_vs_reference(eng, dtype, tol):  # noqa: F811
+    tc.set_dtype(dtype)
+    n, ops, pss = _hea10()
+    c = _build(n, ops)
+    assert _rel(c.state(), FIX["hea10_state_" + dtype]) < tol
+    want = FIX["hea10_exps_" + dtype]
+    got = np.asarray(c.expectation_ps_many(pss))
+    assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3 * len(pss))) < tol
+    tc.set_dtype("complex64")
+
+
+def test_engine_sampler_vs_reference(eng):  # noqa: F811
+    n = 9
+    c = _build(n, orc.random_circuit(n, 6, seed=3))
+    assert _rel(c.state(), FIX["rand9_state"]) < 1e-5
+    u = FIX["rand9_status"]
+    got = c.sample(batch=len(u), allow_state=True, status=u, format="sample_int")
+    nbad = _sample_ok(got, FIX["rand9_sample_int"], np.abs(FIX["rand9_probability_c128"]), u)
+    assert nbad < 20
+    np.testing.assert_array_equal(c.sample(batch=8, allow_state=True, status=u[:8], format="sample_bin"), FIX["rand9_sample_bin_head"])
+    cv = c.sample(batch=len(u), allow_state=True, status=u, format="count_vector")
+    assert np.sum(np.abs(cv - FIX["rand9_count_vector"])) <= 2 * nbad
+    tc.set_dtype("complex128")
+    c = _build(n, orc.random_circuit(n, 6, seed=3))
+    got = c.sample(batch=len(u), allow_state=True, status=u, format="sample_int")
+    assert _sample_ok(got, FIX["rand9_sample_int_c128"], FIX["rand9_probability_c128"], u) <= 2
+    np.testing.assert_allclose(c.probability(), FIX["rand9_probability_c128"], atol=1e-13)
+    tc.set_dtype("complex64")
+
+
+def test_engine_all_gates_vs_reference(eng):  # noqa: F811
+    c = _build(4, ALL_GATES)
+    assert _rel(c.state(), FIX["allgates_state"]) < 1e-5
+    c = _build(4, ALL_GATES, inputs=FIX["allgates_inputs"])
+    assert _rel(c.state(), FIX["allgates_state_inputs"]) < 1e-5
+    np.testing.assert_allclose(c.expectation_ps(x=[0], z=[2]), FIX["allgates_exp_x0z2"], atol=1e-5)
+    np.testing.assert_allclose(c.expectation_ps(y=[1, 3]), FIX["allgates_exp_y1y3"], atol=1e-5)
+    got = c.expectation((FIX["allgates_op2"].reshape(2, 2, 2, 2), [1, 2]), (tc.gates.z(), [0]))
+    np.testing.assert_allclose(got, FIX["allgates_exp_op2_q12"], atol=2e-5)
+    c = tc.Circuit(2)
+    c.rx(0, theta=0.8 + 0.7j)
+    c.rzz(0, 1, theta=-0.2j)
+    assert _rel(c.state(), FIX["complex_param_state"]) < 1e-5
+    c = tc.Circuit(2, inputs=np.eye(4))
+    c.rx(0, theta=0.3)
+    c.cnot(0, 1)
+    assert _rel(c.state(), FIX["unitary_inputs_state"]) < 1e-5
+
+
+def test_engine_vmap_vs_reference(eng):  # noqa: F811
+    K = tc.backend
+
+    def f(theta):
+        c = tc.Circuit(3)
+        c.rx(0, theta=theta[0])
+        c.ry(1, theta=theta[1])
+        c.cnot(0, 2)
+        c.rzz(1, 2, theta=theta[2] * 0.5)
+        return K.real(c.expectation_ps(z=[2]) + 2.0 * c.expectation_ps(x=[1], z=[0]))
+
+    got = K.vmap(f, vectorized_argnums=0)(FIX["vmap_theta"])
+    np.testing.assert_allclose(got, FIX["vmap_values"], atol=1e-5)
