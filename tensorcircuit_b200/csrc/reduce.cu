@@ -243,14 +243,21 @@ __global__ void __launch_bounds__(256) sample_search_kernel(const typename CT<Re
     const C* blk = state + (b << B);
     const uint32_t bs = 1u << B;
     int64_t found = -1;
-    for (uint32_t i0 = 0; i0 < bs; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        double p = 0.0;
-        if (i < bs) {
-            const C c = blk[i];
-            p = (double)c.x * (double)c.x + (double)c.y * (double)c.y;
+    // 4 consecutive amplitudes per lane and iteration (128 per warp step): one warp scan per 128
+    // amplitudes, then the owning lane resolves its 4 entries
+    for (uint32_t i0 = 0; i0 < bs; i0 += 128) {
+        const uint32_t i = i0 + 4u * lane;
+        double p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            p[j] = 0.0;
+            if (i + j < bs) {
+                const C c = blk[i + j];
+                p[j] = (double)c.x * (double)c.x + (double)c.y * (double)c.y;
+            }
         }
-        double inc = p;
+        const double s = (p[0] + p[1]) + (p[2] + p[3]);
+        double inc = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const double t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -259,7 +266,20 @@ __global__ void __launch_bounds__(256) sample_search_kernel(const typename CT<Re
         const double cum = start + inc;
         const unsigned m = __ballot_sync(0xffffffffu, (cum >= r) && (i < bs));
         if (m) {
-            found = (int64_t)((b << B) + i0 + (__ffs(m) - 1));
+            const int L = __ffs(m) - 1;
+            int64_t mine = -1;
+            if (lane == L) {
+                double run = cum - s;  // mass before this lane's first entry
+                int j = 0;
+                for (; j < 3; ++j) {
+                    run += p[j];
+                    if (run >= r) break;
+                }
+                uint32_t idx = i + (uint32_t)j;
+                if (idx >= bs) idx = bs - 1;
+                mine = (int64_t)((b << B) + idx);
+            }
+            found = __shfl_sync(0xffffffffu, mine, L);
             break;
         }
         start = __shfl_sync(0xffffffffu, cum, 31);
