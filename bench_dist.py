@@ -106,7 +106,7 @@ def run_dist(args, tc, rank, world, local):
             "dtype": "c64", "data": "synthetic",
             "config": dict(workload_config(world, n, args.depth, shots), recorded_gates=ngates, fused_blocks=len(blocks),
                            shard_gib=shard_bytes / 2**30, exchange="double-buffered all_to_all" if shard_bytes * 2 < 150 * 2**30 else "chunked all_to_all through staging"),
-            "roofline": {"bound": "hbm", "kernel": "dense_kernel (local passes between remaps)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "cpass_kernel (staged local passes between remaps)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": None},
             "remap": {"per_step": stats["remaps"] / args.steps, "bytes_per_rank_per_remap": (stats["remap_bytes"] / stats["remaps"]) if stats["remaps"] else 0,
                       "ms_per_remap": (stats["remap_ms"] / stats["remaps"]) if stats["remaps"] else 0, "nvlink_gbs_per_direction": remap_gbs,

@@ -11,7 +11,9 @@ oracle/refshim/.  The fixtures pin, with outputs of the reference itself:
     config-4 random-circuit recipe at n = 9, and of a circuit that uses every gate name;
   * expectation_ps of the TFIM strings + random strings, and expectation of general operators;
   * sample(allow_state=True, status=u) indices -- the one quantity no reference test pins;
-  * sample formats and numpy-backend vmap values.
+  * sample formats and numpy-backend vmap values;
+  * Monte-Carlo noise trajectories (depolarizing / amplitudedamping / phasedamping / reset /
+    cond_measure / unitary_kraus / mid_measurement) driven by fixed ``status`` values.
 """
 
 import os
@@ -113,6 +115,24 @@ def main():
     th = np.random.default_rng(0).uniform(0, 2, size=(5, 3))
     out["vmap_theta"] = th
     out["vmap_values"] = np.asarray(K.vmap(f, vectorized_argnums=0)(th))
+    # ---- Monte-Carlo trajectories with fixed status (circuit.py:473-744, basecircuit.py:824-857) ---
+    n = 5
+    rng = np.random.default_rng(21)
+    ntraj = 12
+    st = rng.random((ntraj, orc.NOISY_STATUS_LEN(n)))
+    th = rng.uniform(0, 2 * np.pi, size=(ntraj, 2 * n))
+    out["traj_status"] = st
+    out["traj_theta"] = th
+    for dt in ("complex64", "complex128"):
+        tc.set_dtype(dt)
+        states, picks = [], []
+        for t in range(ntraj):
+            c = tc.Circuit(n)
+            picks.append(orc.noisy_trajectory(c, n, st[t], th[t]))
+            states.append(np.asarray(c.wavefunction()))
+        out["traj_states_" + dt] = np.array(states)
+        out["traj_picks_" + dt] = np.array(picks)
+    tc.set_dtype("complex64")
     path = os.path.join(ROOT, "tests", "golden", "ref_fixtures.npz")
     np.savez_compressed(path, **out)
     print("wrote %s (%d arrays, %.1f KiB)" % (path, len(out), os.path.getsize(path) / 1024))

@@ -102,6 +102,24 @@ class Node(AbstractNode):
     def __rmul__(self, lvalue):
         return Node(lvalue * self.tensor)
 
+    # elementwise arithmetic of tn.Node (network_components.py of tensornetwork 0.4.x:
+    # __add__ / __sub__ / __mul__ / __truediv__ act on the tensors, result is a fresh Node)
+    @staticmethod
+    def _other(o):
+        return o.tensor if isinstance(o, Node) else o
+
+    def __add__(self, other):
+        return Node(self.tensor + Node._other(other))
+
+    def __sub__(self, other):
+        return Node(self.tensor - Node._other(other))
+
+    def __mul__(self, other):
+        return Node(self.tensor * Node._other(other))
+
+    def __truediv__(self, other):
+        return Node(self.tensor / Node._other(other))
+
 
 class CopyNode(Node):
     pass

@@ -366,6 +366,102 @@ class OracleCircuit:
     def sample_int(self, status: Sequence[float]) -> np.ndarray:
         return probability_sample(self.probability(), status)
 
+    # -- Monte-Carlo trajectories (circuit.py:302-352, 473-744; basecircuit.py:824-857) -------
+    def mid_measurement(self, index: int, keep: int = 0) -> int:  # circuit.py:302-347, no renorm
+        proj = np.zeros((2, 2), dtype=CDT)
+        proj[keep, keep] = 1.0
+        self.psi = apply_gate(self.psi, proj, [index], self.ntot)
+        return keep
+
+    def unitary_kraus(self, kraus: Sequence[Any], *index: int, prob=None, status: float = 0.0) -> int:
+        """circuit.py:473-565: the branch is floor-counted by the sign sum of 538-548."""
+        ks = [_as_matrix(k) for k in kraus]
+        if prob is None:
+            prob = [float(np.real(np.trace(k.conj().T @ k)) / k.shape[0]) for k in ks]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                ks = [k / np.sqrt(w + 0j) for k, w in zip(ks, prob)]
+        cum = np.cumsum(np.real(np.asarray(prob, dtype=np.float64)))
+        l = len(ks)
+        r = int(sum(np.sign(status - cum[i]) for i in range(l - 1)) / 2.0 + (l - 1) / 2.0)
+        self.psi = apply_gate(self.psi, ks[r], list(index), self.ntot)
+        return r
+
+    def general_kraus(self, kraus: Sequence[Any], *index: int, status: float = 0.0, with_prob: bool = False):
+        """circuit.py:635-723: p_i = <K_i^dag K_i>, branch K_i / (sqrt(p_i) + 1e-10)."""
+        ks = [_as_matrix(k) for k in kraus]
+        prob = [float(np.real(self.expectation((k.conj().T @ k, list(index))))) for k in ks]
+        new = [k / (np.sqrt(w) + 1e-10) for k, w in zip(ks, prob)]
+        r = self.unitary_kraus(new, *index, prob=prob, status=status)
+        return (r, prob) if with_prob else r
+
+    def cond_measure(self, index: int, status: float = 0.0) -> int:  # basecircuit.py:824-857
+        return self.general_kraus([np.diag([1.0, 0.0]), np.diag([0.0, 1.0])], index, status=status)
+
+    # c.depolarizing / amplitudedamping / phasedamping / reset (circuit.py:725-744)
+    def depolarizing(self, index: int, *, px: float, py: float, pz: float, status: float = 0.0) -> None:
+        self.unitary_kraus(ch_depolarizing(px, py, pz), index, status=status)
+
+    def amplitudedamping(self, index: int, *, gamma: float, p: float, status: float = 0.0) -> None:
+        self.general_kraus(ch_amplitudedamping(gamma, p), index, status=status)
+
+    def phasedamping(self, index: int, *, gamma: float, status: float = 0.0) -> None:
+        self.general_kraus(ch_phasedamping(gamma), index, status=status)
+
+    def reset(self, index: int, status: float = 0.0) -> None:
+        self.general_kraus(ch_reset(), index, status=status)
+
+
+def noisy_trajectory(c: Any, n: int, status: Sequence[float], theta: Sequence[float]) -> List[int]:
+    """One Monte-Carlo trajectory recipe written against the shared Circuit surface (runs on the
+    reference, on the oracle and on the product): two noisy entangling layers, a cond_measure,
+    a reset, an explicit-prob 2-qubit unitary_kraus and a post-selection.  Returns the picks."""
+    k = 0
+    picks: List[int] = []
+    for layer in range(2):
+        for i in range(n):
+            c.h(i)
+        for i in range(n - 1):
+            c.cnot(i, i + 1)
+        for i in range(n):
+            c.rx(i, theta=theta[layer * n + i])
+            c.depolarizing(i, px=0.1, py=0.05, pz=0.15, status=status[k])
+            c.amplitudedamping(i, gamma=0.3, p=0.8, status=status[k + 1])
+            c.phasedamping(i, gamma=0.2, status=status[k + 2])
+            k += 3
+    picks.append(int(c.cond_measure(1, status=status[k])))
+    c.reset(2, status=status[k + 1])
+    zz = np.kron(Z, Z)
+    xx = np.kron(X, X)
+    picks.append(int(c.unitary_kraus([np.eye(4, dtype=CDT), zz, xx], 0, n - 1, prob=[0.5, 0.3, 0.2], status=status[k + 2])))
+    c.mid_measurement(0, keep=1)
+    return picks
+
+
+NOISY_STATUS_LEN = lambda n: 6 * n + 3  # noqa: E731
+
+
+# Kraus lists of channels.py:56-325 (plain matrices)
+def ch_depolarizing(px: float, py: float, pz: float) -> List[np.ndarray]:
+    return [np.sqrt(1 - px - py - pz + 0j) * I2, np.sqrt(px + 0j) * X, np.sqrt(py + 0j) * Y, np.sqrt(pz + 0j) * Z]
+
+
+def ch_amplitudedamping(gamma: float, p: float) -> List[np.ndarray]:
+    g, s = np.sqrt(gamma + 0j), np.sqrt(1 - gamma + 0j)
+    return [
+        np.sqrt(p + 0j) * np.array([[1, 0], [0, s]]),
+        np.sqrt(p + 0j) * np.array([[0, g], [0, 0]]),
+        np.sqrt(1 - p + 0j) * np.array([[s, 0], [0, 1]]),
+        np.sqrt(1 - p + 0j) * np.array([[0, 0], [g, 0]]),
+    ]
+
+
+def ch_phasedamping(gamma: float) -> List[np.ndarray]:
+    return [np.array([[1, 0], [0, np.sqrt(1 - gamma + 0j)]]), np.array([[0, 0], [0, np.sqrt(gamma + 0j)]])]
+
+
+def ch_reset() -> List[np.ndarray]:
+    return [np.array([[1, 0], [0, 0]], dtype=CDT), np.array([[0, 1], [0, 0]], dtype=CDT)]
+
 
 def resolve_ps(n, x=None, y=None, z=None, ps=None):
     if ps is not None:  # quantum.py:1025-1044

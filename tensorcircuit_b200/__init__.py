@@ -30,6 +30,7 @@ from . import b200_backend as _backend_module  # noqa: F401  binds cons.backend
 from . import gates  # noqa: F401
 from .gates import Gate, array_to_tensor, num_to_tensor  # noqa: F401
 from . import quantum  # noqa: F401
+from . import channels  # noqa: F401
 from .circuit import Circuit, DeviceArray, expectation  # noqa: F401
 from . import templates  # noqa: F401
 from . import engine  # noqa: F401

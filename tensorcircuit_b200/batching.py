@@ -264,6 +264,8 @@ def unwrap(x: Any, batch: int) -> Any:
     """vmap output: stack on axis 0 (tensorcircuit/backends/numpy_backend.py:394-418)."""
     if isinstance(x, BatchArray):
         return x.a
+    if getattr(x, "batched_on_device", False):  # circuit.BatchedDeviceArray: leading axis IS the batch
+        return x
     if isinstance(x, (tuple, list)):
         return type(x)(unwrap(e, batch) for e in x)
     if isinstance(x, dict):

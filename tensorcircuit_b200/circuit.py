@@ -583,9 +583,139 @@ class Circuit:
 
     measure_jit = measure
 
+    # ------------------------------------------------------------------------------------
+    # Monte-Carlo noise trajectories driven by ``status`` (circuit.py:302-352, 447-744,
+    # basecircuit.py:824-857).  Everything O(2^n) goes through the same kernels: a Kraus branch
+    # is one more (possibly non-unitary, possibly vmap-batched) gate; branch probabilities of a
+    # general channel are expectations of K^dagger K on the channel's qubits.
+    # ------------------------------------------------------------------------------------
+    def mid_measurement(self, index: int, keep: int = 0) -> Tensor:
+        """Post-selection on |keep> of qubit ``index``; the state is NOT renormalised
+        (circuit.py:302-347)."""
+        proj = np.zeros((2, 2), dtype=np.complex128)
+        k = 0 if keep < 0.5 else 1
+        proj[k, k] = 1.0
+        self.any(index, unitary=proj, name="post-select")
+        return np.asarray(keep).astype("int32")
+
+    mid_measure = mid_measurement
+    post_select = mid_measurement
+    post_selection = mid_measurement
+
+    def unitary_kraus(self, kraus: Sequence[Any], *index: int, prob: Optional[Sequence[float]] = None,
+                      status: Optional[float] = None, name: Optional[str] = None) -> Tensor:
+        """Apply one of ``kraus`` chosen by ``status`` against the cumulative ``prob``
+        (circuit.py:473-565).  ``status`` / ``prob`` may be vmap-batched."""
+        mats = [gates.reshapem(k.tensor if isinstance(k, Gate) else k) for k in kraus]
+        mats = [m if is_batched(m) else np.asarray(m, dtype=np.complex128) for m in mats]
+        if prob is None:
+            prob = []
+            for m in mats:
+                a = m.a if is_batched(m) else m
+                w = np.real(np.einsum("...ij,...ij->...", a.conj(), a)) / a.shape[-1]
+                prob.append(BatchArray(w) if is_batched(m) else w)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                mats = [
+                    BatchArray(m.a / np.sqrt(p.a + 0j)[:, None, None]) if is_batched(m) else m / np.sqrt(p + 0j)
+                    for m, p in zip(mats, prob)
+                ]
+        l = len(mats)
+        if status is None:
+            status = cons.backend.implicit_randu()[0]
+        status = np.real(status) if not is_batched(status) else status.real
+        B = batch_of(status, *prob, *mats)
+        # cumulative probabilities; the step function of circuit.py:538-548:
+        #   r = int( sum_{i<l-1} sign(status - cum_i) / 2 + (l-1)/2 )
+        def raw(x: Any) -> np.ndarray:
+            return x.a if is_batched(x) else np.asarray(x)
+
+        pr = [np.real(raw(p)).astype(np.float64) for p in prob]
+        if B is not None:
+            pr = [np.broadcast_to(p, (B,)) for p in pr]
+        cum = np.cumsum(np.stack(pr, axis=-1), axis=-1)  # [l] or [B, l]
+        st = np.asarray(raw(status), dtype=np.float64)
+        if l == 1:
+            r = np.zeros(st.shape, dtype=np.int32)
+        else:
+            r = (np.sum(np.sign(st[..., None] - cum[..., : l - 1]), axis=-1) / 2.0 + (l - 1) / 2.0).astype(np.int32)
+        if B is None:
+            g = mats[int(r)]
+            self.any(*index, unitary=g, name=name if name is not None else "unitary_kraus")
+            return np.asarray(r)
+        stack = np.stack([np.broadcast_to(raw(m), (B,) + tuple(raw(m).shape[-2:])) for m in mats], axis=1)  # [B, l, d, d]
+        rb = np.broadcast_to(r, (B,))
+        g = stack[np.arange(B), rb]
+        self.any(*index, unitary=BatchArray(g), name=name if name is not None else "unitary_kraus")
+        return BatchArray(rb.astype(np.int32))
+
+    unitary_kraus2 = unitary_kraus
+
+    def general_kraus(self, kraus: Sequence[Any], *index: int, status: Optional[float] = None,
+                      with_prob: bool = False, name: Optional[str] = None) -> Tensor:
+        """Monte-Carlo trajectory step of a general Kraus channel (circuit.py:635-723): branch
+        probabilities p_i = <psi| K_i^dagger K_i |psi> on the current state, then the branch chosen
+        by ``status`` is applied as K_i / (sqrt(p_i) + 1e-10)."""
+        mats = [np.asarray(gates.reshapem(k.tensor if isinstance(k, Gate) else k), dtype=np.complex128) for k in kraus]
+        prob = []
+        for m in mats:
+            kk = m.conj().T @ m
+            prob.append(np.real(self.expectation((kk, list(index)))))
+        eps = 1e-10
+        new = []
+        for m, w in zip(mats, prob):
+            if is_batched(w):
+                new.append(BatchArray(m[None, :, :] / (np.sqrt(w.a)[:, None, None] + eps)))
+            else:
+                new.append(m / (np.sqrt(w) + eps))
+        pick = self.unitary_kraus(new, *index, prob=prob, status=status, name=name)
+        return (pick, prob) if with_prob else pick
+
+    apply_general_kraus = general_kraus
+
+    def cond_measurement(self, index: int, status: Optional[float] = None) -> Tensor:
+        """Z-basis measurement with collapse, returning the outcome (basecircuit.py:824-857)."""
+        return self.general_kraus([np.array([[1.0, 0], [0, 0]]), np.array([[0, 0], [0, 1.0]])], index, status=status, name="measure")
+
+    cond_measure = cond_measurement
+
+    def conditional_gate(self, which: Tensor, kraus: Sequence[Any], *index: int) -> None:
+        """Apply ``kraus[which]`` (abstractcircuit.py conditional_gate); ``which`` may be batched."""
+        mats = [np.asarray(gates.reshapem(k.tensor if isinstance(k, Gate) else k), dtype=np.complex128) for k in kraus]
+        if is_batched(which):
+            sel = np.stack(mats)[which.a.astype(np.int64)]
+            self.any(*index, unitary=BatchArray(sel), name="conditional")
+        else:
+            self.any(*index, unitary=mats[int(which)], name="conditional")
+
+    def depolarizing2(self, index: int, *, px: float, py: float, pz: float, status: Optional[float] = None) -> float:
+        """circuit.py:354-386: x / y / z / i chosen by status against px, px+py, px+py+pz."""
+        ks = [gates._x_matrix, gates._y_matrix, gates._z_matrix, gates._i_matrix]
+        self.unitary_kraus(ks, index, prob=[px, py, pz, 1 - px - py - pz], status=status)
+        return 0.0
+
+    @staticmethod
+    def apply_general_kraus_delayed(krausf: Callable[..., Sequence[Gate]], is_unitary: bool = False) -> Callable[..., None]:
+        def apply(self: "Circuit", *index: int, status: Optional[float] = None, name: Optional[str] = None, **vars: float) -> None:
+            kraus = krausf(**vars)
+            if not is_unitary:
+                self.apply_general_kraus(kraus, *index, status=status, name=name)
+            else:
+                self.unitary_kraus(kraus, *index, status=status, name=name)
+
+        return apply
+
+    @classmethod
+    def _meta_apply_channels(cls) -> None:
+        from . import channels as _ch
+
+        for k in _ch.channels:
+            setattr(cls, k, cls.apply_general_kraus_delayed(getattr(_ch, k + "channel"), is_unitary=k in ("depolarizing", "generaldepolarizing")))
+
 
 class BatchedDeviceArray(DeviceArray):
     """vmap result that stays on the device: leading axis is the batch axis."""
+
+    batched_on_device = True
 
 
 _PAULIS = [np.eye(2), np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.diag([1.0, -1.0])]
@@ -611,6 +741,7 @@ def _pauli_decompose(m: Any, k: int) -> List[Tuple[Any, Tuple[int, ...]]]:
 
 
 Circuit._meta_apply()
+Circuit._meta_apply_channels()
 
 
 def expectation(*ops: Tuple[Any, List[int]], ket: Tensor, bra: Optional[Tensor] = None, conj: bool = True, normalization: bool = False) -> Tensor:

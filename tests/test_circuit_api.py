@@ -641,3 +641,155 @@ def test_planned_passes_small_tiles(eng, kf, monkeypatch):
             if len(blocks[i].bits) <= 4:
                 assert all(q < lrow or q in p.tile_hi for q in blocks[i].bits)
     assert len(passes) < len(blocks)
+
+
+# ---- Monte-Carlo trajectories (tests/test_circuit.py:120-230, 393-401, 772-796, 1439-1446, 1596-1643)
+def test_jittable_depolarizing(eng):
+    # tests/test_circuit.py:120-230: five spellings of a depolarizing trajectory keep the norm
+    n = 5
+    K = tc.backend
+
+    def pre():
+        c = tc.Circuit(n)
+        for i in range(n):
+            c.H(i)
+        for i in range(n):
+            c.cnot(i, (i + 1) % n)
+        return c
+
+    def f1():
+        c = pre()
+        for i in range(n):
+            c.unitary_kraus([tc.gates._x_matrix, tc.gates._y_matrix, tc.gates._z_matrix, tc.gates._i_matrix], i, prob=[0.2, 0.2, 0.2, 0.4])
+        for i in range(n):
+            c.cz(i, (i + 1) % n)
+        return c.wavefunction()
+
+    def f2():
+        c = pre()
+        for i in range(n):
+            c.unitary_kraus(tc.channels.depolarizingchannel(0.2, 0.2, 0.2), i)
+        return c.wavefunction()
+
+    def f3():
+        c = pre()
+        for i in range(n):
+            c.depolarizing(i, px=0.2, py=0.2, pz=0.2)
+        return c.wavefunction()
+
+    def f4():
+        c = pre()
+        for i in range(n):
+            c.depolarizing2(i, px=0.2, py=0.2, pz=0.2)
+        return c.wavefunction()
+
+    def f5():
+        c = pre()
+        for i in range(n):
+            c.unitary_kraus2(tc.channels.depolarizingchannel(0.2, 0.2, 0.2), i)
+        return c.wavefunction()
+
+    for f in [f1, f2, f3, f4, f5]:
+        K.set_random_state(23)
+        np.testing.assert_allclose(K.norm(K.jit(f)()), 1.0, atol=1e-4)
+        np.testing.assert_allclose(K.norm(K.jit(f)()), 1.0, atol=1e-4)
+
+
+def test_postselection(eng):
+    # tests/test_circuit.py:393-401
+    c = tc.Circuit(3)
+    c.H(1)
+    c.H(2)
+    c.mid_measurement(1, 1)
+    c.mid_measurement(2, 1)
+    s = c.wavefunction()
+    np.testing.assert_allclose(A(s[3]).real, 0.5, atol=1e-6)
+
+
+def test_teleportation(eng):
+    # tests/test_circuit.py:772-796
+    tc.backend.set_random_state(42)
+    for _ in range(6):
+        c = tc.Circuit(2)
+        c.H(0)
+        r = c.cond_measurement(0)
+        c.conditional_gate(r, [tc.gates.i(), tc.gates.x()], 1)
+        e = c.expectation([tc.gates.z(), [1]])
+        np.testing.assert_allclose(e, -1 if A(r) > 0.5 else 1, atol=1e-5)
+
+
+def test_channel_auto_register(eng, highp):
+    # tests/test_circuit.py:1439-1446
+    c = tc.Circuit(2)
+    c.H(0)
+    c.reset(0, status=0.8)
+    s = c.state()
+    np.testing.assert_allclose(A(s[0]), 1.0, atol=1e-9)
+
+
+def test_general_kraus_with_prob(eng):
+    # tests/test_circuit.py:1596-1643
+    c = tc.Circuit(2)
+    c.h([0, 1])
+    p = 0.5
+    status = [0.3, 0.8]
+    rs = []
+    for i in range(2):
+        ks = [np.sqrt(p) * np.array([[1.0, 0], [0, 0]]), np.sqrt(p) * np.array([[0, 0], [0, 1.0]]), np.sqrt(1 - p) * np.eye(2)]
+        rs.append(c.general_kraus(ks, i, status=status[i], with_prob=True))
+    np.testing.assert_allclose(rs[0][0], 1)
+    np.testing.assert_allclose(rs[1][0], 2)
+    np.testing.assert_allclose(c.expectation_ps(z=[0]), -1, atol=1e-5)
+    np.testing.assert_allclose(c.expectation_ps(z=[1]), 0, atol=1e-5)
+    np.testing.assert_allclose(A(rs[0][1]), [0.25, 0.25, 0.5], atol=1e-5)
+    np.testing.assert_allclose(A(rs[1][1]), [0.25, 0.25, 0.5], atol=1e-5)
+    np.testing.assert_allclose(tc.backend.norm(c.state()), 1, atol=1e-5)
+
+
+def test_channel_identity(eng):
+    # tests/test_channels.py:24-48: every registered channel is trace preserving
+    ch = tc.channels
+    for ks in [ch.depolarizingchannel(0.1, 0.2, 0.3), ch.amplitudedampingchannel(0.25, 0.3), ch.phasedampingchannel(0.6), ch.resetchannel(),
+               ch.generaldepolarizingchannel(0.02, 2), ch.isotropicdepolarizingchannel(0.3, 2), ch.generaldepolarizingchannel([0.1, 0.2, 0.3], 1)]:
+        ch.kraus_identity_check(ks)
+
+
+def test_depolarizing_trajectory_average(eng, highp):
+    # the trajectory average reproduces the channel: E_status[|psi><psi|] = sum_k K rho K^dag
+    # (tests/test_channels.py:100-135 checks the same through the density-matrix simulator)
+    n, nt = 3, 400
+    K = tc.backend
+
+    def f(status):
+        c = tc.Circuit(n)
+        c.h(0)
+        c.cnot(0, 1)
+        c.ry(2, theta=0.7)
+        c.depolarizing(1, px=0.1, py=0.2, pz=0.3, status=status[0])
+        c.amplitudedamping(2, gamma=0.4, p=1.0, status=status[1])
+        return K.real(c.expectation_ps(z=[1])), K.real(c.expectation_ps(z=[2])), K.real(c.expectation_ps(x=[0], z=[1]))
+
+    st = np.random.default_rng(0).random((nt, 2))
+    z1, z2, xz = [np.asarray(v) for v in K.vmap(f)(st)]
+    # exact channel values from the oracle's density matrix
+    o = OracleCircuit(n)
+    o.h(0)
+    o.cnot(0, 1)
+    o.ry(2, theta=0.7)
+    rho = np.outer(o.state(), o.state().conj())
+
+    def chan(rho, ks, q):
+        out = np.zeros_like(rho)
+        for k in ks:
+            full = np.kron(np.kron(np.eye(2**q), k), np.eye(2 ** (n - q - 1)))
+            out += full @ rho @ full.conj().T
+        return out
+
+    rho = chan(rho, orc.ch_depolarizing(0.1, 0.2, 0.3), 1)
+    rho = chan(rho, orc.ch_amplitudedamping(0.4, 1.0), 2)
+    ez1 = np.real(np.trace(rho @ orc.pauli_string_matrix([0, 3, 0])))
+    ez2 = np.real(np.trace(rho @ orc.pauli_string_matrix([0, 0, 3])))
+    exz = np.real(np.trace(rho @ orc.pauli_string_matrix([1, 3, 0])))
+    assert abs(z1.mean() - ez1) < 4.0 / np.sqrt(nt)
+    assert abs(z2.mean() - ez2) < 4.0 / np.sqrt(nt)
+    assert abs(xz.mean() - exz) < 4.0 / np.sqrt(nt)

@@ -163,3 +163,81 @@ def test_engine_vmap_vs_reference(eng):  # noqa: F811
 
     got = K.vmap(f, vectorized_argnums=0)(FIX["vmap_theta"])
     np.testing.assert_allclose(got, FIX["vmap_values"], atol=1e-5)
+
+
+# ---- Monte-Carlo trajectories driven by status (circuit.py:473-744, basecircuit.py:824-857) ------
+def test_oracle_trajectories_vs_reference():
+    n = 5
+    st, th = FIX["traj_status"], FIX["traj_theta"]
+    for t in range(st.shape[0]):
+        o = orc.OracleCircuit(n)
+        picks = orc.noisy_trajectory(o, n, st[t], th[t])
+        assert picks == list(FIX["traj_picks_complex128"][t])
+        np.testing.assert_allclose(o.state(), FIX["traj_states_complex128"][t], atol=1e-12)
+        # the reference's complex64 run took the same branches
+        assert picks == list(FIX["traj_picks_complex64"][t])
+
+
+@pytest.mark.parametrize("dtype,tol", [("complex64", 2e-5), ("complex128", 1e-11)])
+def test_engine_trajectories_vs_reference(eng, dtype, tol):  # noqa: F811
+    n = 5
+    tc.set_dtype(dtype)
+    st, th = FIX["traj_status"], FIX["traj_theta"]
+    for t in range(st.shape[0]):
+        c = tc.Circuit(n)
+        picks = orc.noisy_trajectory(c, n, st[t], th[t])
+        assert picks == list(FIX["traj_picks_" + dtype][t])
+        ref = FIX["traj_states_" + dtype][t]
+        assert np.linalg.norm(np.asarray(c.wavefunction()) - ref) < tol * max(1.0, np.linalg.norm(ref))
+
+
+def test_engine_trajectories_vmapped_vs_reference(eng):  # noqa: F811
+    """All trajectories as ONE vmapped circuit: status and theta batched (the reference's
+    K.vmap(f, vectorized_argnums=(0, 1)) over Monte-Carlo trajectories, docs/source/advance.rst
+    'noisy circuit simulation')."""
+    n = 5
+    tc.set_dtype("complex128")
+    K = tc.backend
+    st, th = FIX["traj_status"], FIX["traj_theta"]
+
+    def f(status, theta):
+        c = tc.Circuit(n)
+        k = 0
+        for layer in range(2):
+            for i in range(n):
+                c.h(i)
+            for i in range(n - 1):
+                c.cnot(i, i + 1)
+            for i in range(n):
+                c.rx(i, theta=theta[layer * n + i])
+                c.depolarizing(i, px=0.1, py=0.05, pz=0.15, status=status[k])
+                c.amplitudedamping(i, gamma=0.3, p=0.8, status=status[k + 1])
+                c.phasedamping(i, gamma=0.2, status=status[k + 2])
+                k += 3
+        r = c.cond_measure(1, status=status[k])
+        c.reset(2, status=status[k + 1])
+        return c.wavefunction(), r
+
+    # the un-vmapped reference values up to the cond_measure / reset step
+    want, wr = [], []
+    for t in range(st.shape[0]):
+        o = orc.OracleCircuit(n)
+        k = 0
+        for layer in range(2):
+            for i in range(n):
+                o.h(i)
+            for i in range(n - 1):
+                o.cnot(i, i + 1)
+            for i in range(n):
+                o.rx(i, theta=th[t][layer * n + i])
+                o.depolarizing(i, px=0.1, py=0.05, pz=0.15, status=st[t][k])
+                o.amplitudedamping(i, gamma=0.3, p=0.8, status=st[t][k + 1])
+                o.phasedamping(i, gamma=0.2, status=st[t][k + 2])
+                k += 3
+        wr.append(o.cond_measure(1, status=st[t][k]))
+        o.reset(2, status=st[t][k + 1])
+        want.append(o.state())
+    got, r = K.vmap(f, vectorized_argnums=(0, 1))(st, th)
+    assert list(np.asarray(r)) == wr == list(FIX["traj_picks_complex128"][:, 0])
+    np.testing.assert_allclose(np.asarray(got), np.array(want), atol=1e-11)
+    tc.set_dtype("complex64")
