@@ -234,6 +234,13 @@ int tcb200_run_circuit_host(void* state, int nbits, int dtype, int init_zero, in
 /* Number of kernel launches issued by this process through the library so far. */
 int64_t tcb200_launch_count(void);
 
+/* How many of those were the persistent TMA pipeline (tpass_kernel) rather than the LDGSTS-staged
+ * cpass_kernel: tcb200_apply_pass_host picks the pipeline whenever the pass uses the production
+ * 64 KiB tile, the state is larger than one tile and the driver exports cuTensorMapEncodeTiled
+ * (TCB200_TMA=0 forces the staged kernel; TCB200_TMA_STRICT=1 turns a failed tensor-map encode
+ * into an error instead of a fallback). */
+int64_t tcb200_tma_pass_count(void);
+
 #ifdef __cplusplus
 }
 #endif

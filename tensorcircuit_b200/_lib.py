@@ -43,6 +43,7 @@ def _load() -> ctypes.CDLL:
         "tcb200_version": (c_char_p, []),
         "tcb200_last_error": (c_char_p, []),
         "tcb200_launch_count": (c_int64, []),
+        "tcb200_tma_pass_count": (c_int64, []),
         "tcb200_init_zero": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p]),
         "tcb200_load_c128": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
         "tcb200_set_zero": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p]),
@@ -73,7 +74,7 @@ def _load() -> ctypes.CDLL:
 
 lib = _load()
 EXPORTS = [
-    "tcb200_version", "tcb200_last_error", "tcb200_launch_count", "tcb200_init_zero", "tcb200_load_c128",
+    "tcb200_version", "tcb200_last_error", "tcb200_launch_count", "tcb200_tma_pass_count", "tcb200_init_zero", "tcb200_load_c128",
     "tcb200_set_zero", "tcb200_copy_rows",
     "tcb200_apply_dense", "tcb200_apply_dense_batched", "tcb200_apply_diag", "tcb200_apply_pass", "tcb200_apply_pass_host", "tcb200_apply_rpass_host",
     "tcb200_pass_tile_bits", "tcb200_norm2", "tcb200_reduce_workspace_bytes", "tcb200_probability",

@@ -79,19 +79,21 @@ int make_geom(int nbits, int tile_bits, int k, const int* bits, TileGeom* g) {
     return make_geom_hi(nbits, tile_bits, nh, hi, g);
 }
 
-// bank class of a local amplitude bit under swz_unit (see common.cuh): bits that end up in the
-// same class move the same bank-select bit.
-static int bank_class(int apu, int b) {
+// bank class of a local amplitude bit under the tile swizzle (see common.cuh): bits that end up
+// in the same class move the same bank-select bit.  SWZ_SW folds two 3-bit fields onto the
+// chunk index, SWZ_HW128 (the TMA pattern) one.
+static int bank_class(int apu, int b, int mode) {
+    const int top = (mode == SWZ_HW128) ? 6 : 9;   // highest unit bit + 1 that still moves a bank bit
     if (apu == 2) {          // complex64: bit 0 = which half of the 16-byte unit
         if (b == 0) return 0;
-        if (b <= 9) return 1 + (b - 1) % 3;
+        if (b <= top) return 1 + (b - 1) % 3;
         return -1;
     }
-    if (b <= 8) return b % 3;  // complex128: one amplitude per unit
+    if (b < top) return b % 3;  // complex128: one amplitude per unit
     return -1;
 }
 
-int make_group_map(const TileGeom& g, int apu, int k, const int* bits, GroupMap* gm) {
+int make_group_map(const TileGeom& g, int apu, int k, const int* bits, GroupMap* gm, int swz_mode) {
     memset(gm, 0, sizeof(*gm));
     if (k < 1 || k > TCB200_MAX_K) return fail(TCB200_ERR_UNSUPPORTED, "k=%d unsupported", k);
     if (k > g.T) return fail(TCB200_ERR_ARG, "k=%d exceeds the state size", k);
@@ -114,7 +116,7 @@ int make_group_map(const TileGeom& g, int apu, int k, const int* bits, GroupMap*
     const int ncls = (apu == 2) ? 4 : 3;
     for (int c = (gm->vec0 ? 1 : 0); c < ncls; ++c) {
         for (int b = 0; b < g.T; ++b) {
-            if (!is_t[b] && !used[b] && bank_class(apu, b) == c) {
+            if (!is_t[b] && !used[b] && bank_class(apu, b, swz_mode) == c) {
                 order[no++] = b;
                 used[b] = true;
                 break;
@@ -124,10 +126,10 @@ int make_group_map(const TileGeom& g, int apu, int k, const int* bits, GroupMap*
     for (int b = 0; b < g.T; ++b)
         if (!is_t[b] && !used[b]) order[no++] = b;
     for (int i = 0; i < gm->ngb; ++i)
-        gm->ntval[i] = (apu == 2) ? swz_amp<2>(1u << order[i]) : swz_amp<1>(1u << order[i]);
+        gm->ntval[i] = (apu == 2) ? swz_amp<2>(1u << order[i], swz_mode) : swz_amp<1>(1u << order[i], swz_mode);
     for (uint32_t j = 0; j < (1u << k); ++j) {
         const uint32_t e = deposit(j, tl, k);
-        gm->tval[j] = (apu == 2) ? swz_amp<2>(e) : swz_amp<1>(e);
+        gm->tval[j] = (apu == 2) ? swz_amp<2>(e, swz_mode) : swz_amp<1>(e, swz_mode);
     }
     return 0;
 }
@@ -162,8 +164,8 @@ int dense_tile_bits(int dtype, int k) {
 }
 
 int pass_tile_bits(int dtype) {
-    // 64 KiB tiles: three CTAs per SM
-    const int bytes_log2 = env_tile_log2("TCB200_PASS_TILE_BYTES_LOG2", 16);
+    // 64 KiB tiles: three CTAs of cpass_kernel per SM; measured alternatives in DESIGN.md
+    const int bytes_log2 = env_tile_log2("TCB200_PASS_TILE_BYTES_LOG2", PASS_TILE_BYTES_LOG2);
     return bytes_log2 - (dtype == TCB200_C64 ? 3 : 4);
 }
 

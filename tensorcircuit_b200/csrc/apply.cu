@@ -152,12 +152,6 @@ static int check_common(const void* state, int nbits, int dtype, int k, const in
 // ------------------------------------------------------------------------------------------------
 // multi-block pass
 // ------------------------------------------------------------------------------------------------
-struct PassOp {
-    int k;
-    int moff;  // offset (in complex elements) of this block's matrix inside the pass blob
-    GroupMap gm;
-};
-
 struct PassParams {
     void* state;
     const void* mats;      // device blob, per op [batch_mats][4^k]
@@ -680,6 +674,8 @@ int tcb200_apply_pass_host(void* state, int nbits, int dtype, int nops, const in
     if (nops < 1 || nops > TCB200_MAX_PASS_OPS) return fail(TCB200_ERR_ARG, "nops=%d out of range", nops);
     if (nbits < 1 || nbits > 40) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int tr = launch_tpass(dtype, state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, batch, st);
+    if (tr <= 0) return tr;  // launched (0) or failed (< 0); > 0: not eligible for the TMA pipeline
     if (dtype == TCB200_C64)
         return launch_cpass<float>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, batch, st);
     return launch_cpass<double>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, batch, st);
@@ -694,6 +690,10 @@ int tcb200_apply_rpass_host(void* state, int nbits, int dtype, int nrt, const in
     if (nrt < 1 || nrt > TCB200_MAX_PASS_OPS) return fail(TCB200_ERR_ARG, "nrt=%d out of range", nrt);
     if (nbits < 1 || nbits > 40) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == TCB200_C64) {
+        const int tr = launch_trpass(state, nbits, nrt, rt_k, rt_bits, rt_nsub, sub_k, sub_bits, sub_mats, n_hi, tile_hi, batch, st);
+        if (tr <= 0) return tr;  // launched or failed; > 0: not eligible for the TMA pipeline
+    }
     if (dtype == TCB200_C64)
         return launch_rpass<float>(state, nbits, nrt, rt_k, rt_bits, rt_nsub, sub_k, sub_bits, sub_mats, n_hi, tile_hi, batch, st);
     return launch_rpass<double>(state, nbits, nrt, rt_k, rt_bits, rt_nsub, sub_k, sub_bits, sub_mats, n_hi, tile_hi, batch, st);

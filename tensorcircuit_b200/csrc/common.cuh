@@ -89,6 +89,60 @@ __device__ __forceinline__ float2 cmul<float2>(const float2 m, const float2 v) {
 }
 #endif
 
+// Row accumulator  out = sum_j m_j * v_j.  The generic version chains cmul / cfma.  For complex64
+// on sm_100 the two packed products are kept apart,
+//     P += (m.x, m.x) * (v.x, v.y)        Q += (m.y, m.y) * (v.x, v.y)
+//     out = (P.x - Q.y, P.y + Q.x) = (-1, 1) * (Q.y, Q.x) + P        (one more FFMA2 per row)
+// because then every FFMA2 takes the matrix element as a single broadcast register (R.F32) and
+// the amplitude pair exactly as loaded.  The cfma<float2> form above needs the register PAIR
+// (m.y, m.y) for its (-,+) operand; with the matrix in registers (cpass / tpass) ptxas rebuilds
+// that pair with two MOVs for almost every FFMA2 (measured: 69 % of the issued instructions of a
+// 2-bit block were not FFMA2).  The swap and the sign of the final step fold into operand
+// modifiers (.LO_HI, .NP) and a uniform-register constant.
+template <typename C>
+struct RowAcc {
+    C a;
+    TCB_HD void init(const C m, const C v) { a = cmul(m, v); }
+    TCB_HD void mac(const C m, const C v) { cfma(a, m, v); }
+    TCB_HD C result() const { return a; }
+};
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+template <>
+struct RowAcc<float2> {
+    float2 p, q;
+    __device__ __forceinline__ void init(const float2 m, const float2 v) {
+        p = __fmul2_rn(make_float2(m.x, m.x), v);
+        q = __fmul2_rn(make_float2(m.y, m.y), v);
+    }
+    __device__ __forceinline__ void mac(const float2 m, const float2 v) {
+        p = __ffma2_rn(make_float2(m.x, m.x), v, p);
+        q = __ffma2_rn(make_float2(m.y, m.y), v, q);
+    }
+    __device__ __forceinline__ float2 result() const {
+        return __ffma2_rn(make_float2(-1.f, 1.f), make_float2(q.y, q.x), p);
+    }
+};
+#endif
+
+// The chained form (cmul / cfma, 2 FFMA2 per complex multiply-add, no final step) stays the
+// choice where the FP32 pipe itself is the limit and the MOVs hide in spare issue slots
+// (cpass_kernel: 10.25 ms against 10.97 ms for a 12-block pass at n = 30).
+template <typename C>
+struct ChainAcc {
+    C a;
+    TCB_HD void init(const C m, const C v) { a = cmul(m, v); }
+    TCB_HD void mac(const C m, const C v) { cfma(a, m, v); }
+    TCB_HD C result() const { return a; }
+};
+template <typename C, bool SPLIT>
+struct AccSel {
+    using type = ChainAcc<C>;
+};
+template <typename C>
+struct AccSel<C, true> {
+    using type = RowAcc<C>;
+};
+
 // ---- shared-memory swizzle -----------------------------------------------------------------
 // Tiles live in shared memory as 16-byte units.  Unit u is stored at slot
 //   swz(u) = u ^ ((u>>3)&7) ^ ((u>>6)&7)
@@ -101,10 +155,29 @@ __device__ __forceinline__ float2 cmul<float2>(const float2 m, const float2 v) {
 // a quarter/half warp always hit distinct banks, whatever the target bits are.
 TCB_HD uint32_t swz_unit(uint32_t u) { return u ^ ((u >> 3) & 7u) ^ ((u >> 6) & 7u); }
 
+// Layout modes of a staged tile:
+//   SWZ_NONE  linear;
+//   SWZ_SW    the two-term software swizzle above (tiles staged by LDGSTS);
+//   SWZ_HW128 the TMA hardware pattern CU_TENSOR_MAP_SWIZZLE_128B: inside every 1024-byte block the
+//             16-byte chunk index (address bits 4..6) is XORed with the 128-byte line index
+//             (address bits 7..9), i.e. only the first term.  Tiles written by
+//             cp.async.bulk.tensor (tpass_kernel) arrive in this layout.
+constexpr int SWZ_NONE = 0, SWZ_SW = 1, SWZ_HW128 = 2;
+
+// bytes (log2) of a multi-block pass tile: 8192 complex64 / 4096 complex128 amplitudes.  15 selects
+// the two-rings-per-SM build of the TMA pipeline (tpass.cu); measurements of both in DESIGN.md.
+constexpr int PASS_TILE_BYTES_LOG2 = 16;
+
+TCB_HD uint32_t swz_unit_m(int mode, uint32_t u) {
+    if (mode == SWZ_SW) return swz_unit(u);
+    if (mode == SWZ_HW128) return u ^ ((u >> 3) & 7u);
+    return u;
+}
+
 template <int APU>
-TCB_HD uint32_t swz_amp(uint32_t e) {
-    if (APU == 2) return (swz_unit(e >> 1) << 1) | (e & 1u);
-    return swz_unit(e);
+TCB_HD uint32_t swz_amp(uint32_t e, int mode = SWZ_SW) {
+    if (APU == 2) return (swz_unit_m(mode, e >> 1) << 1) | (e & 1u);
+    return swz_unit_m(mode, e);
 }
 
 // ---- tile geometry -------------------------------------------------------------------------
@@ -171,8 +244,8 @@ struct alignas(16) Unit16 {
 };
 
 // Bring the tile with base amplitude index `base` into shared memory.  `rowoff` holds
-// row_offset() of the 2^h rows.  SWZ selects the swizzled layout.
-template <typename C, bool SWZ>
+// row_offset() of the 2^h rows.  SWZ selects the layout (SWZ_NONE / SWZ_SW / SWZ_HW128).
+template <typename C, int SWZ>
 TCB_HD void stage_in(const TileGeom& g, const C* vec, uint64_t base, C* tile,
                      const uint64_t* rowoff, int tid, int nthr) {
     constexpr int APU = 16 / (int)sizeof(C);
@@ -182,7 +255,7 @@ TCB_HD void stage_in(const TileGeom& g, const C* vec, uint64_t base, C* tile,
     for (uint32_t u = tid; u < nunits; u += nthr) {
         const uint32_t e = u * APU;
         const uint64_t gi = base + rowoff[e >> g.lrow] + (e & rowmask);
-        const uint32_t slot = SWZ ? swz_unit(u) : u;
+        const uint32_t slot = swz_unit_m(SWZ, u);
 #if defined(__CUDA_ARCH__)
         cp_async16(t16 + slot, vec + gi);
 #else
@@ -191,7 +264,7 @@ TCB_HD void stage_in(const TileGeom& g, const C* vec, uint64_t base, C* tile,
     }
 }
 
-template <typename C, bool SWZ>
+template <typename C, int SWZ>
 TCB_HD void stage_out(const TileGeom& g, C* vec, uint64_t base, const C* tile,
                       const uint64_t* rowoff, int tid, int nthr) {
     constexpr int APU = 16 / (int)sizeof(C);
@@ -201,7 +274,7 @@ TCB_HD void stage_out(const TileGeom& g, C* vec, uint64_t base, const C* tile,
     for (uint32_t u = tid; u < nunits; u += nthr) {
         const uint32_t e = u * APU;
         const uint64_t gi = base + rowoff[e >> g.lrow] + (e & rowmask);
-        const uint32_t slot = SWZ ? swz_unit(u) : u;
+        const uint32_t slot = swz_unit_m(SWZ, u);
         *reinterpret_cast<Unit16*>(vec + gi) = t16[slot];
     }
 }
@@ -217,6 +290,13 @@ struct GroupMap {
     int vec0;             // 1: local bit 0 is target bit 0 and sizeof(C)==8 -> pairs are one 16B unit
 };
 
+// one fused block of a multi-block pass
+struct PassOp {
+    int k;
+    int moff;  // offset (in complex elements) of this block's matrix inside the pass blob
+    GroupMap gm;
+};
+
 TCB_HD uint32_t group_base(const GroupMap& m, uint32_t gidx) {
     uint32_t b = 0;
     for (int i = 0; i < m.ngb; ++i) b ^= (0u - ((gidx >> i) & 1u)) & m.ntval[i];
@@ -224,10 +304,11 @@ TCB_HD uint32_t group_base(const GroupMap& m, uint32_t gidx) {
 }
 
 // One group: v <- M v with M(i, j) supplied by `mat` (any callable returning C).
-template <typename C, int K, typename Mat>
+template <typename C, int K, typename Mat, bool SPLIT = false>
 TCB_HD void apply_group(C* tile, const uint32_t base, const uint32_t* tval, const bool vec0,
                         const Mat& mat) {
     constexpr int D = 1 << K;
+    using Acc = typename AccSel<C, SPLIT>::type;
     C v[D];
     if (sizeof(C) == 8 && vec0) {
         // bit 0 of the local index is target bit 0: (j, j|1) share one aligned 16-byte unit
@@ -249,20 +330,22 @@ TCB_HD void apply_group(C* tile, const uint32_t base, const uint32_t* tval, cons
             C* qc = reinterpret_cast<C*>(&q);
 #pragma unroll
             for (int ii = 0; ii < 2; ++ii) {
-                C acc = cmul(mat(i + ii, 0), v[0]);
+                Acc acc;
+                acc.init(mat(i + ii, 0), v[0]);
 #pragma unroll
-                for (int j = 1; j < D; ++j) cfma(acc, mat(i + ii, j), v[j]);
-                qc[ii] = acc;
+                for (int j = 1; j < D; ++j) acc.mac(mat(i + ii, j), v[j]);
+                qc[ii] = acc.result();
             }
             *reinterpret_cast<Unit16*>(tile + (base ^ tval[i])) = q;
         }
     } else {
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-            C acc = cmul(mat(i, 0), v[0]);
+            Acc acc;
+            acc.init(mat(i, 0), v[0]);
 #pragma unroll
-            for (int j = 1; j < D; ++j) cfma(acc, mat(i, j), v[j]);
-            tile[base ^ tval[i]] = acc;
+            for (int j = 1; j < D; ++j) acc.mac(mat(i, j), v[j]);
+            tile[base ^ tval[i]] = acc.result();
         }
     }
 }
@@ -286,14 +369,14 @@ TCB_HD void apply_block_on_tile(C* tile, const GroupMap& gm, int tid, int nthr, 
 // Fast path: 256 threads and exactly 2^NITLOG groups per thread (ngb == 8 + NITLOG).  The
 // thread's part of the group index is folded once; the per-iteration part walks a Gray code, so
 // each further group costs one XOR; everything is unrolled with compile-time table indices.
-template <typename C, int K, int NITLOG, bool VEC0, typename Mat>
+template <typename C, int K, int NITLOG, bool VEC0, typename Mat, int TB = 8, bool SPLIT = false>
 TCB_HD void apply_block_fast_v(C* tile, const GroupMap& gm, int tid, const Mat& mat) {
     uint32_t b = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) b ^= (0u - (((uint32_t)tid >> i) & 1u)) & gm.ntval[i];
+    for (int i = 0; i < TB; ++i) b ^= (0u - (((uint32_t)tid >> i) & 1u)) & gm.ntval[i];
     uint32_t hv[NITLOG > 0 ? NITLOG : 1];
 #pragma unroll
-    for (int i = 0; i < NITLOG; ++i) hv[i] = gm.ntval[8 + i];
+    for (int i = 0; i < NITLOG; ++i) hv[i] = gm.ntval[TB + i];
     uint32_t tv[1 << K];
 #pragma unroll
     for (int j = 0; j < (1 << K); ++j) tv[j] = gm.tval[j];
@@ -306,16 +389,29 @@ TCB_HD void apply_block_fast_v(C* tile, const GroupMap& gm, int tid, const Mat& 
                 if (((it >> q) & 1) && ((it & ((1 << q) - 1)) == 0)) z = q;  // count trailing zeros
             b ^= hv[z];
         }
-        apply_group<C, K>(tile, b, tv, VEC0, mat);
+        apply_group<C, K, Mat, SPLIT>(tile, b, tv, VEC0, mat);
     }
 }
 
-template <typename C, int K, int NITLOG, typename Mat>
+template <typename C, int K, int NITLOG, typename Mat, int TB = 8, bool SPLIT = false>
 TCB_HD void apply_block_fast(C* tile, const GroupMap& gm, int tid, const Mat& mat) {
     if (sizeof(C) == 8 && gm.vec0)
-        apply_block_fast_v<C, K, NITLOG, true>(tile, gm, tid, mat);
+        apply_block_fast_v<C, K, NITLOG, true, Mat, TB, SPLIT>(tile, gm, tid, mat);
     else
-        apply_block_fast_v<C, K, NITLOG, false>(tile, gm, tid, mat);
+        apply_block_fast_v<C, K, NITLOG, false, Mat, TB, SPLIT>(tile, gm, tid, mat);
+}
+
+// Same for the persistent TMA pass (2^TB threads per CTA, tile size fixed at compile time):
+// 2^(T-K-TB) groups per thread, generic loop when a wide block leaves less than one per thread.
+template <typename C, int K, int T, int TB, typename Mat>
+TCB_HD void apply_block_tb(C* tile, const GroupMap& gm, int tid, const Mat& mat) {
+    if constexpr (T - K - TB >= 0) {
+        if (gm.ngb == T - K) {
+            apply_block_fast<C, K, T - K - TB, Mat, TB, true>(tile, gm, tid, mat);
+            return;
+        }
+    }
+    apply_block_on_tile<C, K>(tile, gm, tid, 1 << TB, TB, mat);
 }
 
 // Picks the fast path when the launch shape allows it (the production tiles: 2^12 / 2^13
@@ -383,11 +479,11 @@ TCB_HD void rsub2r(C* v, const C* mr) {
             }
         const int i0 = base, i1 = base | (1 << P0), i2 = base | (1 << P1), i3 = base | (1 << P0) | (1 << P1);
         const C a0 = v[i0], a1 = v[i1], a2 = v[i2], a3 = v[i3];
-        C o;
-        o = cmul(mr[0], a0); cfma(o, mr[1], a1); cfma(o, mr[2], a2); cfma(o, mr[3], a3); v[i0] = o;
-        o = cmul(mr[4], a0); cfma(o, mr[5], a1); cfma(o, mr[6], a2); cfma(o, mr[7], a3); v[i1] = o;
-        o = cmul(mr[8], a0); cfma(o, mr[9], a1); cfma(o, mr[10], a2); cfma(o, mr[11], a3); v[i2] = o;
-        o = cmul(mr[12], a0); cfma(o, mr[13], a1); cfma(o, mr[14], a2); cfma(o, mr[15], a3); v[i3] = o;
+        RowAcc<C> o;
+        o.init(mr[0], a0); o.mac(mr[1], a1); o.mac(mr[2], a2); o.mac(mr[3], a3); v[i0] = o.result();
+        o.init(mr[4], a0); o.mac(mr[5], a1); o.mac(mr[6], a2); o.mac(mr[7], a3); v[i1] = o.result();
+        o.init(mr[8], a0); o.mac(mr[9], a1); o.mac(mr[10], a2); o.mac(mr[11], a3); v[i2] = o.result();
+        o.init(mr[12], a0); o.mac(mr[13], a1); o.mac(mr[14], a2); o.mac(mr[15], a3); v[i3] = o.result();
     }
 }
 
@@ -400,9 +496,9 @@ TCB_HD void rsub1(C* v, const C* m) {
         const int lo = r & ((1 << P0) - 1);
         const int i0 = ((r >> P0) << (P0 + 1)) | lo, i1 = i0 | (1 << P0);
         const C a0 = v[i0], a1 = v[i1];
-        C o;
-        o = cmul(m0, a0); cfma(o, m1, a1); v[i0] = o;
-        o = cmul(m2, a0); cfma(o, m3, a1); v[i1] = o;
+        RowAcc<C> o;
+        o.init(m0, a0); o.mac(m1, a1); v[i0] = o.result();
+        o.init(m2, a0); o.mac(m3, a1); v[i1] = o.result();
     }
 }
 
@@ -622,6 +718,156 @@ TCB_HD void rtile_run(C* tile, const RTile& rt, const RSub* subs, const C* bm, i
     }
 }
 
+// ---- 16-amplitude register tiles of the persistent pass (trpass_kernel, complex64) ------------
+// Every op of a trpass is a 4-bit register tile: a thread owns ONE group of 16 amplitudes, loads
+// it once, applies the op's 1- and 2-bit gates on positions 0..3 of the register array, and
+// stores it once.  A plain 2-bit block is the special case "one gate, two filler positions" --
+// the fillers are bits a thread would otherwise iterate over.
+//
+// Control is warp-uniform and lives in the kernel-parameter constant bank: per op a TROp, per
+// gate one code word  (case | matrix offset << 8),  case 0..5 = 2-bit gate on positions
+// (0,1) (0,2) (0,3) (1,2) (1,3) (2,3), case 6..9 = 1-bit gate on position 0..3.  Every gate owns a
+// 16-element matrix slot, so the matrix of the first gate is fetched together with the
+// amplitudes, before its code is looked at (no load -> branch -> load chain at the op start).
+// Per-op control word block (16 bytes, kernel-parameter constant bank).  The compute loop fetches
+// the block of op o+1 while op o is in the FP32 pipe, so an op starts with everything but its
+// amplitudes and its first matrix already in registers.
+struct TROp {
+    uint32_t t01;    // swizzled BYTE offsets of positions 0 and 1 inside the tile (16 bits each)
+    uint32_t t23;    // ... of positions 2 and 3
+    uint32_t flags;  // nsub | vec0 << 8 | sync << 12 | sub0 << 16
+    uint32_t code0;  // code word of the first gate
+};
+// vec0: position 0 is amplitude bit 0, (j, j+1) share an aligned 16-byte unit
+// sync (before this op): 2 = CTA barrier (new segment), 1 = __syncwarp() (same segment)
+TCB_HD int trop_nsub(const TROp& op) { return (int)(op.flags & 0xffu); }
+TCB_HD int trop_vec0(const TROp& op) { return (int)((op.flags >> 8) & 1u); }
+TCB_HD int trop_sync(const TROp& op) { return (int)((op.flags >> 12) & 3u); }
+TCB_HD int trop_sub0(const TROp& op) { return (int)(op.flags >> 16); }
+TCB_HD uint32_t trop_t8(const TROp& op, int i) {
+    const uint32_t w = i < 2 ? op.t01 : op.t23;
+    return (i & 1) ? (w >> 16) : (w & 0xffffu);
+}
+
+TCB_HD void tr_load_matrix(float2* mr, const float2* slot) {
+    const float4* m4 = reinterpret_cast<const float4*>(slot);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 q = m4[i];
+        mr[2 * i] = make_float2(q.x, q.y);
+        mr[2 * i + 1] = make_float2(q.z, q.w);
+    }
+}
+
+// one gate (case word c, common.cuh above) on the 16 amplitudes in registers; an if-tree, not a
+// switch: a jump table would put one more dependent constant load in front of the first FFMA2
+TCB_HD void tr_gate(float2* v, const float2* mr, uint32_t c) {
+    if (c < 3u) {
+        if (c == 0u) rsub2r<float2, 4, 0, 1>(v, mr);
+        else if (c == 1u) rsub2r<float2, 4, 0, 2>(v, mr);
+        else rsub2r<float2, 4, 0, 3>(v, mr);
+    } else if (c < 6u) {
+        if (c == 3u) rsub2r<float2, 4, 1, 2>(v, mr);
+        else if (c == 4u) rsub2r<float2, 4, 1, 3>(v, mr);
+        else rsub2r<float2, 4, 2, 3>(v, mr);
+    } else if (c < 8u) {
+        if (c == 6u) rsub1<float2, 4, 0>(v, mr);
+        else rsub1<float2, 4, 1>(v, mr);
+    } else {
+        if (c == 8u) rsub1<float2, 4, 2>(v, mr);
+        else rsub1<float2, 4, 3>(v, mr);
+    }
+}
+
+// tile: shared-memory tile (bytes); b8: swizzled byte offset of the thread's group (element 0)
+TCB_HD void trtile_thread(unsigned char* tile, uint32_t b8, const TROp op, const uint32_t* subcode, const float2* bm) {
+    uint32_t a[16];
+    a[0] = b8;
+#pragma unroll
+    for (int j = 1; j < 16; ++j) {
+        const int low = j & (-j);  // lowest set bit: a[j] = a[j - low] ^ t8[log2(low)]
+        a[j] = a[j ^ low] ^ trop_t8(op, low == 1 ? 0 : (low == 2 ? 1 : (low == 4 ? 2 : 3)));
+    }
+    const bool vec0 = trop_vec0(op) != 0;
+    float2 v[16];
+    if (vec0) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            const float4 q = *reinterpret_cast<const float4*>(tile + a[j]);
+            v[j] = make_float2(q.x, q.y);
+            v[j + 1] = make_float2(q.z, q.w);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(tile + a[j]);
+    }
+    uint32_t code = op.code0;
+    float2 mr[16];
+    tr_load_matrix(mr, bm + (code >> 8));
+    const int nsub = trop_nsub(op), sub0 = trop_sub0(op);
+    for (int s = 0;;) {
+        const uint32_t next = (s + 1 < nsub) ? subcode[sub0 + s + 1] : 0u;  // in flight during the FMAs
+        tr_gate(v, mr, code & 15u);
+        if (++s >= nsub) break;
+        code = next;
+        tr_load_matrix(mr, bm + (code >> 8));
+    }
+    if (vec0) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2)
+            *reinterpret_cast<float4*>(tile + a[j]) = make_float4(v[j].x, v[j].y, v[j + 1].x, v[j + 1].y);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) *reinterpret_cast<float2*>(tile + a[j]) = v[j];
+    }
+}
+
+
+// ---- TMA decomposition of a tile (tpass_kernel) ----------------------------------------------
+// The state is described to the TMA unit as a rank-5 tensor of 128-byte lines:
+//   d0 = the scalars of one line, d1 = line index over the whole buffer (stride 128 B),
+//   d2..d4 = up to three "stride bits" (size 2, stride 2^bit amplitudes).
+// One box = 2^lrow2 contiguous amplitudes x the box's stride bits; the remaining stride bits of
+// the tile are enumerated as 2^nextra boxes.  Stride bits are the gathered bits of the tile,
+// preceded by the top bits of a row that is longer than 256 lines.  Boxes land back to back in
+// shared memory, so the local amplitude index is exactly the TileGeom one, stored in the
+// SWZ_HW128 layout.
+struct TmaPlan {
+    int line_bits;      // log2(amplitudes per 128-byte line): 4 (complex64) / 3 (complex128)
+    int lrow2;          // contiguous low bits of one box row (<= line_bits + 8)
+    int nbox_bits;      // stride bits inside one box (<= 3)
+    int box_bit[3];     // their global bit positions
+    int nextra;         // stride bits enumerated across boxes
+    int extra_bit[8];   // their global bit positions
+    int box_amps_log2;  // lrow2 + nbox_bits
+};
+
+// 0 when the tile can be moved by TMA boxes, -1 otherwise (rows shorter than 8 lines)
+inline int make_tma_plan(const TileGeom& g, int apu, TmaPlan* tp) {
+    tp->line_bits = (apu == 2) ? 4 : 3;
+    if (g.lrow < tp->line_bits) return -1;  // a row is at least one 128-byte line
+    tp->lrow2 = g.lrow < tp->line_bits + 8 ? g.lrow : tp->line_bits + 8;
+    int sb[16];
+    int ns = 0;
+    for (int b = tp->lrow2; b < g.lrow; ++b) sb[ns++] = b;
+    for (int j = 0; j < g.h; ++j) sb[ns++] = g.hb[j];
+    tp->nbox_bits = ns < 3 ? ns : 3;
+    for (int i = 0; i < 3; ++i) tp->box_bit[i] = i < tp->nbox_bits ? sb[i] : -1;
+    tp->nextra = ns - tp->nbox_bits;
+    if (tp->nextra > 8) return -1;
+    for (int i = 0; i < 8; ++i) tp->extra_bit[i] = i < tp->nextra ? sb[tp->nbox_bits + i] : -1;
+    tp->box_amps_log2 = tp->lrow2 + tp->nbox_bits;
+    return 0;
+}
+
+// amplitude offset (relative to the tile base) of box c
+TCB_HD uint64_t tma_box_offset(const TmaPlan& tp, uint32_t c) {
+    uint64_t o = 0;
+    for (int i = 0; i < tp.nextra; ++i)
+        if ((c >> i) & 1u) o |= 1ull << tp.extra_bit[i];
+    return o;
+}
+
 // ---- host helpers (plan.cpp part of abi.cu) ------------------------------------------------
 // Choose the tile for a set of ascending target bits: gathers exactly the targets that do not
 // fall into the contiguous low part.  Returns <0 on error.
@@ -629,7 +875,16 @@ int make_geom(int nbits, int tile_bits, int k, const int* bits, TileGeom* g);
 // Tile with explicitly requested gathered bits.
 int make_geom_hi(int nbits, int tile_bits, int n_hi, const int* tile_hi, TileGeom* g);
 // Fill the GroupMap for a block with the given ascending global bits inside geometry g.
-int make_group_map(const TileGeom& g, int apu, int k, const int* bits, GroupMap* gm);
+int make_group_map(const TileGeom& g, int apu, int k, const int* bits, GroupMap* gm, int swz_mode = SWZ_SW);
+// Persistent TMA pipeline for a multi-block pass (tpass.cu).  0: launched; > 0: not eligible
+// (tile size overridden, state smaller than a tile, no driver entry point, TCB200_TMA=0) and the
+// caller falls back to cpass_kernel; < 0: error.
+int launch_tpass(int dtype, void* state, int nbits, int nops, const int* ops_k, const int* ops_bits,
+                 const double* mats, int n_hi, const int* tile_hi, int64_t batch, cudaStream_t st);
+// complex64 register-tile pass (<= 4-bit tiles of 1-/2-bit gates) through the same pipeline
+int launch_trpass(void* state, int nbits, int nrt, const int* rt_k, const int* rt_bits, const int* rt_nsub,
+                  const int* sub_k, const int* sub_bits, const double* sub_mats, int n_hi, const int* tile_hi,
+                  int64_t batch, cudaStream_t st);
 int pick_threads(int T, int k, int apu);   // log2(blockDim.x)
 int dense_tile_bits(int dtype, int k);     // log2(tile amplitudes) of the single-block kernel
 int pass_tile_bits(int dtype);             // ... of the multi-block pass kernel

@@ -24,7 +24,7 @@ def _build_emu():
     # apply.cu is compiled with -DTCB200_EMU only here: that adds the CPU execution of the
     # register-tile pass (same parameter block and device functions as rpass_kernel)
     srcs = [os.path.join(EMU_DIR, "emu.cu"), os.path.join(ROOT, "tensorcircuit_b200", "csrc", "abi.cu"),
-            os.path.join(ROOT, "tensorcircuit_b200", "csrc", "apply.cu")]
+            os.path.join(ROOT, "tensorcircuit_b200", "csrc", "apply.cu"), os.path.join(ROOT, "tensorcircuit_b200", "csrc", "tpass.cu")]
     deps = srcs + [os.path.join(ROOT, "tensorcircuit_b200", "csrc", "common.cuh"), os.path.join(ROOT, "include", "tcb200.h")]
     if os.path.exists(EMU_LIB) and all(os.path.getmtime(EMU_LIB) > os.path.getmtime(d) for d in deps):
         return
@@ -219,3 +219,116 @@ def test_emu_expectation(emu, dtype, tile_log2, monkeypatch):
         assert rc == 0, emu.emu_last_error()
         got = out[0::2] + 1j * out[1::2]
         np.testing.assert_allclose(got, np.array(want), atol=50 * TOL[dtype])
+
+
+# ---- persistent TMA pass (tpass.cu): box decomposition, SWIZZLE_128B layout, 512-thread group walk
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_emu_tpass(emu, dtype):
+    dt = 0 if dtype == np.complex64 else 1
+    rng = np.random.default_rng(17)
+    T = emu.emu_pass_tile_bits(dt)
+    emu.emu_apply_tpass.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                    ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double), ctypes.c_int,
+                                    ctypes.POINTER(ctypes.c_int), ctypes.c_int64]
+    for trial in range(10):
+        n = int(rng.integers(T + 1, T + 5))
+        batch = 1 if trial % 3 else 3
+        n_hi = min(int(rng.integers(0, 7)), n - T) if trial else 0   # trial 0: h = 0 (row longer than a box)
+        lrow = T - n_hi
+        hi = sorted(rng.choice(np.arange(lrow, n), size=n_hi, replace=False).tolist()) if n_hi else []
+        avail = list(range(lrow)) + hi
+        nops = int(rng.integers(1, 6))
+        refs = [_rand_state(rng, n, dtype) for _ in range(batch)]
+        got = np.stack(refs).copy()
+        refs = [r.astype(np.complex128) for r in refs]
+        ks, bl, ml = [], [], []
+        for _ in range(nops):
+            k = int(rng.integers(1, 5))
+            bits = sorted(rng.choice(avail, size=k, replace=False).tolist())
+            u = rng.normal(size=(2**k, 2**k)) + 1j * rng.normal(size=(2**k, 2**k))
+            u /= np.linalg.norm(u, 2)
+            refs = [orc.apply_gate(r, u, _bits_to_qubits(n, bits), n) for r in refs]
+            ks.append(k)
+            bl += bits
+            ml.append(np.ascontiguousarray(u, dtype=np.complex128).reshape(-1))
+        mats = np.concatenate(ml)
+        rc = emu.emu_apply_tpass(got.ctypes.data_as(ctypes.c_void_p), n, dt, nops, _ip(ks), _ip(bl), _dp(mats.view(np.float64)),
+                                 n_hi, _ip(hi if hi else [0]), batch)
+        assert rc == 0, (rc, emu.emu_last_error())
+        for bi in range(batch):
+            err = np.linalg.norm(got[bi] - refs[bi]) / np.linalg.norm(refs[bi])
+            assert err < 50 * TOL[dtype], (trial, bi, err)
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_emu_tpass_conflicts(emu, dtype):
+    """Under the hardware SWIZZLE_128B layout each bank-select bit has two source bits (three in the
+    software swizzle), so a block can lose a class: never worse than 2-way, and conflict-free for
+    1-bit blocks and for the 2-bit blocks of neighbouring qubits the circuits are made of."""
+    dt = 0 if dtype == np.complex64 else 1
+    n = 20
+    T = emu.emu_pass_tile_bits(dt)
+    hi = [15, 17]
+    local = list(range(T - 2)) + hi
+    hist = {}
+    for k in (1, 2, 3):
+        for bits in itertools.combinations(local, k):
+            d = emu.emu_conflict_degree_tpass(n, dt, k, _ip(bits), 2, _ip(hi))
+            assert 1 <= d <= 2, (bits, d)
+            hist.setdefault(k, []).append(d)
+            if k == 1 or (k == 2 and bits[1] == bits[0] + 1):
+                assert d == 1, (bits, d)
+    assert np.mean(np.array(hist[2]) == 1) > 0.9
+
+
+def _random_regtile_pass(rng, n, avail, max_tiles=8):
+    """random register tiles (<= 4 bits) of 1-/2-bit gates inside `avail`; returns the ABI arrays
+    and the gate list [(bits, u)] in execution order"""
+    rt_k, rt_bits, rt_nsub, sub_k, sub_bits, mats, gates = [], [], [], [], [], [], []
+    for _ in range(int(rng.integers(1, max_tiles + 1))):
+        kt = int(rng.integers(1, 5))
+        tb = sorted(rng.choice(avail, size=kt, replace=False).tolist())
+        ns = int(rng.integers(1, 5))
+        rt_k.append(kt)
+        rt_bits += tb
+        rt_nsub.append(ns)
+        for _ in range(ns):
+            k = int(rng.integers(1, min(2, kt) + 1))
+            gb = sorted(rng.choice(tb, size=k, replace=False).tolist())
+            u = rng.normal(size=(2**k, 2**k)) + 1j * rng.normal(size=(2**k, 2**k))
+            u /= np.linalg.norm(u, 2)
+            sub_k.append(k)
+            sub_bits += gb
+            mats.append(np.ascontiguousarray(u, dtype=np.complex128).reshape(-1))
+            gates.append((gb, u))
+    return rt_k, rt_bits, rt_nsub, sub_k, sub_bits, np.concatenate(mats), gates
+
+
+def test_emu_trpass(emu):
+    """trpass_kernel's compute half: 4-bit register tiles with filler positions, group-offset table,
+    gate positions, vec0 / non-vec0 access, on the SWIZZLE_128B box layout."""
+    rng = np.random.default_rng(23)
+    T = emu.emu_pass_tile_bits(0)
+    emu.emu_apply_trpass.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 5 + [
+        ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int64]
+    for trial in range(12):
+        n = int(rng.integers(T + 1, T + 4))
+        batch = 1 if trial % 4 else 2
+        n_hi = min(int(rng.integers(0, 7)), n - T) if trial else 0
+        lrow = T - n_hi
+        hi = sorted(rng.choice(np.arange(lrow, n), size=n_hi, replace=False).tolist()) if n_hi else []
+        avail = list(range(lrow)) + hi
+        if trial == 1:
+            avail = avail[1:]  # bit 0 never a target: every tile gets it as a filler (vec0)
+        rt_k, rt_bits, rt_nsub, sub_k, sub_bits, mats, gates = _random_regtile_pass(rng, n, avail)
+        refs = [_rand_state(rng, n, np.complex64) for _ in range(batch)]
+        got = np.stack(refs).copy()
+        refs = [r.astype(np.complex128) for r in refs]
+        for gb, u in gates:
+            refs = [orc.apply_gate(r, u, _bits_to_qubits(n, gb), n) for r in refs]
+        rc = emu.emu_apply_trpass(got.ctypes.data_as(ctypes.c_void_p), n, len(rt_k), _ip(rt_k), _ip(rt_bits), _ip(rt_nsub), _ip(sub_k),
+                                  _ip(sub_bits), _dp(mats.view(np.float64)), n_hi, _ip(hi if hi else [0]), batch)
+        assert rc == 0, (rc, emu.emu_last_error())
+        for bi in range(batch):
+            err = np.linalg.norm(got[bi] - refs[bi]) / np.linalg.norm(refs[bi])
+            assert err < 100 * TOL[np.complex64], (trial, bi, err)

@@ -404,3 +404,122 @@ def test_config3_full_size_vmap_1024x20():
         o = orc.run_gatelist(n, orc.hea_circuit(n, params[b]))
         want = sum(w * o.expectation_ps(ps=ps).real for w, ps in terms)
         assert abs(got[b] - want) / max(abs(want), 1e-3 * len(terms)) < 1e-5, b
+
+
+# ---- persistent TMA pipeline (tpass.cu) ------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_tma_pass_vs_oracle_and_staged_kernel(dtype, monkeypatch):
+    """tcb200_apply_pass_host through tpass_kernel (default) and through cpass_kernel
+    (TCB200_TMA=0): both against the oracle, and bit-identical to each other (same FMA order)."""
+    monkeypatch.setenv("TCB200_TMA_STRICT", "1")
+    rng = np.random.default_rng(5)
+    T = _lib.lib.tcb200_pass_tile_bits(0 if dtype == "complex64" else 1)
+    for trial in range(10):
+        n = int(rng.integers(T + 1, T + 7))
+        batch = 1 if trial % 3 else 3
+        n_hi = min(int(rng.integers(0, 7)), n - T) if trial else 0
+        lrow = T - n_hi
+        hi = sorted(rng.choice(np.arange(lrow, n), size=n_hi, replace=False).tolist())
+        avail = list(range(lrow)) + hi
+        psis = [_rand_state(rng, n) for _ in range(batch)]
+        refs = [p.copy() for p in psis]
+        blocks = []
+        mat_bytes = 0
+        for _ in range(int(rng.integers(1, 9))):
+            k = int(rng.integers(1, 5))
+            mat_bytes += 4**k * (8 if dtype == "complex64" else 16)
+            if mat_bytes > 12 * 1024:  # the pass blob of matrices is limited to 12 KiB
+                break
+            bits = sorted(rng.choice(avail, size=k, replace=False).tolist())
+            u = rng.normal(size=(2**k, 2**k)) + 1j * rng.normal(size=(2**k, 2**k))
+            u /= np.linalg.norm(u, 2)
+            refs = [orc.apply_gate(r, u, _bits_to_qubits(n, bits), n) for r in refs]
+            blocks.append(_block(n, bits, u))
+        outs = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("TCB200_TMA", mode)
+            st = DeviceState(n, dtype, batch=batch)
+            for b in range(batch):
+                st.buf[b].copy_(torch.as_tensor(psis[b]).to(st.buf.dtype))
+            c0 = _lib.lib.tcb200_tma_pass_count()
+            st.apply_pass_host(blocks, hi)
+            torch.cuda.synchronize()
+            assert _lib.lib.tcb200_tma_pass_count() - c0 == (1 if mode == "1" else 0), (trial, mode)
+            outs[mode] = st.buf.cpu().numpy()
+            for b in range(batch):
+                assert _relerr(outs[mode][b], refs[b]) < 5 * TOL[dtype], (trial, mode, b)
+        if dtype == "complex128":
+            assert np.array_equal(outs["0"], outs["1"]), trial
+        else:  # complex64 passes of narrow blocks run as register tiles: same math, other schedule
+            assert np.abs(outs["0"] - outs["1"]).max() < 1e-6, trial
+
+
+def test_tma_pass_many_tiles_per_cta(monkeypatch):
+    """2^24 amplitudes = 2048 tiles over 148 persistent CTAs: the ring wraps ~14 times per CTA
+    (mbarrier phases, buffer hand-over between bulk stores and loads)."""
+    monkeypatch.setenv("TCB200_TMA", "1")
+    n, dtype = 24, "complex64"
+    c = tc.Circuit(n)
+    ops = orc.random_circuit(n, 4, seed=11)
+    for name, q, p in ops:
+        getattr(c, name)(*q, **p)
+    c0 = _lib.lib.tcb200_tma_pass_count()
+    got = np.asarray(c.state())
+    assert _lib.lib.tcb200_tma_pass_count() > c0
+    o = orc.run_gatelist(n, ops)
+    assert _relerr(got, o.state()) < 2e-5
+
+
+def test_tma_regtile_pass_vs_oracle(monkeypatch):
+    """tcb200_apply_rpass_host through trpass_kernel: random <= 4-bit register tiles of 1-/2-bit
+    gates (filler positions, vec0 and non-vec0 access, gathered bits, batch > 1)."""
+    import ctypes
+
+    monkeypatch.setenv("TCB200_TMA_STRICT", "1")
+    monkeypatch.setenv("TCB200_TMA", "1")
+    rng = np.random.default_rng(29)
+    T = _lib.lib.tcb200_pass_tile_bits(0)
+    ip = _lib.iptr
+    for trial in range(12):
+        n = int(rng.integers(T + 1, T + 7))
+        batch = 1 if trial % 4 else 2
+        n_hi = min(int(rng.integers(0, 7)), n - T) if trial else 0
+        lrow = T - n_hi
+        hi = sorted(rng.choice(np.arange(lrow, n), size=n_hi, replace=False).tolist())
+        avail = list(range(lrow)) + hi
+        if trial == 1:
+            avail = avail[1:]
+        rt_k, rt_bits, rt_nsub, sub_k, sub_bits, mats, gates = [], [], [], [], [], [], []
+        for _ in range(int(rng.integers(1, 9))):
+            kt = int(rng.integers(1, 5))
+            tb = sorted(rng.choice(avail, size=kt, replace=False).tolist())
+            ns = int(rng.integers(1, 5))
+            rt_k.append(kt)
+            rt_bits += tb
+            rt_nsub.append(ns)
+            for _ in range(ns):
+                k = int(rng.integers(1, min(2, kt) + 1))
+                gb = sorted(rng.choice(tb, size=k, replace=False).tolist())
+                u = rng.normal(size=(2**k, 2**k)) + 1j * rng.normal(size=(2**k, 2**k))
+                u /= np.linalg.norm(u, 2)
+                sub_k.append(k)
+                sub_bits += gb
+                mats.append(np.ascontiguousarray(u, dtype=np.complex128).reshape(-1))
+                gates.append((gb, u))
+        mats = np.concatenate(mats)
+        psis = [_rand_state(rng, n) for _ in range(batch)]
+        refs = [p.copy() for p in psis]
+        for gb, u in gates:
+            refs = [orc.apply_gate(r, u, _bits_to_qubits(n, gb), n) for r in refs]
+        st = DeviceState(n, "complex64", batch=batch)
+        for b in range(batch):
+            st.buf[b].copy_(torch.as_tensor(psis[b]).to(st.buf.dtype))
+        a = [np.asarray(x, dtype=np.int32) for x in (rt_k, rt_bits, rt_nsub, sub_k, sub_bits, hi if hi else [0])]
+        c0 = _lib.lib.tcb200_tma_pass_count()
+        _lib.check(_lib.lib.tcb200_apply_rpass_host(ctypes.c_void_p(st.buf.data_ptr()), n, 0, len(rt_k), ip(a[0]), ip(a[1]), ip(a[2]), ip(a[3]),
+                                                    ip(a[4]), _lib.dptr(mats.view(np.float64)), n_hi, ip(a[5]), batch, None))
+        torch.cuda.synchronize()
+        assert _lib.lib.tcb200_tma_pass_count() == c0 + 1
+        out = st.buf.cpu().numpy()
+        for b in range(batch):
+            assert _relerr(out[b], refs[b]) < 10 * TOL["complex64"], (trial, b)
