@@ -136,9 +136,12 @@ class DeviceState:
         for b in blocks:
             self.apply_block(b)
 
-    # widest set of gathered high bits a staged pass may use (64 KiB tile: 7 low bits stay
-    # contiguous = 1 KiB rows for complex64)
-    pass_max_hi = int(os.environ.get("TCB200_PASS_MAX_HI", "6"))
+    # widest set of gathered high bits a staged pass may use.  64 KiB tile, 8 gathered bits: the 5
+    # low bits stay contiguous (256-byte rows for complex64).  Measured on the config-4 recipe:
+    # n = 32: 60 / 47 / 44 / 41 passes and 1380 / 1247 / 1261 / 1212 ms for max_hi = 5 / 6 / 7 / 8;
+    # n = 33: 2575 -> 2475 ms from 6 to 7 (profiles/README.md) -- fewer, fuller passes win although
+    # the shorter rows cost some HBM efficiency per pass.
+    pass_max_hi = int(os.environ.get("TCB200_PASS_MAX_HI", "8"))
 
     def apply_planned(self, blocks: Sequence[Block]) -> int:
         """Run ``blocks`` as staged multi-block passes (fusion.plan_passes): each pass is one HBM

@@ -233,7 +233,7 @@ def test_emu_tpass(emu, dtype):
     for trial in range(10):
         n = int(rng.integers(T + 1, T + 5))
         batch = 1 if trial % 3 else 3
-        n_hi = min(int(rng.integers(0, 7)), n - T) if trial else 0   # trial 0: h = 0 (row longer than a box)
+        n_hi = min(int(rng.integers(0, 9)), n - T) if trial else 0   # trial 0: h = 0 (row longer than a box)
         lrow = T - n_hi
         hi = sorted(rng.choice(np.arange(lrow, n), size=n_hi, replace=False).tolist()) if n_hi else []
         avail = list(range(lrow)) + hi
@@ -314,7 +314,7 @@ def test_emu_trpass(emu):
     for trial in range(12):
         n = int(rng.integers(T + 1, T + 4))
         batch = 1 if trial % 4 else 2
-        n_hi = min(int(rng.integers(0, 7)), n - T) if trial else 0
+        n_hi = min(int(rng.integers(0, 9)), n - T) if trial else 0
         lrow = T - n_hi
         hi = sorted(rng.choice(np.arange(lrow, n), size=n_hi, replace=False).tolist()) if n_hi else []
         avail = list(range(lrow)) + hi

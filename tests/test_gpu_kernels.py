@@ -417,7 +417,7 @@ def test_tma_pass_vs_oracle_and_staged_kernel(dtype, monkeypatch):
     for trial in range(10):
         n = int(rng.integers(T + 1, T + 7))
         batch = 1 if trial % 3 else 3
-        n_hi = min(int(rng.integers(0, 7)), n - T) if trial else 0
+        n_hi = min(int(rng.integers(0, 9)), n - T) if trial else 0
         lrow = T - n_hi
         hi = sorted(rng.choice(np.arange(lrow, n), size=n_hi, replace=False).tolist())
         avail = list(range(lrow)) + hi
@@ -483,7 +483,7 @@ def test_tma_regtile_pass_vs_oracle(monkeypatch):
     for trial in range(12):
         n = int(rng.integers(T + 1, T + 7))
         batch = 1 if trial % 4 else 2
-        n_hi = min(int(rng.integers(0, 7)), n - T) if trial else 0
+        n_hi = min(int(rng.integers(0, 9)), n - T) if trial else 0
         lrow = T - n_hi
         hi = sorted(rng.choice(np.arange(lrow, n), size=n_hi, replace=False).tolist())
         avail = list(range(lrow)) + hi
