@@ -296,29 +296,11 @@ struct CPassParams {
     typename CT<Real>::type m[CPASS_MAT_BYTES / sizeof(typename CT<Real>::type)];
 };
 
+// the blocks of the pass on one staged tile (a __syncthreads() after every block)
 template <typename Real>
-__global__ void __launch_bounds__(256) cpass_kernel(const __grid_constant__ CPassParams<Real> p) {
+__device__ __forceinline__ void cpass_ops(const CPassParams<Real>& p, typename CT<Real>::type* tile,
+                                          const typename CT<Real>::type* bm, int tid, int nthr) {
     using C = typename CT<Real>::type;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    C* tile = reinterpret_cast<C*>(smem_raw);
-    __shared__ uint64_t rowoff[256];
-
-    const int tid = threadIdx.x;
-    const int nthr = blockDim.x;
-    if (tid < (1 << p.g.h)) rowoff[tid] = row_offset(p.g, tid);
-    C* vec = p.state + ((uint64_t)blockIdx.y << p.g.n);
-    const uint64_t base = tile_base(p.g, blockIdx.x);
-    // The constant bank is only the transport of the matrices: an index that depends on the
-    // op counter would make every FMA operand a register-indexed LDC.  Copy them once per CTA
-    // behind the tile; 1- and 2-bit blocks then keep their matrix in registers for all the
-    // groups of a thread, wider blocks read it with broadcast LDS.
-    C* bm = tile + (1u << p.g.T);
-    for (int i = tid; i < p.mat_total; i += nthr) bm[i] = p.m[i];
-    __syncthreads();
-    stage_in<C, true>(p.g, vec, base, tile, rowoff, tid, nthr);
-    cp_async_wait_all();
-    __syncthreads();
-
     for (int o = 0; o < p.nops; ++o) {
         const PassOp& op = p.op[o];
         const C* m = bm + op.moff;
@@ -346,6 +328,32 @@ __global__ void __launch_bounds__(256) cpass_kernel(const __grid_constant__ CPas
         }
         __syncthreads();
     }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) cpass_kernel(const __grid_constant__ CPassParams<Real> p) {
+    using C = typename CT<Real>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    C* tile = reinterpret_cast<C*>(smem_raw);
+    __shared__ uint64_t rowoff[256];
+
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    if (tid < (1 << p.g.h)) rowoff[tid] = row_offset(p.g, tid);
+    C* vec = p.state + ((uint64_t)blockIdx.y << p.g.n);
+    const uint64_t base = tile_base(p.g, blockIdx.x);
+    // The constant bank is only the transport of the matrices: an index that depends on the
+    // op counter would make every FMA operand a register-indexed LDC.  Copy them once per CTA
+    // behind the tile; 1- and 2-bit blocks then keep their matrix in registers for all the
+    // groups of a thread, wider blocks read it with broadcast LDS.
+    C* bm = tile + (1u << p.g.T);
+    for (int i = tid; i < p.mat_total; i += nthr) bm[i] = p.m[i];
+    __syncthreads();
+    stage_in<C, true>(p.g, vec, base, tile, rowoff, tid, nthr);
+    cp_async_wait_all();
+    __syncthreads();
+
+    cpass_ops<Real>(p, tile, bm, tid, nthr);
     stage_out<C, true>(p.g, vec, base, tile, rowoff, tid, nthr);
 }
 

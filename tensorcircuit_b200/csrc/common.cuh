@@ -239,6 +239,18 @@ __device__ __forceinline__ void cp_async_wait_all() {
 #endif
 }
 
+__device__ __forceinline__ void cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+#endif
+}
+
 struct alignas(16) Unit16 {
     uint32_t w[4];
 };
@@ -420,6 +432,10 @@ template <typename C, int K, typename Mat>
 TCB_HD void apply_block_dispatch(C* tile, const GroupMap& gm, int tid, int nthr, int tb, const Mat& mat) {
     if (nthr == 256) {
         const int nl = gm.ngb - 8;
+        if (nl == 11 - K - 8 && 11 - K - 8 >= 0) {
+            apply_block_fast<C, K, (11 - K - 8 >= 0 ? 11 - K - 8 : 0)>(tile, gm, tid, mat);
+            return;
+        }
         if (nl == 12 - K - 8 && 12 - K - 8 >= 0) {
             apply_block_fast<C, K, (12 - K - 8 >= 0 ? 12 - K - 8 : 0)>(tile, gm, tid, mat);
             return;
