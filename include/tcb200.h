@@ -231,6 +231,19 @@ int tcb200_run_circuit_host(void* state, int nbits, int dtype, int init_zero, in
                             int64_t shots, const double* uniforms_host, int64_t* out_idx_host,
                             void* workspace, size_t ws_bytes, void* stream);
 
+/* Diagonal Pauli strings (only I and Z): expectation_ps(z=[...]) / the cost function of an Ising
+ * or QAOA Hamiltonian, quantum.py:1461-1482 with an empty flip mask.  Up to
+ * tcb200_expect_z_max_terms(dtype) strings (32 complex64 / 16 complex128) are evaluated in ONE
+ * streaming read of the state -- no tile, no shared memory, one FFMA per (amplitude, string) -- against
+ * 8 strings per read in tcb200_expect_pauli.  sign[t]: amplitude-index bits carrying a Z.
+ * out_dev: [batch][nterms][2] doubles (imaginary parts are 0), device memory.  The state must have at
+ * least tcb200_expect_z_min_bits(dtype) bits (13 / 12); smaller states go through tcb200_expect_pauli. */
+int tcb200_expect_z_max_terms(int dtype);
+int tcb200_expect_z_min_bits(int dtype);
+size_t tcb200_expect_z_workspace_bytes(int nbits, int64_t batch);
+int tcb200_expect_z(const void* state, int nbits, int dtype, int nterms, const uint64_t* sign,
+                    double* out_dev, int64_t batch, void* workspace, size_t ws_bytes, void* stream);
+
 /* Number of kernel launches issued by this process through the library so far. */
 int64_t tcb200_launch_count(void);
 

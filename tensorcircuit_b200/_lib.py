@@ -60,6 +60,10 @@ def _load() -> ctypes.CDLL:
         "tcb200_probability": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p]),
         "tcb200_expect_pauli": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_int), c_int, POINTER(c_int), c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
         "tcb200_expect_workspace_bytes": (c_size_t, [c_int, c_int64]),
+        "tcb200_expect_z_max_terms": (c_int, [c_int]),
+        "tcb200_expect_z_min_bits": (c_int, [c_int]),
+        "tcb200_expect_z_workspace_bytes": (c_size_t, [c_int, c_int64]),
+        "tcb200_expect_z": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_uint64), c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
         "tcb200_expect_tile_bits": (c_int, [c_int]),
         "tcb200_sample": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_double, c_double, c_void_p, c_size_t, c_void_p]),
         "tcb200_sample_workspace_bytes": (c_size_t, [c_int]),
@@ -78,7 +82,8 @@ EXPORTS = [
     "tcb200_set_zero", "tcb200_copy_rows",
     "tcb200_apply_dense", "tcb200_apply_dense_batched", "tcb200_apply_diag", "tcb200_apply_pass", "tcb200_apply_pass_host", "tcb200_apply_rpass_host",
     "tcb200_pass_tile_bits", "tcb200_norm2", "tcb200_reduce_workspace_bytes", "tcb200_probability",
-    "tcb200_expect_pauli", "tcb200_expect_workspace_bytes", "tcb200_expect_tile_bits", "tcb200_sample",
+    "tcb200_expect_pauli", "tcb200_expect_workspace_bytes", "tcb200_expect_tile_bits",
+    "tcb200_expect_z_max_terms", "tcb200_expect_z_min_bits", "tcb200_expect_z_workspace_bytes", "tcb200_expect_z", "tcb200_sample",
     "tcb200_sample_workspace_bytes", "tcb200_run_circuit_host",
 ]
 

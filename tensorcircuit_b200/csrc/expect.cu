@@ -211,3 +211,240 @@ int tcb200_expect_pauli(const void* state, int nbits, int dtype, int nterms,
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Diagonal strings (only I / Z): <P_t> = sum_e |psi_e|^2 (-1)^{popc(e & mask_t)}
+// ------------------------------------------------------------------------------------------------
+// No partner amplitude is needed, so there is no tile and no shared memory: every thread
+// streams 16-byte loads, and the sign of (amplitude, term) is split as
+//     popc(e & m) = popc(chunk_base & m) + popc(thread_offset & m) + popc(iteration_offset & m)   (mod 2)
+// The iteration part is the same for all threads: a +-1 table in the kernel-parameter constant
+// bank, so one (amplitude, term) pair costs exactly ONE FFMA with a constant operand.  The chunk
+// part is applied once per chunk (2^13 amplitudes), the thread part once at the end.  32 strings
+// (16 for complex128) ride on one read of the state: a QAOA / Ising cost function is one pass.
+namespace tcb {
+
+constexpr int ZK = 16;  // 16-byte loads per thread and chunk
+
+template <typename Real>
+struct ZCfg {
+    static constexpr int ZT = sizeof(Real) == 4 ? 32 : 16;  // strings per launch
+    static constexpr int APU = CT<Real>::APU;
+    static constexpr int AB = APU == 2 ? 1 : 0;
+    static constexpr int CHUNK_BITS = 4 + 8 + AB;  // ZK x 256 threads x APU amplitudes
+};
+
+template <typename Real>
+struct ZExpectParams {
+    const void* state;
+    double* partials;  // [batch][gridDim.x][ZT]
+    int nbits;
+    uint64_t mask[ZCfg<Real>::ZT];
+    Real s[ZK][ZCfg<Real>::APU][ZCfg<Real>::ZT];  // (-1)^{popc(iteration offset & mask)}
+};
+
+// one chunk of one thread: tmp[t] += sum over its ZK * APU amplitudes of s * |psi|^2
+template <typename Real>
+TCB_HD void zexpect_chunk(const typename CT<Real>::type* vec, uint64_t base, int tid,
+                          const Real (*s)[ZCfg<Real>::APU][ZCfg<Real>::ZT], Real* tmp) {
+    using C = typename CT<Real>::type;
+    constexpr int ZT = ZCfg<Real>::ZT, APU = ZCfg<Real>::APU;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        Unit16 q[ZK / 2];
+#pragma unroll
+        for (int i = 0; i < ZK / 2; ++i) {
+            const C* src = vec + base + (uint64_t)(half * (ZK / 2) + i) * (256 * APU) + (uint64_t)tid * APU;
+#if defined(__CUDA_ARCH__)
+            const uint4 r = __ldg(reinterpret_cast<const uint4*>(src));
+            q[i].w[0] = r.x; q[i].w[1] = r.y; q[i].w[2] = r.z; q[i].w[3] = r.w;
+#else
+            q[i] = *reinterpret_cast<const Unit16*>(src);
+#endif
+        }
+#pragma unroll
+        for (int i = 0; i < ZK / 2; ++i) {
+            const C* a = reinterpret_cast<const C*>(&q[i]);
+#pragma unroll
+            for (int j = 0; j < APU; ++j) {
+                const Real p = a[j].x * a[j].x + a[j].y * a[j].y;
+#pragma unroll
+                for (int t = 0; t < ZT; ++t) tmp[t] = fma(p, s[half * (ZK / 2) + i][j][t], tmp[t]);
+            }
+        }
+    }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256, 2) zexpect_kernel(const __grid_constant__ ZExpectParams<Real> p) {
+    using C = typename CT<Real>::type;
+    constexpr int ZT = ZCfg<Real>::ZT, AB = ZCfg<Real>::AB, CB = ZCfg<Real>::CHUNK_BITS;
+    __shared__ double red[8][ZT];
+    const int tid = threadIdx.x;
+    const C* vec = static_cast<const C*>(p.state) + ((uint64_t)blockIdx.y << p.nbits);
+    const uint64_t nchunks = 1ull << (p.nbits - CB);
+    Real acc[ZT];
+#pragma unroll
+    for (int t = 0; t < ZT; ++t) acc[t] = 0;
+    for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const uint64_t base = c << CB;
+        Real tmp[ZT];
+#pragma unroll
+        for (int t = 0; t < ZT; ++t) tmp[t] = 0;
+        zexpect_chunk<Real>(vec, base, tid, p.s, tmp);
+#pragma unroll
+        for (int t = 0; t < ZT; ++t) acc[t] += parity64(base & p.mask[t]) ? -tmp[t] : tmp[t];
+    }
+    const int w = tid >> 5, l = tid & 31;
+#pragma unroll
+    for (int t = 0; t < ZT; ++t) {
+        double v = (double)acc[t];
+        if (parity64(((uint64_t)tid << AB) & p.mask[t])) v = -v;
+        v = warp_sum_d(v);
+        if (l == 0) red[w][t] = v;
+    }
+    __syncthreads();
+    if (tid < ZT) {
+        double sum = 0.0;
+        for (int ww = 0; ww < 8; ++ww) sum += red[ww][tid];
+        p.partials[((uint64_t)blockIdx.y * gridDim.x + blockIdx.x) * ZT + tid] = sum;
+    }
+}
+
+struct ZFinalParams {
+    const double* partials;
+    double* out;  // [batch][nterms][2]
+    int nctas;
+    int nterms;
+    int zt;
+};
+
+__global__ void zexpect_final_kernel(const __grid_constant__ ZFinalParams p) {
+    const int t = threadIdx.x;
+    if (t >= p.nterms) return;
+    const double* src = p.partials + (uint64_t)blockIdx.x * p.nctas * p.zt;
+    double re = 0.0;
+    for (int c = 0; c < p.nctas; ++c) re += src[(uint64_t)c * p.zt + t];
+    double* o = p.out + ((uint64_t)blockIdx.x * p.nterms + t) * 2;
+    o[0] = re;
+    o[1] = 0.0;
+}
+
+static unsigned zexpect_grid_x(int nbits, int chunk_bits, int64_t batch) {
+    const uint64_t nchunks = 1ull << (nbits - chunk_bits);
+    uint64_t cap = (148ull * 8) / (uint64_t)batch;
+    if (cap < 4) cap = 4;
+    return (unsigned)(nchunks < cap ? nchunks : cap);
+}
+
+template <typename Real>
+static void zexpect_fill(ZExpectParams<Real>& p, int nterms, const uint64_t* sign) {
+    constexpr int ZT = ZCfg<Real>::ZT, APU = ZCfg<Real>::APU, AB = ZCfg<Real>::AB;
+    for (int t = 0; t < ZT; ++t) {
+        p.mask[t] = t < nterms ? sign[t] : 0ull;
+        for (int k = 0; k < ZK; ++k)
+            for (int j = 0; j < APU; ++j) {
+                const uint64_t off = ((uint64_t)k << (8 + AB)) | (uint64_t)j;
+                p.s[k][j][t] = parity64(off & p.mask[t]) ? (Real)-1 : (Real)1;
+            }
+    }
+}
+
+template <typename Real>
+static int launch_zexpect(const void* state, int nbits, int nterms, const uint64_t* sign, double* out_dev,
+                          int64_t batch, void* workspace, cudaStream_t st) {
+    constexpr int ZT = ZCfg<Real>::ZT, CB = ZCfg<Real>::CHUNK_BITS;
+    static thread_local ZExpectParams<Real>* tp = nullptr;
+    if (!tp) tp = new ZExpectParams<Real>();
+    ZExpectParams<Real>& p = *tp;
+    p.state = state;
+    p.partials = static_cast<double*>(workspace);
+    p.nbits = nbits;
+    zexpect_fill<Real>(p, nterms, sign);
+    const unsigned gx = zexpect_grid_x(nbits, CB, batch);
+    dim3 grid(gx, (unsigned)batch);
+    zexpect_kernel<Real><<<grid, 256, 0, st>>>(p);
+    TCB_LAUNCH_CHECK("zexpect_kernel");
+    ZFinalParams f;
+    f.partials = p.partials;
+    f.out = out_dev;
+    f.nctas = (int)gx;
+    f.nterms = nterms;
+    f.zt = ZT;
+    zexpect_final_kernel<<<(unsigned)batch, 32, 0, st>>>(f);
+    TCB_LAUNCH_CHECK("zexpect_final_kernel");
+    return 0;
+}
+
+#ifdef TCB200_EMU
+// tests/emu only: the same parameter block and per-thread chunk body on the CPU
+template <typename Real>
+static int emu_zexpect_t(const void* state, int nbits, int nterms, const uint64_t* sign, double* out) {
+    using C = typename CT<Real>::type;
+    constexpr int ZT = ZCfg<Real>::ZT, AB = ZCfg<Real>::AB, CB = ZCfg<Real>::CHUNK_BITS;
+    if (nbits < CB || nterms < 1 || nterms > ZT) return 1;
+    ZExpectParams<Real>* pp = new ZExpectParams<Real>();
+    ZExpectParams<Real>& p = *pp;
+    zexpect_fill<Real>(p, nterms, sign);
+    const C* vec = static_cast<const C*>(state);
+    double tot[ZT] = {0};
+    for (uint64_t c = 0; c < (1ull << (nbits - CB)); ++c)
+        for (int tid = 0; tid < 256; ++tid) {
+            Real tmp[ZT];
+            for (int t = 0; t < ZT; ++t) tmp[t] = 0;
+            zexpect_chunk<Real>(vec, c << CB, tid, p.s, tmp);
+            for (int t = 0; t < ZT; ++t) {
+                double v = parity64((c << CB) & p.mask[t]) ? -(double)tmp[t] : (double)tmp[t];
+                if (parity64(((uint64_t)tid << AB) & p.mask[t])) v = -v;
+                tot[t] += v;
+            }
+        }
+    for (int t = 0; t < nterms; ++t) out[t] = tot[t];
+    delete pp;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int emu_expect_z(const void* state, int nbits, int dtype, int nterms,
+                                                                    const uint64_t* sign, double* out) {
+    return dtype == TCB200_C64 ? emu_zexpect_t<float>(state, nbits, nterms, sign, out)
+                               : emu_zexpect_t<double>(state, nbits, nterms, sign, out);
+}
+#endif
+
+}  // namespace tcb
+
+extern "C" {
+
+int tcb200_expect_z_max_terms(int dtype) { return dtype == TCB200_C64 ? ZCfg<float>::ZT : ZCfg<double>::ZT; }
+
+int tcb200_expect_z_min_bits(int dtype) { return dtype == TCB200_C64 ? ZCfg<float>::CHUNK_BITS : ZCfg<double>::CHUNK_BITS; }
+
+size_t tcb200_expect_z_workspace_bytes(int nbits, int64_t batch) {
+    (void)nbits;
+    if (batch < 1) batch = 1;
+    // partials [batch][grid.x][32]; grid.x * batch <= 148 * 8 + 4 * batch (zexpect_grid_x)
+    return ((size_t)148 * 8 + 4 * (size_t)batch) * 32 * sizeof(double) + 256;
+}
+
+int tcb200_expect_z(const void* state, int nbits, int dtype, int nterms, const uint64_t* sign,
+                    double* out_dev, int64_t batch, void* workspace, size_t ws_bytes, void* stream) {
+    if (!state || !sign || !out_dev || !workspace) return fail(TCB200_ERR_ARG, "NULL argument");
+    if (dtype != TCB200_C64 && dtype != TCB200_C128) return fail(TCB200_ERR_ARG, "bad dtype %d", dtype);
+    if (nbits < 1 || nbits > 40) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
+    if (nterms < 1 || nterms > tcb200_expect_z_max_terms(dtype)) return fail(TCB200_ERR_ARG, "nterms=%d out of range", nterms);
+    if (batch < 1 || batch > 65535) return fail(TCB200_ERR_ARG, "batch=%lld out of range", (long long)batch);
+    if (ws_bytes < tcb200_expect_z_workspace_bytes(nbits, batch)) return fail(TCB200_ERR_WORKSPACE, "workspace too small");
+    const uint64_t full = (1ull << nbits) - 1ull;
+    for (int t = 0; t < nterms; ++t)
+        if (sign[t] & ~full) return fail(TCB200_ERR_ARG, "mask of term %d exceeds the state", t);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int cb = dtype == TCB200_C64 ? ZCfg<float>::CHUNK_BITS : ZCfg<double>::CHUNK_BITS;
+    if (nbits < cb)
+        return fail(TCB200_ERR_UNSUPPORTED, "tcb200_expect_z needs a state of >= %d bits (use tcb200_expect_pauli)", cb);
+    if ((size_t)batch * zexpect_grid_x(nbits, cb, batch) * 32 * sizeof(double) > ws_bytes)
+        return fail(TCB200_ERR_WORKSPACE, "workspace too small");
+    if (dtype == TCB200_C64) return launch_zexpect<float>(state, nbits, nterms, sign, out_dev, batch, workspace, st);
+    return launch_zexpect<double>(state, nbits, nterms, sign, out_dev, batch, workspace, st);
+}
+
+}  // extern "C"

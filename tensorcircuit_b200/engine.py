@@ -251,9 +251,25 @@ class DeviceState:
         if nt == 0:
             return out_all
         T = lib.tcb200_expect_tile_bits(self.dt)
-        groups = plan_expect_groups(flips, self.nbits, T)
-        ws = self._workspace(lib.tcb200_expect_workspace_bytes(self.nbits, self.batch))
         outs = []
+        rest = list(range(nt))
+        if self.nbits >= lib.tcb200_expect_z_min_bits(self.dt):
+            # diagonal strings (no X / Y): 32 (16 for complex128) per streaming read of the state
+            zids = [t for t in rest if int(flips[t]) == 0]
+            rest = [t for t in rest if int(flips[t]) != 0]
+            zt = lib.tcb200_expect_z_max_terms(self.dt)
+            wsz = self._workspace(lib.tcb200_expect_z_workspace_bytes(self.nbits, self.batch))
+            for c0 in range(0, len(zids), zt):
+                ids = zids[c0 : c0 + zt]
+                s = np.asarray([int(signs[t]) for t in ids], dtype=np.uint64)
+                out = torch.empty((self.batch, len(ids), 2), dtype=torch.float64, device=self.device)
+                check(lib.tcb200_expect_z(_ptr(self.buf), self.nbits, self.dt, len(ids), _lib.u64ptr(s), _ptr(out), self.batch,
+                                          _ptr(wsz), wsz.numel(), _stream()))
+                STATS["expect_launches"] += 1
+                outs.append((ids, out))
+        sub = plan_expect_groups([flips[t] for t in rest], self.nbits, T)
+        groups = [([rest[i] for i in ids], union) for ids, union in sub]
+        ws = self._workspace(lib.tcb200_expect_workspace_bytes(self.nbits, self.batch))
         for ids, union in groups:
             hi = tile_hi_fixpoint(union, T, self.nbits)
             f = np.asarray([int(flips[t]) for t in ids], dtype=np.uint64)

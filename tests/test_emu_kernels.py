@@ -24,7 +24,8 @@ def _build_emu():
     # apply.cu is compiled with -DTCB200_EMU only here: that adds the CPU execution of the
     # register-tile pass (same parameter block and device functions as rpass_kernel)
     srcs = [os.path.join(EMU_DIR, "emu.cu"), os.path.join(ROOT, "tensorcircuit_b200", "csrc", "abi.cu"),
-            os.path.join(ROOT, "tensorcircuit_b200", "csrc", "apply.cu"), os.path.join(ROOT, "tensorcircuit_b200", "csrc", "tpass.cu")]
+            os.path.join(ROOT, "tensorcircuit_b200", "csrc", "apply.cu"), os.path.join(ROOT, "tensorcircuit_b200", "csrc", "tpass.cu"),
+            os.path.join(ROOT, "tensorcircuit_b200", "csrc", "expect.cu")]
     deps = srcs + [os.path.join(ROOT, "tensorcircuit_b200", "csrc", "common.cuh"), os.path.join(ROOT, "include", "tcb200.h")]
     if os.path.exists(EMU_LIB) and all(os.path.getmtime(EMU_LIB) > os.path.getmtime(d) for d in deps):
         return
@@ -332,3 +333,26 @@ def test_emu_trpass(emu):
         for bi in range(batch):
             err = np.linalg.norm(got[bi] - refs[bi]) / np.linalg.norm(refs[bi])
             assert err < 100 * TOL[np.complex64], (trial, bi, err)
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_emu_expect_z(emu, dtype):
+    """zexpect_kernel's sign split (chunk / thread / iteration parts of popc(e & mask)) and its
+    constant +-1 table, thread by thread on the CPU, against the oracle's closed form."""
+    dt = 0 if dtype == np.complex64 else 1
+    rng = np.random.default_rng(31)
+    n = 15
+    psi = _rand_state(rng, n, dtype)
+    zt = 32 if dt == 0 else 16
+    for nterms in (1, 5, zt):
+        masks, want = [], []
+        for t in range(nterms):
+            m = int(rng.integers(1, 2**n)) if t else (1 << (n - 1)) | 1  # top and bottom bit
+            z = [n - 1 - b for b in range(n) if (m >> b) & 1]
+            masks.append(m)
+            want.append(orc.pauli_expectation(psi.astype(np.complex128), n, [], [], z).real)
+        out = np.zeros(nterms)
+        ma = np.array(masks, dtype=np.uint64)
+        rc = emu.emu_expect_z(psi.ctypes.data_as(ctypes.c_void_p), n, dt, nterms, ma.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), _dp(out))
+        assert rc == 0
+        np.testing.assert_allclose(out, np.array(want), atol=50 * TOL[dtype])

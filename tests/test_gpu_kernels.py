@@ -523,3 +523,44 @@ def test_tma_regtile_pass_vs_oracle(monkeypatch):
         out = st.buf.cpu().numpy()
         for b in range(batch):
             assert _relerr(out[b], refs[b]) < 10 * TOL["complex64"], (trial, b)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n,batch", [(13, 1), (17, 1), (22, 1), (15, 3)])
+def test_expect_z_kernel(dtype, n, batch):
+    """Diagonal strings through tcb200_expect_z (one streaming read for up to 32 / 16 strings)
+    against the oracle and against the general tile kernel; more strings than one launch holds."""
+    rng = np.random.default_rng(n)
+    psis = [_rand_state(rng, n) for _ in range(batch)]
+    st = DeviceState(n, dtype, batch=batch)
+    for b in range(batch):
+        st.buf[b].copy_(torch.as_tensor(psis[b]).to(st.buf.dtype))
+    nterms = 45
+    masks = [int(m) for m in rng.integers(1, 2**n, size=nterms)]
+    masks[0] = (1 << (n - 1)) | 1
+    masks[1] = (1 << n) - 1
+    want = np.zeros((batch, nterms))
+    for b in range(batch):
+        p = np.abs(psis[b]) ** 2
+        idx = np.arange(2**n, dtype=np.uint64)
+        for t, m in enumerate(masks):
+            par = np.zeros(2**n, dtype=np.uint64)
+            x = idx & np.uint64(m)
+            for s in range(n):
+                par ^= (x >> np.uint64(s)) & np.uint64(1)
+            want[b, t] = np.sum(p * (1.0 - 2.0 * par.astype(np.float64)))
+    engine.reset_stats()
+    got = st.expectation_terms([0] * nterms, masks, [0] * nterms)
+    zt = _lib.lib.tcb200_expect_z_max_terms(0 if dtype == "complex64" else 1)
+    assert engine.STATS["expect_launches"] == -(-nterms // zt)
+    assert np.abs(got.imag).max() == 0.0
+    np.testing.assert_allclose(got.real, want, atol=4 * TOL[dtype])
+    # mixed with flipping strings: ids are scattered back to their places
+    fl = [0, 1, 0, 1 << (n - 1), 0]
+    sg = [masks[0], 0, masks[2], 0, masks[3]]
+    mix = st.expectation_terms(fl, sg, [0] * 5)
+    np.testing.assert_allclose(mix[:, [0, 2, 4]].real, want[:, [0, 2, 3]], atol=4 * TOL[dtype])
+    for b in range(batch):
+        x0 = 2 * np.real(np.vdot(psis[b][0::2], psis[b][1::2]))
+        np.testing.assert_allclose(mix[b, 1].real, x0, atol=4 * TOL[dtype])
+    assert np.array_equal(st.expectation_terms([0] * nterms, masks, [0] * nterms), got)  # deterministic
