@@ -933,41 +933,83 @@ TCB_HD void expect_tile_term(const C* tile, uint32_t tsz, uint32_t fl, uint32_t 
     *out_im = pi;
 }
 
-// All terms of a launch on one staged tile: every amplitude of the thread is loaded once and
-// reused by all terms; Z-type terms (no flip) need no partner load at all.
+TCB_HD uint32_t parity32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(x) & 1u;
+#else
+    x ^= x >> 16;
+    x ^= x >> 8;
+    x ^= x >> 4;
+    x ^= x >> 2;
+    x ^= x >> 1;
+    return x & 1u;
+#endif
+}
+
+// One term on the NI amplitudes a thread holds in registers (elements e0 + i * nthr).
+// ODD: the imaginary component is the non-zero one; SIGNED: the local sign mask is not empty;
+// GUARD: the tile may end inside the NI elements (small states only).
+template <typename C, typename R, int NI, bool ODD, bool SIGNED, bool GUARD>
+TCB_HD R expect_term_loop(const C* a, const C* tile, uint32_t tsz, uint32_t e0, uint32_t nthr, uint32_t f, uint32_t s) {
+    R acc = 0;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const uint32_t e = e0 + (uint32_t)i * nthr;
+        if (GUARD && e >= tsz) break;
+        const C b = tile[e ^ f];
+        R d;
+        if (ODD) {
+            d = a[i].x * b.y;
+            d = fma(-a[i].y, b.x, d);
+        } else {
+            d = a[i].x * b.x;
+            d = fma(a[i].y, b.y, d);
+        }
+        // popc(e & s) = popc(e0 & s) + popc((i * nthr) & s) mod 2: nthr is a power of two above tid
+        if (SIGNED && parity32(((uint32_t)i * nthr) & s)) d = -d;
+        acc += d;
+    }
+    if (SIGNED && parity32(e0 & s)) acc = -acc;
+    return acc;
+}
+
+// All terms of a launch on one staged tile.  The thread's own amplitudes (element tid + i * nthr)
+// are loaded once into registers and reused by every term; a term then costs one partner load
+// and two FMAs per amplitude: S = sum_e conj(psi_e) psi_{e^f} (-1)^{popc(e & s)} is real when the
+// string holds an even number of Y's and imaginary when odd (the string is Hermitian and the
+// phase (-i)^{n_y} is applied afterwards), so only that component is formed (pv[t]) -- bit t of
+// `odd_mask` selects the imaginary one -- and the other is exactly 0.
 template <typename C, typename R, int MT>
 TCB_HD void expect_tile_terms(const C* tile, uint32_t tsz, int nterms, const uint32_t* fl, const uint32_t* sl,
-                              int tid, int nthr, R* pr, R* pi) {
+                              uint32_t odd_mask, int tid, int nthr, R* pv) {
+    constexpr int NI = 8;  // amplitudes held in registers at a time (the 32 KiB tile gives a thread 16 / 8)
 #pragma unroll
-    for (int t = 0; t < MT; ++t) pr[t] = pi[t] = 0;
-    for (uint32_t e = tid; e < tsz; e += nthr) {
-        const C a = tile[e];
-        const R p = a.x * a.x + a.y * a.y;
+    for (int t = 0; t < MT; ++t) pv[t] = 0;
+    const bool whole = (tsz % (NI * (uint32_t)nthr)) == 0;
+    for (uint32_t e0 = (uint32_t)tid; e0 < tsz; e0 += NI * (uint32_t)nthr) {
+        C a[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const uint32_t e = e0 + (uint32_t)i * (uint32_t)nthr;
+            a[i] = (whole || e < tsz) ? tile[e] : mk<C, R>(0, 0);
+        }
 #pragma unroll
         for (int t = 0; t < MT; ++t) {
             if (t < nterms) {
-                R re = p, im = 0;
-                if (fl[t] != 0) {
-                    const C b = tile[e ^ fl[t]];
-                    re = a.x * b.x + a.y * b.y;
-                    im = a.x * b.y - a.y * b.x;
+                const uint32_t f = fl[t], s = sl[t], nt = (uint32_t)nthr;
+                const bool odd = (odd_mask >> t) & 1u;
+                R acc;
+                if (!whole) {
+                    acc = odd ? expect_term_loop<C, R, NI, true, true, true>(a, tile, tsz, e0, nt, f, s)
+                              : expect_term_loop<C, R, NI, false, true, true>(a, tile, tsz, e0, nt, f, s);
+                } else if (s == 0) {
+                    acc = odd ? expect_term_loop<C, R, NI, true, false, false>(a, tile, tsz, e0, nt, f, s)
+                              : expect_term_loop<C, R, NI, false, false, false>(a, tile, tsz, e0, nt, f, s);
+                } else {
+                    acc = odd ? expect_term_loop<C, R, NI, true, true, false>(a, tile, tsz, e0, nt, f, s)
+                              : expect_term_loop<C, R, NI, false, true, false>(a, tile, tsz, e0, nt, f, s);
                 }
-#if defined(__CUDA_ARCH__)
-                const uint32_t par = (uint32_t)__popc(e & sl[t]);
-#else
-                uint32_t par = e & sl[t];
-                par ^= par >> 16;
-                par ^= par >> 8;
-                par ^= par >> 4;
-                par ^= par >> 2;
-                par ^= par >> 1;
-#endif
-                if (par & 1u) {
-                    re = -re;
-                    im = -im;
-                }
-                pr[t] += re;
-                pi[t] += im;
+                pv[t] += acc;
             }
         }
     }

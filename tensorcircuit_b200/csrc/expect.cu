@@ -21,6 +21,7 @@ struct ExpectParams {
     uint32_t flip_l[TCB200_MAX_TERMS];
     uint32_t sign_l[TCB200_MAX_TERMS];
     uint64_t sign_hi[TCB200_MAX_TERMS];  // sign bits outside the tile (global positions)
+    uint32_t odd_mask;                   // bit t: the string holds an odd number of Y's
 };
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -30,13 +31,13 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 template <typename Real>
-__global__ void __launch_bounds__(256, 4) expect_kernel(const __grid_constant__ ExpectParams p) {
+__global__ void __launch_bounds__(256, 3) expect_kernel(const __grid_constant__ ExpectParams p) {
     using C = typename CT<Real>::type;
     constexpr int MT = TCB200_MAX_TERMS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     C* tile = reinterpret_cast<C*>(smem_raw);
     __shared__ uint64_t rowoff[256];
-    __shared__ double red[8][MT][2];
+    __shared__ double red[8][MT];
 
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
@@ -46,9 +47,9 @@ __global__ void __launch_bounds__(256, 4) expect_kernel(const __grid_constant__ 
     const uint64_t ntiles = 1ull << (p.g.n - p.g.T);
     const uint32_t tsz = 1u << p.g.T;
 
-    double acc_re[MT], acc_im[MT];
+    double acc[MT];  // the non-zero component of every term (expect_tile_terms)
 #pragma unroll
-    for (int t = 0; t < MT; ++t) acc_re[t] = acc_im[t] = 0.0;
+    for (int t = 0; t < MT; ++t) acc[t] = 0.0;
 
     for (uint64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
         const uint64_t base = tile_base(p.g, tl);
@@ -56,14 +57,13 @@ __global__ void __launch_bounds__(256, 4) expect_kernel(const __grid_constant__ 
         cp_async_wait_all();
         __syncthreads();
         {
-            Real pr[MT], pi[MT];
-            expect_tile_terms<C, Real, MT>(tile, tsz, p.nterms, p.flip_l, p.sign_l, tid, nthr, pr, pi);
+            Real pv[MT];
+            expect_tile_terms<C, Real, MT>(tile, tsz, p.nterms, p.flip_l, p.sign_l, p.odd_mask, tid, nthr, pv);
 #pragma unroll
             for (int t = 0; t < MT; ++t) {
                 if (t < p.nterms) {
                     const bool neg = parity64(base & p.sign_hi[t]);
-                    acc_re[t] += neg ? -(double)pr[t] : (double)pr[t];
-                    acc_im[t] += neg ? -(double)pi[t] : (double)pi[t];
+                    acc[t] += neg ? -(double)pv[t] : (double)pv[t];
                 }
             }
         }
@@ -74,21 +74,20 @@ __global__ void __launch_bounds__(256, 4) expect_kernel(const __grid_constant__ 
 #pragma unroll
     for (int t = 0; t < MT; ++t) {
         if (t < p.nterms) {
-            const double r = warp_sum_d(acc_re[t]);
-            const double i = warp_sum_d(acc_im[t]);
-            if (l == 0) {
-                red[w][t][0] = r;
-                red[w][t][1] = i;
-            }
+            const double r = warp_sum_d(acc[t]);
+            if (l == 0) red[w][t] = r;
         }
     }
     __syncthreads();
-    if (tid < p.nterms * 2) {
-        const int t = tid >> 1, c = tid & 1;
+    if (tid < p.nterms) {
+        const int t = tid;
         double s = 0.0;
         const int nw = nthr >> 5;
-        for (int ww = 0; ww < nw; ++ww) s += red[ww][t][c];
-        p.partials[(((uint64_t)blockIdx.y * gridDim.x + blockIdx.x) * MT + t) * 2 + c] = s;
+        for (int ww = 0; ww < nw; ++ww) s += red[ww][t];
+        const bool odd = (p.odd_mask >> t) & 1u;
+        double* o = p.partials + (((uint64_t)blockIdx.y * gridDim.x + blockIdx.x) * MT + t) * 2;
+        o[0] = odd ? 0.0 : s;
+        o[1] = odd ? s : 0.0;
     }
 }
 
@@ -100,15 +99,30 @@ struct ExpectFinalParams {
     int ny[TCB200_MAX_TERMS];
 };
 
-__global__ void expect_final_kernel(const __grid_constant__ ExpectFinalParams p) {
+// grid (batch, nterms), 256 threads: strided partial sums, then a fixed shuffle / shared-memory tree
+// (the order of the additions does not depend on timing: results are reproducible bit for bit)
+__global__ void __launch_bounds__(256) expect_final_kernel(const __grid_constant__ ExpectFinalParams p) {
     constexpr int MT = TCB200_MAX_TERMS;
-    const int t = threadIdx.x;
-    if (t >= p.nterms) return;
+    __shared__ double red[8][2];
+    const int t = blockIdx.y, tid = threadIdx.x;
     const double* src = p.partials + (uint64_t)blockIdx.x * p.nctas * MT * 2;
     double re = 0.0, im = 0.0;
-    for (int c = 0; c < p.nctas; ++c) {
+    for (int c = tid; c < p.nctas; c += 256) {
         re += src[((uint64_t)c * MT + t) * 2];
         im += src[((uint64_t)c * MT + t) * 2 + 1];
+    }
+    re = warp_sum_d(re);
+    im = warp_sum_d(im);
+    if ((tid & 31) == 0) {
+        red[tid >> 5][0] = re;
+        red[tid >> 5][1] = im;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    re = im = 0.0;
+    for (int w = 0; w < 8; ++w) {
+        re += red[w][0];
+        im += red[w][1];
     }
     // times (-i)^ny
     double ore = re, oim = im;
@@ -183,6 +197,7 @@ int tcb200_expect_pauli(const void* state, int nbits, int dtype, int nterms,
         p.flip_l[t] = fl;
         p.sign_l[t] = sl;
         p.sign_hi[t] = shi;
+        if (ny[t] & 1) p.odd_mask |= 1u << t;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned gx = expect_grid_x(nbits, dtype, batch);
@@ -205,7 +220,7 @@ int tcb200_expect_pauli(const void* state, int nbits, int dtype, int nterms,
     f.nctas = (int)gx;
     f.nterms = nterms;
     for (int t = 0; t < nterms; ++t) f.ny[t] = ny[t];
-    expect_final_kernel<<<(unsigned)batch, 32, 0, st>>>(f);
+    expect_final_kernel<<<dim3((unsigned)batch, (unsigned)nterms), 256, 0, st>>>(f);
     TCB_LAUNCH_CHECK("expect_final_kernel");
     return 0;
 }
@@ -319,12 +334,18 @@ struct ZFinalParams {
     int zt;
 };
 
-__global__ void zexpect_final_kernel(const __grid_constant__ ZFinalParams p) {
-    const int t = threadIdx.x;
-    if (t >= p.nterms) return;
+__global__ void __launch_bounds__(256) zexpect_final_kernel(const __grid_constant__ ZFinalParams p) {
+    __shared__ double red[8];
+    const int t = blockIdx.y, tid = threadIdx.x;
     const double* src = p.partials + (uint64_t)blockIdx.x * p.nctas * p.zt;
     double re = 0.0;
-    for (int c = 0; c < p.nctas; ++c) re += src[(uint64_t)c * p.zt + t];
+    for (int c = tid; c < p.nctas; c += 256) re += src[(uint64_t)c * p.zt + t];
+    re = warp_sum_d(re);
+    if ((tid & 31) == 0) red[tid >> 5] = re;
+    __syncthreads();
+    if (tid != 0) return;
+    re = 0.0;
+    for (int w = 0; w < 8; ++w) re += red[w];
     double* o = p.out + ((uint64_t)blockIdx.x * p.nterms + t) * 2;
     o[0] = re;
     o[1] = 0.0;
@@ -371,7 +392,7 @@ static int launch_zexpect(const void* state, int nbits, int nterms, const uint64
     f.nctas = (int)gx;
     f.nterms = nterms;
     f.zt = ZT;
-    zexpect_final_kernel<<<(unsigned)batch, 32, 0, st>>>(f);
+    zexpect_final_kernel<<<dim3((unsigned)batch, (unsigned)nterms), 256, 0, st>>>(f);
     TCB_LAUNCH_CHECK("zexpect_final_kernel");
     return 0;
 }

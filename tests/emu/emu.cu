@@ -154,12 +154,13 @@ int emu_expect_t(const void* state, int nbits, int nterms, const uint64_t* flip,
             for (int tid = 0; tid < nthr; ++tid) stage_in<C, false>(g, vec, base, tile, rowoff, tid, nthr);
             for (int tid = 0; tid < nthr; ++tid) {
                 // the kernel's multi-term body, run here with this term in slot 0
-                Real pr[TCB200_MAX_TERMS], pi[TCB200_MAX_TERMS];
+                Real pv[TCB200_MAX_TERMS];
                 const uint32_t fla[TCB200_MAX_TERMS] = {fl}, sla[TCB200_MAX_TERMS] = {sl};
-                expect_tile_terms<C, Real, TCB200_MAX_TERMS>(tile, (uint32_t)tile_elems, 1, fla, sla, tid, nthr, pr, pi);
+                expect_tile_terms<C, Real, TCB200_MAX_TERMS>(tile, (uint32_t)tile_elems, 1, fla, sla, (uint32_t)(ny[t] & 1), tid, nthr, pv);
                 const bool neg = parity64(base & shi);
-                re += neg ? -(double)pr[0] : (double)pr[0];
-                im += neg ? -(double)pi[0] : (double)pi[0];
+                const double v = neg ? -(double)pv[0] : (double)pv[0];
+                if (ny[t] & 1) im += v;
+                else re += v;
             }
         }
         double ore = re, oim = im;
