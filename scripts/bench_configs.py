@@ -93,6 +93,9 @@ def config3():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "3":  # config 3 only (for ncu launch lists)
+        print(json.dumps(config3(), indent=1))
+        sys.exit(0)
     res = {"config2": config2(), "config3": config3()}
     print(json.dumps(res, indent=1))
     os.makedirs("gpurun_out", exist_ok=True)
