@@ -12,6 +12,7 @@ oracle/refshim/.  The fixtures pin, with outputs of the reference itself:
   * expectation_ps of the TFIM strings + random strings, and expectation of general operators;
   * sample(allow_state=True, status=u) indices -- the one quantity no reference test pins;
   * sample formats and numpy-backend vmap values;
+  * a 14-qubit QAOA MaxCut circuit: strided amplitudes, every ZZ cost term, samples;
   * Monte-Carlo noise trajectories (depolarizing / amplitudedamping / phasedamping / reset /
     cond_measure / unitary_kraus / mid_measurement) driven by fixed ``status`` values.
 """
@@ -132,6 +133,31 @@ def main():
             states.append(np.asarray(c.wavefunction()))
         out["traj_states_" + dt] = np.array(states)
         out["traj_picks_" + dt] = np.array(picks)
+    tc.set_dtype("complex64")
+    # ---- QAOA MaxCut, n = 14, p = 2 (diagonal cost function: every term is a ZZ string) -------------
+    n = 14
+    edges = [(i, (i + 1) % n) for i in range(n)] + [(i, (i + 5) % n) for i in range(0, n, 2)]
+    gam, bet = [0.37, -0.61], [0.52, 0.23]
+    out["qaoa_edges"] = np.array(edges)
+    out["qaoa_angles"] = np.array([gam, bet])
+    for dt in ("complex64", "complex128"):
+        tc.set_dtype(dt)
+        c = tc.Circuit(n)
+        for i in range(n):
+            c.h(i)
+        for l in range(2):
+            for a, b in edges:
+                c.rzz(a, b, theta=2 * gam[l])
+            for i in range(n):
+                c.rx(i, theta=2 * bet[l])
+        psi = np.asarray(c.wavefunction())
+        out["qaoa_amps_" + dt] = psi[:: 2**n // 256]          # 256 strided amplitudes
+        out["qaoa_zz_" + dt] = np.array([np.asarray(c.expectation_ps(z=[a, b])) for a, b in edges])
+        out["qaoa_z3_" + dt] = np.asarray(c.expectation_ps(z=[0, 6, 13]))
+        if dt == "complex64":
+            u = np.random.default_rng(11).random(512)
+            out["qaoa_status"] = u
+            out["qaoa_sample_int"] = np.asarray(c.sample(batch=512, allow_state=True, status=u, format="sample_int"))
     tc.set_dtype("complex64")
     path = os.path.join(ROOT, "tests", "golden", "ref_fixtures.npz")
     np.savez_compressed(path, **out)
