@@ -134,6 +134,15 @@ def main():
         out["traj_states_" + dt] = np.array(states)
         out["traj_picks_" + dt] = np.array(picks)
     tc.set_dtype("complex64")
+    # ---- sample_expectation_ps (basecircuit.py:618-758): exact and from shots with status -----------
+    c = build(tc, 4, ALL_GATES)
+    out["sexpps_exact"] = np.array([np.asarray(c.sample_expectation_ps(x=[0], y=[1], z=[3])),
+                                    np.asarray(c.sample_expectation_ps(z=[0, 2])),
+                                    np.asarray(c.sample_expectation_ps(y=[2, 3]))])
+    u = np.random.default_rng(12).random(4096)
+    out["sexpps_status"] = u
+    out["sexpps_shots"] = np.array([np.asarray(c.sample_expectation_ps(x=[0], y=[1], z=[3], shots=4096, status=u)),
+                                    np.asarray(c.sample_expectation_ps(x=[1, 2], shots=4096, status=u))])
     # ---- QAOA MaxCut, n = 14, p = 2 (diagonal cost function: every term is a ZZ string) -------------
     n = 14
     edges = [(i, (i + 1) % n) for i in range(n)] + [(i, (i + 5) % n) for i in range(0, n, 2)]

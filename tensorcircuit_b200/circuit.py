@@ -21,7 +21,7 @@ from . import cons, gates
 from .batching import BatchArray, batch_of, is_batched
 from .fusion import GateOp, fuse
 from .gates import Gate
-from .quantum import ps2xyz, sample2all, sample_int2bin
+from .quantum import correlation_from_samples, ps2xyz, sample2all, sample_int2bin
 
 Tensor = Any
 
@@ -553,6 +553,55 @@ class Circuit:
             r = list(zip(confg, prob))
             return r[0] if batch is None else r
         return sample2all(sample=ch, n=self._nqubits, format=format, jittable=True)
+
+    def sample_expectation_ps(
+        self,
+        x: Optional[Sequence[int]] = None,
+        y: Optional[Sequence[int]] = None,
+        z: Optional[Sequence[int]] = None,
+        shots: Optional[int] = None,
+        random_generator: Optional[Any] = None,
+        status: Optional[Tensor] = None,
+        readout_error: Optional[Sequence[Any]] = None,
+        noise_conf: Optional[Any] = None,
+        **kws: Any,
+    ) -> Tensor:
+        """Measurement-based Pauli-string expectation (basecircuit.py:618-758): rotate the x sites
+        with H and the y sites with rx(pi/2), then the string is a product of Z's -- evaluated
+        exactly from the probabilities (``shots=None``: one pass of the diagonal-string kernel)
+        or from ``shots`` samples drawn with ``status``.
+
+        The reference rotates a copy of the state; a copy does not fit at 34 qubits, so the
+        rotation is applied in place and undone afterwards (the recorded circuit is unchanged)."""
+        if noise_conf is not None or readout_error is not None:
+            raise NotImplementedError("readout_error / noise_conf are outside the statevector hot path")
+        x, y, z = list(x or []), list(y or []), list(z or [])
+        n_ops, n_qir = len(self._ops), len(self._qir)
+        self._ensure_state()
+        try:
+            for i in x:
+                self.h(i)
+            for i in y:
+                self.rx(i, theta=np.pi / 2)
+            if shots is None:
+                r = self.expectation_ps(z=x + y + z)
+                r = r.real if is_batched(r) else np.real(r)
+            else:
+                s = self.sample(batch=int(shots), allow_state=True, random_generator=random_generator, status=status, format="sample_bin")
+                r = correlation_from_samples(x + y + z, np.asarray(s), self._nqubits)
+        finally:
+            # undo the basis rotation on the device state and drop it from the record
+            for i in reversed(y):
+                self.rx(i, theta=-np.pi / 2)
+            for i in reversed(x):
+                self.h(i)
+            self._ensure_state()
+            del self._ops[n_ops:]
+            del self._qir[n_qir:]
+            self._applied = n_ops
+        return r
+
+    sexpps = sample_expectation_ps
 
     def measure(self, *index: int, with_prob: bool = False, status: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         """basecircuit.py:359-443 equivalent for the final state: one shot, marginal over ``index``."""

@@ -297,3 +297,25 @@ def test_engine_qaoa_vs_reference(eng, dtype, tol):  # noqa: F811
         bad = _sample_ok(got, FIX["qaoa_sample_int"], np.abs(np.asarray(c.wavefunction()).astype(np.complex128)) ** 2, u, tie=2e-5)
         assert bad <= 0.06 * len(u)  # float64-exact CDF vs the reference float32 one: 21 of 512 at this size
     tc.set_dtype("complex64")
+
+
+# ---- sample_expectation_ps (basecircuit.py:618-758) --------------------------------------------------
+def test_engine_sample_expectation_ps_vs_reference(eng):  # noqa: F811
+    c = _build(4, ALL_GATES)
+    before = np.asarray(c.wavefunction()).copy()
+    nq = len(c.to_qir())
+    got = [c.sample_expectation_ps(x=[0], y=[1], z=[3]), c.sample_expectation_ps(z=[0, 2]), c.sexpps(y=[2, 3])]
+    np.testing.assert_allclose(np.asarray(got, dtype=np.float64), FIX["sexpps_exact"], atol=2e-6)
+    u = FIX["sexpps_status"]
+    s1 = c.sample_expectation_ps(x=[0], y=[1], z=[3], shots=4096, status=u)
+    s2 = c.sample_expectation_ps(x=[1, 2], shots=4096, status=u)
+    # identical samples -> identical estimate (2 / 4096 per shot that sits on a float32 CDF tie)
+    np.testing.assert_allclose([s1, s2], FIX["sexpps_shots"], atol=3 * 2 / 4096)
+    # the basis rotation is undone: same state, same record
+    assert len(c.to_qir()) == nq
+    np.testing.assert_allclose(np.asarray(c.wavefunction()), before, atol=5e-7)
+    # oracle: rotate, then a product of Z's
+    o = orc.run_gatelist(4, ALL_GATES)
+    o.h(0)
+    o.rx(1, theta=np.pi / 2)
+    np.testing.assert_allclose(o.expectation_ps(z=[0, 1, 3]).real, FIX["sexpps_exact"][0], atol=2e-6)
