@@ -81,3 +81,27 @@ def spin_glass_measurements(c: Circuit, g: Any, reuse: bool = True) -> Tensor:
             pss.append(ps)
             ws.append(w)
     return pauli_sum_expectation(c, pss, ws)
+
+
+def heisenberg_measurements(c: Circuit, g: Any, hzz: float = 1.0, hxx: float = 1.0, hyy: float = 1.0, hz: float = 0.0,
+                            hx: float = 0.0, hy: float = 0.0, reuse: bool = True) -> Tensor:
+    """measurements.py:211-287:  sum_e w_e (hxx XX + hyy YY + hzz ZZ) + sum_v (hx X + hy Y + hz Z).
+    All strings go through the multi-term kernels in one call (the ZZ / Z ones share a single
+    streaming read of the state)."""
+    n = c._nqubits
+    pss, ws = [], []
+    for e1, e2 in g.edges:
+        w = g[e1][e2].get("weight", 1.0)
+        for p, h in ((3, hzz), (2, hyy), (1, hxx)):
+            ps = [0] * n
+            ps[e1] = ps[e2] = p
+            pss.append(ps)
+            ws.append(w * h)
+    for p, h in ((1, hx), (2, hy), (3, hz)):
+        if h != 0:
+            for i in range(len(g.nodes)):
+                ps = [0] * n
+                ps[i] = p
+                pss.append(ps)
+                ws.append(h)
+    return pauli_sum_expectation(c, pss, ws)

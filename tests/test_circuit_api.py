@@ -793,3 +793,25 @@ def test_depolarizing_trajectory_average(eng, highp):
     assert abs(z1.mean() - ez1) < 4.0 / np.sqrt(nt)
     assert abs(z2.mean() - ez2) < 4.0 / np.sqrt(nt)
     assert abs(xz.mean() - exz) < 4.0 / np.sqrt(nt)
+
+
+def test_heisenberg_measurements(eng):
+    # templates/measurements.py:211-287 docstring example (energy 1 for |10000> on an open... ring of 5)
+    g = tc.templates.graphs.Line1D(n=5)
+    c = tc.Circuit(5)
+    c.X(0)
+    np.testing.assert_allclose(tc.templates.measurements.heisenberg_measurements(c, g), 1.0, atol=1e-5)
+    # generic state and couplings against the oracle, term by term
+    n = 6
+    g = tc.templates.graphs.Line1D(n, edge_weight=[0.5, 1.0, -0.7, 0.3, 1.2, 0.9], pbc=True)
+    ops = orc.hea_circuit(n, np.random.default_rng(5).uniform(0, 6, size=[2, 2, n]))
+    c = _run_gatelist(n, ops)
+    o = orc.run_gatelist(n, ops)
+    want = 0.0
+    for a, b in g.edges:
+        w = g[a][b]["weight"]
+        want += w * (0.8 * o.expectation_ps(z=[a, b]) + 0.6 * o.expectation_ps(y=[a, b]) - 0.4 * o.expectation_ps(x=[a, b])).real
+    for i in range(n):
+        want += (0.3 * o.expectation_ps(x=[i]) - 0.2 * o.expectation_ps(z=[i])).real
+    got = tc.templates.measurements.heisenberg_measurements(c, g, hzz=0.8, hyy=0.6, hxx=-0.4, hx=0.3, hz=-0.2)
+    np.testing.assert_allclose(got, want, atol=2e-5)
