@@ -244,6 +244,15 @@ size_t tcb200_expect_z_workspace_bytes(int nbits, int64_t batch);
 int tcb200_expect_z(const void* state, int nbits, int dtype, int nterms, const uint64_t* sign,
                     double* out_dev, int64_t batch, void* workspace, size_t ws_bytes, void* stream);
 
+/* Probability mass of a partial measurement record: sum of |psi_e|^2 over the amplitudes with
+ * (e & mask) == value.  This is the reduced-density element rho[0,0] that measure_jit /
+ * perfect_sampling contract qubit by qubit (basecircuit.py:359-443): with `mask` = the bits measured
+ * so far plus the current one and `value` = their outcomes (current bit 0).  One streaming read,
+ * float64 accumulation, fixed-order reduction.  out_dev: one double (device). */
+size_t tcb200_masked_norm2_workspace_bytes(void);
+int tcb200_masked_norm2(const void* state, int nbits, int dtype, uint64_t mask, uint64_t value, double* out_dev,
+                        void* workspace, size_t ws_bytes, void* stream);
+
 /* Number of kernel launches issued by this process through the library so far. */
 int64_t tcb200_launch_count(void);
 

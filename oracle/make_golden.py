@@ -12,6 +12,7 @@ oracle/refshim/.  The fixtures pin, with outputs of the reference itself:
   * expectation_ps of the TFIM strings + random strings, and expectation of general operators;
   * sample(allow_state=True, status=u) indices -- the one quantity no reference test pins;
   * sample formats and numpy-backend vmap values;
+  * measure / perfect_sampling outcomes and record probabilities for given per-qubit status;
   * a 14-qubit QAOA MaxCut circuit: strided amplitudes, every ZZ cost term, samples;
   * Monte-Carlo noise trajectories (depolarizing / amplitudedamping / phasedamping / reset /
     cond_measure / unitary_kraus / mid_measurement) driven by fixed ``status`` values.
@@ -143,6 +144,25 @@ def main():
     out["sexpps_status"] = u
     out["sexpps_shots"] = np.array([np.asarray(c.sample_expectation_ps(x=[0], y=[1], z=[3], shots=4096, status=u)),
                                     np.asarray(c.sample_expectation_ps(x=[1, 2], shots=4096, status=u))])
+    # ---- measure_jit / perfect_sampling with status (basecircuit.py:359-443) ---------------------------
+    st = np.random.default_rng(13).random((16, 4))
+    out["measure_status"] = st
+    for dt in ("complex64", "complex128"):
+        tc.set_dtype(dt)
+        c = build(tc, 4, ALL_GATES)
+        bits, probs, pbits, pprobs = [], [], [], []
+        for row in st:
+            b, pr = c.measure(0, 2, 3, with_prob=True, status=row)
+            bits.append(np.asarray(b))
+            probs.append(np.asarray(pr))
+            b, pr = c.perfect_sampling(status=row)
+            pbits.append(np.asarray(b))
+            pprobs.append(np.asarray(pr))
+        out["measure_bits_" + dt] = np.array(bits)
+        out["measure_probs_" + dt] = np.array(probs)
+        out["perfect_bits_" + dt] = np.array(pbits)
+        out["perfect_probs_" + dt] = np.array(pprobs)
+    tc.set_dtype("complex64")
     # ---- QAOA MaxCut, n = 14, p = 2 (diagonal cost function: every term is a ZZ string) -------------
     n = 14
     edges = [(i, (i + 1) % n) for i in range(n)] + [(i, (i + 5) % n) for i in range(0, n, 2)]

@@ -604,31 +604,44 @@ class Circuit:
     sexpps = sample_expectation_ps
 
     def measure(self, *index: int, with_prob: bool = False, status: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
-        """basecircuit.py:359-443 equivalent for the final state: one shot, marginal over ``index``."""
-        u = cons.backend.implicit_randu(shape=[1]) if status is None else np.asarray(status, dtype=np.float64).reshape(-1)[:1]
+        """Qubit-by-qubit measurement of the final state with the reference's rule
+        (basecircuit.py:365-443): for the k-th measured qubit j, ``pu`` = probability of outcome 0
+        given the outcomes so far (the reduced-density element the reference contracts; here one
+        masked-norm pass over the state), outcome = ``sign(status[k] - pu + 0.31415926e-12)/2 + 0.5``,
+        and the running probability is updated as ``p * (pu * (-1)**outcome + outcome)``.
+        Returns (outcomes as a real vector, probability of the record or -1.0)."""
+        if self._batch is not None:
+            raise NotImplementedError("measure() inside vmap")
         st = self._ensure_state()
-        ch = int(st.sample(u)[0])
-        bits = sample_int2bin(np.array([ch]), self._nqubits)[0]
+        if self._ntot != self._nqubits:
+            raise NotImplementedError("measure with unitary-form inputs")
+        rd = np.float32 if self._dtype == "complex64" else np.float64
         idx = [i if i >= 0 else self._nqubits + i for i in index]
-        sel = bits[idx]
-        if not with_prob:
-            return sel, -1.0
-        # marginal probability of the observed outcome = <prod projectors>
-        pss, coef = [[0] * self._nqubits], [1.0]
-        for q, b in zip(idx, sel):
-            new_p, new_c = [], []
-            for ps, c in zip(pss, coef):
-                new_p.append(list(ps))
-                new_c.append(0.5 * c)
-                pz = list(ps)
-                pz[q] = 3
-                new_p.append(pz)
-                new_c.append(0.5 * c * (1 - 2 * int(b)))
-            pss, coef = new_p, new_c
-            if len(pss) > 1024:
-                raise NotImplementedError("measure(with_prob=True) on more than 10 qubits")
-        vals = self.expectation_ps_many(pss)
-        return sel, float(np.real(np.sum(np.asarray(coef) * vals)))
+        if status is not None:
+            status = np.asarray(status).reshape(-1)
+            if status.shape[0] < len(idx):
+                raise ValueError("status must hold one uniform per measured qubit")
+        eps = 0.31415926 * 1e-12
+        sample: List[Any] = []
+        p = rd(1.0)
+        mask = value = 0
+        for k, j in enumerate(idx):
+            bit = 1 << self._bitpos(j)
+            pu = rd(st.masked_norm2(mask | bit, value) / float(p))
+            r = cons.backend.implicit_randu()[0] if status is None else status[k]
+            r = rd(np.real(r))
+            sign = rd(np.sign(r - pu + eps) / 2 + 0.5)  # 0.5 only if status sits exactly on pu - eps
+            sample.append(sign)
+            p = rd(p * (pu * rd(-1.0) ** sign + sign)) if sign in (0.0, 1.0) else rd(p * 0.5)
+            mask |= bit
+            if sign > 0.5:
+                value |= bit
+        out = np.asarray(sample, dtype=rd)
+        return (out, p) if with_prob else (out, -1.0)
+
+    def perfect_sampling(self, status: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        """basecircuit.py:359-363: one bitstring by measuring every qubit in order, with its probability."""
+        return self.measure(*range(self._nqubits), with_prob=True, status=status)
 
     measure_jit = measure
 

@@ -110,6 +110,28 @@ __global__ void __launch_bounds__(1024) final_sum_kernel(const double* in, uint6
     if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
+// part[c] = sum of |psi_e|^2 over the amplitudes of CTA c's grid-stride share with (e & mask) == value:
+// the probability mass of a partial measurement record (perfect sampling, basecircuit.py:359-443)
+template <typename Real>
+__global__ void __launch_bounds__(256) masked_sums_kernel(const Unit16* state, int n, uint64_t mask, uint64_t value, double* part) {
+    __shared__ double sh[32];
+    constexpr int APU = CT<Real>::APU;
+    using C = typename CT<Real>::type;
+    const uint64_t units = (1ull << n) / APU > 0 ? (1ull << n) / APU : 1;
+    double acc = 0.0;
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (uint64_t)gridDim.x * blockDim.x) {
+        const Unit16 q = state[u];
+        const C* a = reinterpret_cast<const C*>(&q);
+#pragma unroll
+        for (int j = 0; j < APU; ++j) {
+            const uint64_t e = u * APU + j;
+            if ((e & mask) == value && e < (1ull << n)) acc += (double)a[j].x * (double)a[j].x + (double)a[j].y * (double)a[j].y;
+        }
+    }
+    const double s = cta_sum(acc, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
 template <typename Real>
 __global__ void __launch_bounds__(256) prob_kernel(const typename CT<Real>::type* state, Real* out, uint64_t n) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -364,6 +386,32 @@ int tcb200_norm2(const void* state, int nbits, int dtype, int64_t batch, double*
         block_sums_kernel<double><<<grid, 256, 0, st>>>(static_cast<const Unit16*>(state), nbits, B, part);
     TCB_LAUNCH_CHECK("block_sums_kernel");
     final_sum_kernel<<<(unsigned)batch, 1024, 0, st>>>(part, nb, out_dev);
+    TCB_LAUNCH_CHECK("final_sum_kernel");
+    return 0;
+}
+
+size_t tcb200_masked_norm2_workspace_bytes(void) { return sizeof(double) * 148 * 8 + 256; }
+
+int tcb200_masked_norm2(const void* state, int nbits, int dtype, uint64_t mask, uint64_t value, double* out_dev,
+                        void* workspace, size_t ws_bytes, void* stream) {
+    if (!state || !out_dev || !workspace) return fail(TCB200_ERR_ARG, "NULL argument");
+    if (dtype != TCB200_C64 && dtype != TCB200_C128) return fail(TCB200_ERR_ARG, "bad dtype %d", dtype);
+    if (nbits < 1 || nbits > 40) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
+    if ((mask >> nbits) || (value & ~mask)) return fail(TCB200_ERR_ARG, "mask / value outside the state or inconsistent");
+    if (ws_bytes < tcb200_masked_norm2_workspace_bytes()) return fail(TCB200_ERR_WORKSPACE, "workspace too small");
+    const uint64_t units = (1ull << nbits) >> (dtype == TCB200_C64 ? 1 : 0);
+    uint64_t want = (units + 255) / 256;
+    if (want < 1) want = 1;
+    const unsigned grid = (unsigned)(want < 148ull * 8 ? want : 148ull * 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* part = static_cast<double*>(workspace);
+    if (dtype == TCB200_C64) {
+        masked_sums_kernel<float><<<grid, 256, 0, st>>>(static_cast<const Unit16*>(state), nbits, mask, value, part);
+    } else {
+        masked_sums_kernel<double><<<grid, 256, 0, st>>>(static_cast<const Unit16*>(state), nbits, mask, value, part);
+    }
+    TCB_LAUNCH_CHECK("masked_sums_kernel");
+    final_sum_kernel<<<1, 1024, 0, st>>>(part, grid, out_dev);
     TCB_LAUNCH_CHECK("final_sum_kernel");
     return 0;
 }

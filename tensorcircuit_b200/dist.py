@@ -354,6 +354,24 @@ class DistState:
         dist.all_reduce(v, group=self.group)
         return float(v.item())
 
+    def masked_norm2(self, mask: int, value: int) -> float:
+        """sum of |psi_e|^2 over (e & mask) == value for logical-bit masks: bits that are global at
+        the moment select the ranks that contribute, the others become a local mask"""
+        lmask = lval = 0
+        mine = True
+        for q in range(self.n):
+            if (int(mask) >> q) & 1:
+                p, bit = self.phys[q], (int(value) >> q) & 1
+                if p < self.nloc:
+                    lmask |= 1 << p
+                    lval |= bit << p
+                elif ((self.rank >> (p - self.nloc)) & 1) != bit:
+                    mine = False
+        m = self.local.masked_norm2(lmask, lval) if mine else 0.0
+        v = torch.tensor([float(m)], dtype=torch.float64, device=self.local.buf.device)
+        dist.all_reduce(v, group=self.group)
+        return float(v.item())
+
     def expectation_terms(self, flips: Sequence[int], signs: Sequence[int], nys: Sequence[int]) -> np.ndarray:
         """<P_t> for logical-bit masks; complex [nterms].  Z-type factors on global bits become
         a per-rank sign; terms that flip a global bit are evaluated after a remap that makes
@@ -460,6 +478,9 @@ class DistEngineState:
 
     def norm2(self) -> np.ndarray:
         return np.asarray([self.ds.norm2()])
+
+    def masked_norm2(self, mask: int, value: int) -> float:
+        return self.ds.masked_norm2(mask, value)
 
     def expectation_terms(self, flips: Sequence[int], signs: Sequence[int], nys: Sequence[int]) -> np.ndarray:
         return self.ds.expectation_terms(flips, signs, nys)[None, :]

@@ -235,6 +235,16 @@ class DeviceState:
         check(lib.tcb200_norm2(_ptr(self.buf), self.nbits, self.dt, self.batch, _ptr(out), _ptr(ws), ws.numel(), _stream()))
         return out.cpu().numpy()
 
+    def masked_norm2(self, mask: int, value: int) -> float:
+        """sum of |psi_e|^2 over the amplitudes with (e & mask) == value (batch 1): the mass of a
+        partial measurement record, basecircuit.py:359-443"""
+        if self.batch != 1:
+            raise _lib.EngineError("masked_norm2 on a batched state is not supported")
+        ws = self._workspace(lib.tcb200_masked_norm2_workspace_bytes())
+        out = torch.empty(1, dtype=torch.float64, device=self.device)
+        check(lib.tcb200_masked_norm2(_ptr(self.buf), self.nbits, self.dt, int(mask), int(value), _ptr(out), _ptr(ws), ws.numel(), _stream()))
+        return float(out.cpu().numpy()[0])
+
     def probability(self) -> torch.Tensor:
         rd = torch.float32 if self.dtype == "complex64" else torch.float64
         p = torch.empty((self.batch, 1 << self.nbits), dtype=rd, device=self.device)

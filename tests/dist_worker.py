@@ -53,6 +53,12 @@ def main():
             # state unchanged (as a logical vector) by the remaps done for the expectations
             got2 = ds.gather_state()
             assert np.linalg.norm(got2 - o.state()) / np.linalg.norm(o.state()) < tol
+            # mass of partial measurement records (masks over local AND currently-global bits)
+            p_all = np.abs(o.state()) ** 2
+            idx_all = np.arange(2**n)
+            for mask, value in ((1 << (n - 1), 0), ((1 << (n - 1)) | 1, 1), (0b1011 << (n - 4), 0b1001 << (n - 4)), (0, 0)):
+                want_m = float(np.sum(p_all[(idx_all & mask) == value]))
+                assert abs(ds.masked_norm2(mask, value) - want_m) < 20 * tol, (mode, dtype, mask)
             # sampling: identical indices on every rank, equal to the oracle rule
             u = np.random.default_rng(4).random(3000)
             s_idx = ds.sample(u)

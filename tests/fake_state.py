@@ -117,6 +117,11 @@ class FakeState:
     def norm2(self):
         return np.sum(np.abs(self.np.astype(np.complex128)) ** 2, axis=1)
 
+    def masked_norm2(self, mask, value):
+        idx = np.arange(1 << self.nbits, dtype=np.uint64)
+        sel = (idx & np.uint64(mask)) == np.uint64(value)
+        return float(np.sum(np.abs(self.np[0].astype(np.complex128)[sel]) ** 2))
+
     def probability(self):
         rd = np.float32 if self.dtype == "complex64" else np.float64
         return torch.from_numpy((np.abs(self.np) ** 2).astype(rd))

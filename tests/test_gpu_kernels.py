@@ -564,3 +564,25 @@ def test_expect_z_kernel(dtype, n, batch):
         x0 = 2 * np.real(np.vdot(psis[b][0::2], psis[b][1::2]))
         np.testing.assert_allclose(mix[b, 1].real, x0, atol=4 * TOL[dtype])
     assert np.array_equal(st.expectation_terms([0] * nterms, masks, [0] * nterms), got)  # deterministic
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n", [1, 4, 13, 21])
+def test_masked_norm2(dtype, n):
+    """tcb200_masked_norm2: probability mass of a partial measurement record (basecircuit.py:359-443)."""
+    rng = np.random.default_rng(40 + n)
+    psi = _rand_state(rng, n)
+    st = DeviceState(n, dtype)
+    st.load(psi)
+    p = np.abs(psi) ** 2
+    idx = np.arange(2**n, dtype=np.uint64)
+    cases = [(0, 0), (1, 0), (1, 1), (1 << (n - 1), 1 << (n - 1)), ((1 << n) - 1, int(rng.integers(0, 2**n)))]
+    for _ in range(4):
+        m = int(rng.integers(0, 2**n))
+        cases.append((m, int(rng.integers(0, 2**n)) & m))
+    for mask, value in cases:
+        want = float(np.sum(p[(idx & np.uint64(mask)) == np.uint64(value)]))
+        got = st.masked_norm2(mask, value)
+        assert abs(got - want) < 4 * TOL[dtype], (mask, value, got, want)
+    with pytest.raises(_lib.EngineError):
+        st.masked_norm2(1, 2)  # value outside the mask

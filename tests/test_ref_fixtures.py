@@ -319,3 +319,30 @@ def test_engine_sample_expectation_ps_vs_reference(eng):  # noqa: F811
     o.h(0)
     o.rx(1, theta=np.pi / 2)
     np.testing.assert_allclose(o.expectation_ps(z=[0, 1, 3]).real, FIX["sexpps_exact"][0], atol=2e-6)
+
+
+# ---- measure_jit / perfect_sampling with per-qubit status (basecircuit.py:359-443) --------------------
+@pytest.mark.parametrize("dtype,tol", [("complex64", 2e-6), ("complex128", 2e-7)])
+def test_engine_measure_vs_reference(eng, dtype, tol):  # noqa: F811
+    # complex128 tolerance: the reference builds its td / sd gates as adjoints at import time, in the
+    # default complex64, so its own complex128 state of this all-gates circuit is only good to 2e-8
+    # (first deviation from the float64 oracle at the td gate); the engine and the oracle agree to 1e-16.
+    tc.set_dtype(dtype)
+    c = _build(4, ALL_GATES)
+    st = FIX["measure_status"]
+    for k, row in enumerate(st):
+        b, pr = c.measure(0, 2, 3, with_prob=True, status=row)
+        assert list(np.asarray(b)) == list(FIX["measure_bits_" + dtype][k])
+        np.testing.assert_allclose(pr, FIX["measure_probs_" + dtype][k], atol=tol)
+        b, pr = c.perfect_sampling(status=row)
+        assert list(np.asarray(b)) == list(FIX["perfect_bits_" + dtype][k])
+        np.testing.assert_allclose(pr, FIX["perfect_probs_" + dtype][k], atol=tol)
+    b, pr = c.measure(1, status=[0.3])
+    assert pr == -1.0 and b.shape == (1,)
+    # the record probabilities of all 16 outcomes of perfect_sampling form the distribution |psi|^2
+    psi = np.asarray(c.wavefunction()).astype(np.complex128)
+    for row in st[:4]:
+        b, pr = c.perfect_sampling(status=row)
+        i = int("".join(str(int(x)) for x in np.asarray(b)), 2)
+        np.testing.assert_allclose(pr, abs(psi[i]) ** 2, atol=2e-6 if dtype == "complex64" else 1e-13)
+    tc.set_dtype("complex64")
