@@ -134,6 +134,10 @@ def cpu_port_run(n, depth, seed, shots, budget_s=15.0):
     from oracle import port, tc_oracle as orc
 
     ops = orc.random_circuit(n, depth, seed)
+    try:  # all the host threads this process may use (torchrun sets OMP_NUM_THREADS=1 per rank)
+        port.lib().svp_set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
     cores = int(port.lib().svp_num_threads())
     psi = np.empty(2**n, dtype=np.complex64)
     mats = []

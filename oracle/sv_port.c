@@ -37,6 +37,15 @@ static inline uint64_t insert_zeros(uint64_t g, const int* bits, int k) {
     return g;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline is meant to use the host */
+void svp_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int svp_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
