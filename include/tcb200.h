@@ -253,6 +253,16 @@ size_t tcb200_masked_norm2_workspace_bytes(void);
 int tcb200_masked_norm2(const void* state, int nbits, int dtype, uint64_t mask, uint64_t value, double* out_dev,
                         void* workspace, size_t ws_bytes, void* stream);
 
+/* Readout error (basecircuit.py:587-596, 760-803): the reference maps p = |psi|^2 through the tensor
+ * product of per-qubit 2x2 stochastic matrices before it samples.  Here the probabilities are kept
+ * in a complex buffer of the state's dtype so that the existing kernels do all the work:
+ *   mode 0: out_e = (|in_e|^2, 0)            -- then the readout matrices are applied as ordinary
+ *                                               (real, non-unitary) 1-bit blocks with tcb200_apply_*
+ *   mode 1: out_e = (sqrt(max(Re in_e,0)),0) -- afterwards |out_e|^2 = p'_e, so tcb200_sample and
+ *                                               tcb200_expect_z read the noisy distribution
+ * in and out may be the same buffer. */
+int tcb200_probability_state(const void* in, void* out, int nbits, int dtype, int mode, void* stream);
+
 /* Number of kernel launches issued by this process through the library so far. */
 int64_t tcb200_launch_count(void);
 

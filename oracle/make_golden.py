@@ -12,6 +12,7 @@ oracle/refshim/.  The fixtures pin, with outputs of the reference itself:
   * expectation_ps of the TFIM strings + random strings, and expectation of general operators;
   * sample(allow_state=True, status=u) indices -- the one quantity no reference test pins;
   * sample formats and numpy-backend vmap values;
+  * readout error: noisy probabilities, samples and sample_expectation_ps;
   * measure / perfect_sampling outcomes and record probabilities for given per-qubit status;
   * a 14-qubit QAOA MaxCut circuit: strided amplitudes, every ZZ cost term, samples;
   * Monte-Carlo noise trajectories (depolarizing / amplitudedamping / phasedamping / reset /
@@ -144,6 +145,17 @@ def main():
     out["sexpps_status"] = u
     out["sexpps_shots"] = np.array([np.asarray(c.sample_expectation_ps(x=[0], y=[1], z=[3], shots=4096, status=u)),
                                     np.asarray(c.sample_expectation_ps(x=[1, 2], shots=4096, status=u))])
+    # ---- readout error (basecircuit.py:587-596, 760-803) ------------------------------------------------
+    ro = [[0.9, 0.75], [0.4, 0.7], [0.95, 0.97], [0.6, 0.8]]
+    out["readout_error"] = np.array(ro)
+    c = build(tc, 4, ALL_GATES)
+    out["readout_probs"] = np.asarray(c.readouterror_bs(ro, c.probability()))
+    u = np.random.default_rng(14).random(2000)
+    out["readout_status"] = u
+    out["readout_sample_int"] = np.asarray(c.sample(batch=2000, allow_state=True, readout_error=ro, status=u, format="sample_int"))
+    out["readout_sexpps"] = np.array([np.asarray(c.sample_expectation_ps(x=[0], y=[1], z=[3], readout_error=ro)),
+                                      np.asarray(c.sample_expectation_ps(z=[0, 2], readout_error=ro)),
+                                      np.asarray(c.sample_expectation_ps(x=[1, 2], shots=2000, status=u, readout_error=ro))])
     # ---- measure_jit / perfect_sampling with status (basecircuit.py:359-443) ---------------------------
     st = np.random.default_rng(13).random((16, 4))
     out["measure_status"] = st

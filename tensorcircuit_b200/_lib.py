@@ -57,6 +57,7 @@ def _load() -> ctypes.CDLL:
         "tcb200_pass_tile_bits": (c_int, [c_int]),
         "tcb200_norm2": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
         "tcb200_reduce_workspace_bytes": (c_size_t, [c_int, c_int64]),
+        "tcb200_probability_state": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
         "tcb200_masked_norm2_workspace_bytes": (c_size_t, []),
         "tcb200_masked_norm2": (c_int, [c_void_p, c_int, c_int, c_uint64, c_uint64, c_void_p, c_void_p, c_size_t, c_void_p]),
         "tcb200_probability": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p]),
@@ -83,7 +84,7 @@ EXPORTS = [
     "tcb200_version", "tcb200_last_error", "tcb200_launch_count", "tcb200_tma_pass_count", "tcb200_init_zero", "tcb200_load_c128",
     "tcb200_set_zero", "tcb200_copy_rows",
     "tcb200_apply_dense", "tcb200_apply_dense_batched", "tcb200_apply_diag", "tcb200_apply_pass", "tcb200_apply_pass_host", "tcb200_apply_rpass_host",
-    "tcb200_pass_tile_bits", "tcb200_norm2", "tcb200_reduce_workspace_bytes", "tcb200_masked_norm2_workspace_bytes", "tcb200_masked_norm2", "tcb200_probability",
+    "tcb200_pass_tile_bits", "tcb200_norm2", "tcb200_reduce_workspace_bytes", "tcb200_masked_norm2_workspace_bytes", "tcb200_masked_norm2", "tcb200_probability_state", "tcb200_probability",
     "tcb200_expect_pauli", "tcb200_expect_workspace_bytes", "tcb200_expect_tile_bits",
     "tcb200_expect_z_max_terms", "tcb200_expect_z_min_bits", "tcb200_expect_z_workspace_bytes", "tcb200_expect_z", "tcb200_sample",
     "tcb200_sample_workspace_bytes", "tcb200_run_circuit_host",

@@ -525,8 +525,6 @@ class Circuit:
         draws from the same exact distribution through the same state sampler here."""
         if format_ is not None:
             format = format_
-        if readout_error is not None:
-            raise NotImplementedError("readout_error is outside the statevector hot path")
         if self._batch is not None:
             raise NotImplementedError("sample() inside vmap")
         nbatch = 1 if batch is None else int(batch)
@@ -543,6 +541,8 @@ class Circuit:
         st = self._ensure_state()
         if self._ntot != self._nqubits:
             raise NotImplementedError("sample with unitary-form inputs")
+        if readout_error is not None:  # basecircuit.py:592-596: sample the readout-corrupted distribution
+            st = self._readout_state(readout_error)
         ch = st.sample(u)
         if format is None:  # backward-compatible tuple form (basecircuit.py:609-615)
             import torch
@@ -553,6 +553,35 @@ class Circuit:
             r = list(zip(confg, prob))
             return r[0] if batch is None else r
         return sample2all(sample=ch, n=self._nqubits, format=format, jittable=True)
+
+    def _readout_state(self, readout_error: Sequence[Any]) -> Any:
+        """A state-shaped device buffer whose |amplitude|^2 is the distribution after readout error
+        (basecircuit.py:760-803: p' = (tensor product of [[p0|0, 1-p1|1], [1-p0|0, p1|1]]) p).  The
+        probabilities sit in the real parts of a complex buffer, the per-qubit stochastic matrices
+        go through the ordinary fused passes, then a square root makes it samplable."""
+        st = self._ensure_state()
+        if self._ntot != self._nqubits or not hasattr(st, "probability_state"):
+            raise NotImplementedError("readout_error needs a single-device pure state")
+        if len(readout_error) != self._nqubits:
+            raise ValueError("readout_error needs one [p0|0, p1|1] pair per qubit")
+        r = st.probability_state()
+        ops = []
+        for q, e in enumerate(readout_error):
+            p0, p1 = float(np.real(e[0])), float(np.real(e[1]))
+            ops.append(GateOp((q,), np.array([[p0, 1 - p1], [1 - p0, p1]], dtype=np.complex128), "readout"))
+        r.apply_planned(fuse(ops, self._nqubits, kmax=self.fusion_kmax)) if hasattr(r, "apply_planned") else r.apply_blocks(fuse(ops, self._nqubits, kmax=self.fusion_kmax))
+        r.sqrt_real_inplace()
+        return r
+
+    def readouterror_bs(self, readout_error: Optional[Sequence[Any]] = None, p: Optional[Any] = None) -> Any:
+        """basecircuit.py:760-803: the bit-string probabilities after readout error, as a device
+        array.  ``p`` (the reference's second argument) is always the circuit's own distribution here."""
+        if p is not None:
+            raise NotImplementedError("readouterror_bs acts on the circuit's own probabilities")
+        if readout_error is None:
+            return self.probability()
+        r = self._readout_state(readout_error)
+        return DeviceArray(r.probability()[0])
 
     def sample_expectation_ps(
         self,
@@ -573,8 +602,8 @@ class Circuit:
 
         The reference rotates a copy of the state; a copy does not fit at 34 qubits, so the
         rotation is applied in place and undone afterwards (the recorded circuit is unchanged)."""
-        if noise_conf is not None or readout_error is not None:
-            raise NotImplementedError("readout_error / noise_conf are outside the statevector hot path")
+        if noise_conf is not None:
+            raise NotImplementedError("noise_conf is outside the statevector hot path")
         x, y, z = list(x or []), list(y or []), list(z or [])
         n_ops, n_qir = len(self._ops), len(self._qir)
         self._ensure_state()
@@ -584,10 +613,16 @@ class Circuit:
             for i in y:
                 self.rx(i, theta=np.pi / 2)
             if shots is None:
-                r = self.expectation_ps(z=x + y + z)
-                r = r.real if is_batched(r) else np.real(r)
+                if readout_error is None:
+                    r = self.expectation_ps(z=x + y + z)
+                    r = r.real if is_batched(r) else np.real(r)
+                else:  # sum_e p'_e (-1)^{bits}: the same diagonal string on the noisy distribution
+                    _, sign, _ = self._pauli_masks([], [], x + y + z)
+                    rs = self._readout_state(readout_error)
+                    r = float(np.real(rs.expectation_terms([0], [sign], [0])[0, 0]))
             else:
-                s = self.sample(batch=int(shots), allow_state=True, random_generator=random_generator, status=status, format="sample_bin")
+                s = self.sample(batch=int(shots), allow_state=True, readout_error=readout_error, random_generator=random_generator,
+                                status=status, format="sample_bin")
                 r = correlation_from_samples(x + y + z, np.asarray(s), self._nqubits)
         finally:
             # undo the basis rotation on the device state and drop it from the record

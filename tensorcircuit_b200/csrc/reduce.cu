@@ -110,6 +110,21 @@ __global__ void __launch_bounds__(1024) final_sum_kernel(const double* in, uint6
     if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
+// out_e = (|in_e|^2, 0)  (mode 0)   or   out_e = (sqrt(max(Re in_e, 0)), 0)  (mode 1); in may equal out
+template <typename Real>
+__global__ void __launch_bounds__(256) prob_state_kernel(const typename CT<Real>::type* in, typename CT<Real>::type* out,
+                                                         uint64_t n, int mode) {
+    using C = typename CT<Real>::type;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const C c = in[i];
+        C o;
+        o.x = mode == 0 ? c.x * c.x + c.y * c.y : sqrt(c.x > (Real)0 ? c.x : (Real)0);
+        o.y = 0;
+        out[i] = o;
+    }
+}
+
 // part[c] = sum of |psi_e|^2 over the amplitudes of CTA c's grid-stride share with (e & mask) == value:
 // the probability mass of a partial measurement record (perfect sampling, basecircuit.py:359-443)
 template <typename Real>
@@ -413,6 +428,22 @@ int tcb200_masked_norm2(const void* state, int nbits, int dtype, uint64_t mask, 
     TCB_LAUNCH_CHECK("masked_sums_kernel");
     final_sum_kernel<<<1, 1024, 0, st>>>(part, grid, out_dev);
     TCB_LAUNCH_CHECK("final_sum_kernel");
+    return 0;
+}
+
+int tcb200_probability_state(const void* in, void* out, int nbits, int dtype, int mode, void* stream) {
+    if (!in || !out) return fail(TCB200_ERR_ARG, "NULL argument");
+    if (dtype != TCB200_C64 && dtype != TCB200_C128) return fail(TCB200_ERR_ARG, "bad dtype %d", dtype);
+    if (nbits < 1 || nbits > 40) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
+    if (mode != 0 && mode != 1) return fail(TCB200_ERR_ARG, "mode=%d", mode);
+    const uint64_t n = 1ull << nbits;
+    const unsigned grid = stream_grid(n, 256 * 4);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == TCB200_C64)
+        prob_state_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float2*>(in), static_cast<float2*>(out), n, mode);
+    else
+        prob_state_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double2*>(in), static_cast<double2*>(out), n, mode);
+    TCB_LAUNCH_CHECK("prob_state_kernel");
     return 0;
 }
 

@@ -235,6 +235,19 @@ class DeviceState:
         check(lib.tcb200_norm2(_ptr(self.buf), self.nbits, self.dt, self.batch, _ptr(out), _ptr(ws), ws.numel(), _stream()))
         return out.cpu().numpy()
 
+    def probability_state(self) -> "DeviceState":
+        """a new state-shaped buffer holding (|psi_e|^2, 0): the probabilities as something the
+        apply kernels can transform (readout error, basecircuit.py:760-803)"""
+        if self.batch != 1:
+            raise _lib.EngineError("probability_state on a batched state is not supported")
+        r = type(self)(self.nbits, self.dtype)
+        check(lib.tcb200_probability_state(_ptr(self.buf), _ptr(r.buf), self.nbits, self.dt, 0, _stream()))
+        return r
+
+    def sqrt_real_inplace(self) -> None:
+        """(p, *) -> (sqrt(max(p, 0)), 0): afterwards |amplitude|^2 is the distribution p"""
+        check(lib.tcb200_probability_state(_ptr(self.buf), _ptr(self.buf), self.nbits, self.dt, 1, _stream()))
+
     def masked_norm2(self, mask: int, value: int) -> float:
         """sum of |psi_e|^2 over the amplitudes with (e & mask) == value (batch 1): the mass of a
         partial measurement record, basecircuit.py:359-443"""

@@ -117,6 +117,14 @@ class FakeState:
     def norm2(self):
         return np.sum(np.abs(self.np.astype(np.complex128)) ** 2, axis=1)
 
+    def probability_state(self):
+        r = type(self)(self.nbits, self.dtype)
+        r.np[0] = (np.abs(self.np[0]) ** 2).astype(self.np.dtype)
+        return r
+
+    def sqrt_real_inplace(self):
+        self.np[0] = np.sqrt(np.maximum(self.np[0].real, 0)).astype(self.np.dtype)
+
     def masked_norm2(self, mask, value):
         idx = np.arange(1 << self.nbits, dtype=np.uint64)
         sel = (idx & np.uint64(mask)) == np.uint64(value)

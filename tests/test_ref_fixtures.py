@@ -346,3 +346,21 @@ def test_engine_measure_vs_reference(eng, dtype, tol):  # noqa: F811
         i = int("".join(str(int(x)) for x in np.asarray(b)), 2)
         np.testing.assert_allclose(pr, abs(psi[i]) ** 2, atol=2e-6 if dtype == "complex64" else 1e-13)
     tc.set_dtype("complex64")
+
+
+# ---- readout error (basecircuit.py:587-596, 760-803) ---------------------------------------------------
+def test_engine_readout_error_vs_reference(eng):  # noqa: F811
+    c = _build(4, ALL_GATES)
+    ro = [list(map(float, r)) for r in FIX["readout_error"]]
+    np.testing.assert_allclose(np.asarray(c.readouterror_bs(ro)), FIX["readout_probs"], atol=2e-6)
+    u = FIX["readout_status"]
+    got = np.asarray(c.sample(batch=len(u), allow_state=True, readout_error=ro, status=u, format="sample_int"))
+    bad = _sample_ok(got, FIX["readout_sample_int"], FIX["readout_probs"], u, tie=1e-6)
+    assert bad <= 3
+    e1 = c.sample_expectation_ps(x=[0], y=[1], z=[3], readout_error=ro)
+    e2 = c.sample_expectation_ps(z=[0, 2], readout_error=ro)
+    e3 = c.sample_expectation_ps(x=[1, 2], shots=len(u), status=u, readout_error=ro)
+    np.testing.assert_allclose([e1, e2], FIX["readout_sexpps"][:2], atol=3e-6)
+    np.testing.assert_allclose(e3, FIX["readout_sexpps"][2], atol=3 * 2 / len(u))
+    # no readout error given: plain probabilities
+    np.testing.assert_allclose(np.asarray(c.readouterror_bs(None)), np.abs(np.asarray(c.wavefunction())) ** 2, atol=1e-6)
