@@ -75,23 +75,37 @@ def run_dist(args, tc, rank, world, local):
     tc.set_distributed(True)
     e2e_steps = 1
 
-    def api_step():
+    def api_step(keep=False):
         c = recipes.build(tc.Circuit(n), ops)
         r = c.sample(batch=shots, allow_state=True, status=u_host, format="sample_int")
+        if keep:
+            return r, c
         del c
         gc.collect()
-        return r
+        return r, None
 
     api_step()
     sync()
     w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        s_api = api_step()
+    for k in range(e2e_steps):
+        s_api, c_last = api_step(keep=(k == e2e_steps - 1))
     sync()
     e2e_s = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device="cuda")
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
     same = bool(np.array_equal(s_api, s))
+
+    # config 5's second half: all 2n TFIM strings on the sharded state (not part of the timed steps)
+    terms = recipes.tfim_terms(n)
+    sync()
+    w1 = time.perf_counter()
+    energy = float(np.real(tc.templates.measurements.pauli_sum_expectation(c_last, [ps for _, ps in terms], [w for w, _ in terms])))
+    sync()
+    exp_s = torch.tensor([time.perf_counter() - w1], dtype=torch.float64, device="cuda")
+    dist.all_reduce(exp_s, op=dist.ReduceOp.MAX)
+    exp_s = float(exp_s.item())
+    del c_last
+    gc.collect()
 
     if rank == 0:
         value = args.steps * ngates * float(2**n) / (total_ms * 1e-3)
@@ -115,6 +129,8 @@ def run_dist(args, tc, rank, world, local):
                       "remap_share_of_step": stats["remap_ms"] / total_ms},
             "e2e": {"value": e2e_steps * ngates * float(2**n) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(shots * 8), "d2h_bytes_per_step": int(shots * 8),
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "samples_match_device_leg": same},
+            "expectation": {"strings": len(terms), "what": "TFIM energy, X_i and Z_i Z_i+1 on the sharded state (remaps for global X included)",
+                            "ms": 1e3 * exp_s, "energy": energy},
             "gpu_launches": int(launches),
             "clocks": clk,
             "checks": {"norm2": norm2, "sample_min": int(s.min()), "sample_max": int(s.max())},
