@@ -68,7 +68,42 @@ def main():
     assert s.shape == (1000,) and np.all(np.abs(ref[s]) > 0)
     psi = np.asarray(c.state())
     assert np.linalg.norm(psi - ref) / np.linalg.norm(ref) < 1e-5
+    # measure on the sharded state: masks over local and global bits (basecircuit.py:359-443)
+    b, pr = c.measure(0, 1, n - 1, with_prob=True, status=[0.3, 0.8, 0.5])
+    oc = orc.run_gatelist(n, ops)
+    # same rule on the oracle state
+    p_all = np.abs(oc.state()) ** 2
+    idx_all = np.arange(2**n)
+    mask = value = 0
+    pp = 1.0
+    for k, q in enumerate((0, 1, n - 1)):
+        bit = 1 << (n - 1 - q)
+        pu = float(np.sum(p_all[(idx_all & (mask | bit)) == value])) / pp
+        sign = 1.0 if [0.3, 0.8, 0.5][k] - pu + 0.31415926e-12 > 0 else 0.0
+        assert float(b[k]) == sign, (k, b, pu)
+        pp *= (1 - pu) if sign else pu
+        mask |= bit
+        value |= bit if sign else 0
+    assert abs(float(pr) - pp) < 1e-5
     tc.set_distributed(False)
+    # vmap batch sharded over the ranks (config 3's layout): one all-gather of the results
+    def energy(th):
+        cc = tc.Circuit(10)
+        for i in range(10):
+            cc.rx(i, theta=th[i])
+        for i in range(9):
+            cc.rzz(i, i + 1, theta=th[i] * 0.5)
+        return tc.backend.real(cc.expectation_ps(z=[0, 1]) + cc.expectation_ps(x=[9]))
+
+    th = np.random.default_rng(6).uniform(0, 6, size=(7, 10))  # 7 does not divide evenly
+    got = np.asarray(tc.backend.vmap(energy)(th))
+    for k in range(7):
+        oo = orc.OracleCircuit(10)
+        for i in range(10):
+            oo.rx(i, theta=th[k, i])
+        for i in range(9):
+            oo.rzz(i, i + 1, theta=th[k, i] * 0.5)
+        assert abs(got[k] - (oo.expectation_ps(z=[0, 1]) + oo.expectation_ps(x=[9])).real) < 1e-5, k
     dist.barrier()
     if rank == 0:
         print("DIST_GPU_OK world=%d" % world)
