@@ -362,6 +362,12 @@ def run_ours(args):
                      "fp32_fma_per_amp_per_launch": sum(4 * 2 ** len(b.bits) for b in blocks) / max(1, npass),
                      "note": "a staged pass holding several blocks is FP32-FMA-bound, not HBM-bound: see roofline_single_block for the one-block-per-pass kernel"},
         "roofline_single_block": dict(probe, bound="hbm", kernel="dense_kernel", peak=peak, unit="GB/s"),
+        # the bound that actually binds a multi-block pass: CUDA-core FP32 (no tensor cores on this path).
+        # real FMAs = 4 * 2^k per amplitude and block; peak = 148 SMs x 128 FMA/clk x the max SM clock
+        "roofline_fp32": (lambda fma, pk: {"bound": "fp32 (CUDA cores)", "achieved": fma / (apply_ms * 1e-3) / 1e12, "peak": pk, "unit": "T FMA/s",
+                                          "frac": fma / (apply_ms * 1e-3) / 1e12 / pk, "fma_per_amplitude_per_step": fma / (args.steps * float(2**n))})(
+            args.steps * float(2**n) * sum(4 * 2 ** len(b.bits) for b in blocks),
+            148 * 128 * ((clk or {}).get("sm_max_mhz") or 1965.0) * 1e6 / 1e12),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(shots * 8 + sum(16 * 4 ** len(b.bits) for b in blocks)), "d2h_bytes_per_step": int(shots * 8),
                 "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "samples_match_device_leg": same},
         "gpu_launches": int(launches),
