@@ -1,0 +1,289 @@
+"""``value_and_grad`` / ``vvag`` for loss functions built from circuit expectation values.
+
+The reference differentiates through its backend's autodiff (jax_backend.py:668-776).  The
+engine has no autodiff, but an expectation value is a *quadratic form in every gate matrix*:
+with psi(M_j) linear in the matrix of gate j,
+
+    E(M_j + D) - E(M_j - D) = 4 Re <psi| H |d psi>,      d psi = psi with gate j replaced by D,
+
+so for D = dM_j/d theta the derivative of E through gate j is exactly (E+ - E-)/2 -- a shift
+rule that holds for ANY gate (no generator assumption, no truncation error), needs only forward
+simulations with non-unitary matrices, and therefore runs on the existing kernels: all shifted
+circuits of a query are evaluated as ONE vmap-style batch (batched matrices for the shifted
+gates only).  Cost: two batch elements per (parameter, dependent gate) pair, like a
+parameter-shift gradient; the adjoint-state sweep (O(1) simulations) is the next step
+(DESIGN.md 7).
+
+What is differentiated is the function itself, not a restricted form of it:
+  * dM_j/d theta_k comes from re-running the *recording* of ``f`` (no device work) at
+    theta_k +- h and differencing the recorded gate matrices (central difference on smooth
+    2x2 / 4x4 matrices in float64: error ~1e-9);
+  * the host arithmetic that turns expectation values into the loss is differentiated the same
+    way: ``f`` is replayed with one stored expectation value nudged at a time (exact when the
+    loss is linear in the expectation values, as in every energy function).
+Limits: real parameters; queries are expectation values (``expectation_ps``, ``expectation``,
+the measurement templates); circuits start from |0..0>; the structure of ``f`` must not depend on
+the parameter values (the same restriction ``jit`` has in the reference)."""
+
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import circuit as _circuit
+from . import engine as _engine
+from .batching import BatchArray
+
+_H_PARAM = 1e-4   # central-difference step for d(gate matrix)/d(parameter)
+_H_VALUE = 1e-3   # nudge of a stored expectation value when differentiating the host arithmetic
+_MAX_BATCH_AMPS = 1 << 28
+
+
+class _Query:
+    def __init__(self, circ: Any, fl: Sequence[int], sg: Sequence[int], ny: Sequence[int]):
+        self.nqubits = circ._nqubits
+        self.ops = [(tuple(op.qubits), np.array(np.asarray(op.matrix), dtype=np.complex128)) for op in circ._ops]
+        self.fl, self.sg, self.ny = list(fl), list(sg), list(ny)
+        self.values: Optional[np.ndarray] = None  # complex [nterms]
+
+
+class _Trace:
+    """Context shared by the recording / replaying state stand-ins."""
+
+    def __init__(self, replay: Optional[List[np.ndarray]] = None):
+        self.queries: List[_Query] = []
+        self.replay = replay
+
+
+class _RecordingState:
+    """Wraps the real device state: every expectation query is logged with the circuit that asked."""
+
+    def __init__(self, real: Any, trace: _Trace):
+        self.__dict__["_real"] = real
+        self.__dict__["_trace"] = trace
+        self.__dict__["_circ"] = None
+
+    def __getattr__(self, name: str) -> Any:
+        return getattr(self._real, name)
+
+    def __setattr__(self, name: str, value: Any) -> None:
+        if name in ("_circ",):
+            self.__dict__[name] = value
+        else:
+            setattr(self._real, name, value)
+
+    def expectation_terms(self, fl: Sequence[int], sg: Sequence[int], ny: Sequence[int]) -> np.ndarray:
+        r = self._real.expectation_terms(fl, sg, ny)
+        if self._real.batch != 1:
+            raise NotImplementedError("value_and_grad of a function that vmaps internally")
+        q = _Query(self._circ, fl, sg, ny)
+        q.values = np.array(r[0], dtype=np.complex128)
+        self._trace.queries.append(q)
+        return r
+
+
+class _ReplayState:
+    """No device at all: gates are only recorded by the Circuit, queries return stored values."""
+
+    batch = 1
+
+    def __init__(self, nbits: int, dtype: str, batch: int, trace: _Trace):
+        if batch != 1:
+            raise NotImplementedError("value_and_grad of a function that vmaps internally")
+        self.nbits, self.dtype, self._trace, self._circ = nbits, dtype, trace, None
+
+    def init_zero(self) -> None:
+        pass
+
+    def load(self, src: Any) -> None:
+        raise NotImplementedError("value_and_grad: circuits with inputs= are not differentiable here yet")
+
+    def apply_planned(self, blocks: Any) -> int:
+        return 0
+
+    def apply_blocks(self, blocks: Any) -> None:
+        pass
+
+    def expectation_terms(self, fl: Sequence[int], sg: Sequence[int], ny: Sequence[int]) -> np.ndarray:
+        i = len(self._trace.queries)
+        q = _Query(self._circ, fl, sg, ny)
+        self._trace.queries.append(q)
+        if self._trace.replay is None or i >= len(self._trace.replay) or len(self._trace.replay[i]) != len(fl):
+            raise RuntimeError("value_and_grad: the structure of the function changed between evaluations")
+        return np.asarray(self._trace.replay[i], dtype=np.complex128)[None, :]
+
+    def __getattr__(self, name: str) -> Any:
+        raise NotImplementedError("value_and_grad: %s() is not differentiable (only expectation values are)" % name)
+
+
+def _run(f: Callable[..., Any], args: Sequence[Any], kws: Dict[str, Any], trace: _Trace, replay: bool) -> Any:
+    """Call ``f`` with the Circuit class bound to a recording (device) or replaying (host) state."""
+    real_cls = _engine.DeviceState
+
+    def factory(nbits: int, dtype: str = "complex64", batch: int = 1, **kw: Any) -> Any:
+        if replay:
+            return _ReplayState(nbits, dtype, batch, trace)
+        return _RecordingState(real_cls(nbits, dtype, batch, **kw), trace)
+
+    old_hook = _circuit._STATE_HOOK
+    _engine.DeviceState = factory  # type: ignore[assignment]
+    _circuit._STATE_HOOK = lambda circ, st: setattr(st, "_circ", circ)
+    try:
+        return f(*args, **kws)
+    finally:
+        _engine.DeviceState = real_cls  # type: ignore[assignment]
+        _circuit._STATE_HOOK = old_hook
+
+
+def _scalar(out: Any, has_aux: bool) -> Tuple[float, Any]:
+    aux = None
+    if has_aux:
+        out, aux = out[0], out[1]
+    v = np.asarray(out)
+    if v.size != 1:
+        raise ValueError("value_and_grad needs a scalar loss")
+    return float(np.real(v.reshape(-1)[0])), aux
+
+
+def _shift_batch(q: _Query, base: _Query, shifts: List[Tuple[int, np.ndarray]], dtype: str) -> np.ndarray:
+    """E+ - E- for every (gate j, D) in ``shifts`` on query ``q``: complex [nshifts, nterms], each the
+    difference of the query's expectation values with gate j replaced by M_j + D and M_j - D."""
+    n = q.nqubits
+    out = np.zeros((len(shifts), len(q.fl)), dtype=np.complex128)
+    per = max(1, _MAX_BATCH_AMPS >> n) // 2
+    for c0 in range(0, len(shifts), per):
+        chunk = shifts[c0 : c0 + per]
+        B = 2 * len(chunk)
+        touched: Dict[int, np.ndarray] = {}
+        for b, (j, D) in enumerate(chunk):
+            if j not in touched:
+                touched[j] = np.broadcast_to(base.ops[j][1], (B,) + base.ops[j][1].shape).copy()
+            touched[j][2 * b] = base.ops[j][1] + D
+            touched[j][2 * b + 1] = base.ops[j][1] - D
+        c = _circuit.Circuit(n)
+        for j, (qubits, M) in enumerate(base.ops):
+            c.any(*qubits, unitary=BatchArray(touched[j]) if j in touched else M)
+        if c._batch is None:  # nothing batched (cannot happen with a non-empty chunk)
+            continue
+        st = c._ensure_state()
+        r = np.asarray(st.expectation_terms(q.fl, q.sg, q.ny), dtype=np.complex128)  # [B, nterms]
+        out[c0 : c0 + len(chunk)] = r[0::2] - r[1::2]
+    return out
+
+
+def value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0, has_aux: bool = False) -> Callable[..., Any]:
+    single = isinstance(argnums, int)
+    nums: Tuple[int, ...] = (argnums,) if single else tuple(argnums)  # type: ignore[assignment]
+
+    def wrapper(*args: Any, **kws: Any) -> Any:
+        args = list(args)
+        for i in nums:
+            a = np.asarray(args[i])
+            if np.iscomplexobj(a):
+                if np.abs(a.imag).max() > 0:
+                    raise NotImplementedError("value_and_grad with respect to complex parameters")
+                a = a.real
+            args[i] = np.array(a, dtype=np.float64)
+        # 1. the value, on the device, with every expectation query logged
+        base = _Trace()
+        out = _run(f, args, kws, base, replay=False)
+        value, aux = _scalar(out, has_aux)
+        stored = [q.values for q in base.queries]
+
+        def replay(a: Sequence[Any], values: List[np.ndarray]) -> Tuple[float, _Trace]:
+            t = _Trace(replay=values)
+            v, _ = _scalar(_run(f, a, kws, t, replay=True), has_aux)
+            return v, t
+
+        # 2. d loss / d (expectation value), by nudging one stored value at a time
+        dl_de = [np.zeros(len(v)) for v in stored]
+        for qi, v in enumerate(stored):
+            for t in range(len(v)):
+                step = _H_VALUE * max(1.0, abs(v[t]))
+                up = [w.copy() for w in stored]
+                dn = [w.copy() for w in stored]
+                up[qi][t] += step
+                dn[qi][t] -= step
+                dl_de[qi][t] = (replay(args, up)[0] - replay(args, dn)[0]) / (2 * step)
+        # 3. per parameter: direct dependence of the host arithmetic + the gates it moves
+        dtype = _circuit.cons.dtypestr
+        grads = []
+        for i in nums:
+            theta = args[i]
+            g = np.zeros(theta.size)
+            flat = theta.reshape(-1)
+            pending: List[List[Tuple[int, int, np.ndarray]]] = [[] for _ in base.queries]  # per query: (k, gate j, D)
+            for k in range(theta.size):
+                h = _H_PARAM * max(1.0, abs(flat[k]))
+                ap, am = list(args), list(args)
+                tp, tm = flat.copy(), flat.copy()
+                tp[k] += h
+                tm[k] -= h
+                ap[i], am[i] = tp.reshape(theta.shape), tm.reshape(theta.shape)
+                vp, trp = replay(ap, stored)
+                vm, trm = replay(am, stored)
+                g[k] += (vp - vm) / (2 * h)  # loss terms that use the parameter outside the circuits
+                if len(trp.queries) != len(base.queries) or len(trm.queries) != len(base.queries):
+                    raise RuntimeError("value_and_grad: the structure of the function depends on the parameter values")
+                for qi, (qp, qm, qb) in enumerate(zip(trp.queries, trm.queries, base.queries)):
+                    if len(qp.ops) != len(qb.ops) or len(qm.ops) != len(qb.ops):
+                        raise RuntimeError("value_and_grad: the circuit structure depends on the parameter values")
+                    if not np.any(dl_de[qi]):
+                        continue
+                    for j, ((_, Mp), (_, Mm)) in enumerate(zip(qp.ops, qm.ops)):
+                        D = (Mp - Mm) / (2 * h)
+                        if np.abs(D).max() > 1e-12:
+                            pending[qi].append((k, j, D))
+            for qi, lst in enumerate(pending):
+                if not lst:
+                    continue
+                diff = _shift_batch(base.queries[qi], base.queries[qi], [(j, D) for _, j, D in lst], dtype)  # [nshift, nterms]
+                de = 0.5 * np.real(diff)  # d E_t / d theta through that gate
+                contrib = de @ dl_de[qi]
+                for (k, _, _), c in zip(lst, contrib):
+                    g[k] += c
+            grads.append(g.reshape(theta.shape))
+        gr: Any = grads[0] if single else tuple(grads)
+        val: Any = np.asarray(value)
+        return ((val, aux), gr) if has_aux else (val, gr)
+
+    return wrapper
+
+
+def grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0, has_aux: bool = False) -> Callable[..., Any]:
+    vg = value_and_grad(f, argnums=argnums, has_aux=has_aux)
+
+    def wrapper(*args: Any, **kws: Any) -> Any:
+        v, g = vg(*args, **kws)
+        return (g, v[1]) if has_aux else g
+
+    return wrapper
+
+
+def vectorized_value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0,
+                              vectorized_argnums: Union[int, Sequence[int]] = 0, has_aux: bool = False) -> Callable[..., Any]:
+    """jax_backend.py:734-776: values per batch element; the gradient is that of the SUM over the
+    batch -- so it is per element for an argument that is itself vectorised and summed otherwise."""
+    if has_aux:
+        raise NotImplementedError("vvag with has_aux")
+    single = isinstance(argnums, int)
+    nums: Tuple[int, ...] = (argnums,) if single else tuple(argnums)  # type: ignore[assignment]
+    vnums: Tuple[int, ...] = (vectorized_argnums,) if isinstance(vectorized_argnums, int) else tuple(vectorized_argnums)
+    vg = value_and_grad(f, argnums=nums)
+
+    def wrapper(*args: Any, **kws: Any) -> Any:
+        B = int(np.shape(args[vnums[0]])[0])
+        vals, per = [], []
+        for b in range(B):
+            a = [np.asarray(x)[b] if i in vnums else x for i, x in enumerate(args)]
+            v, g = vg(*a, **kws)
+            vals.append(v)
+            per.append(g)
+        grads = []
+        for pos, i in enumerate(nums):
+            gs = np.stack([p[pos] for p in per])
+            grads.append(gs if i in vnums else gs.sum(axis=0))
+        return np.asarray(vals), (grads[0] if single else tuple(grads))
+
+    return wrapper

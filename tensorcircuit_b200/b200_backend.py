@@ -277,19 +277,24 @@ class B200Backend:
 
         return wrapper
 
+    # Gradients of losses built from expectation values (autodiff.py): an exact shift rule on the
+    # gate matrices, all shifted circuits evaluated as one batch on the same kernels.
+    def value_and_grad(self, f: Callable[..., Any], argnums: Any = 0, has_aux: bool = False) -> Callable[..., Any]:
+        from . import autodiff
+
+        return autodiff.value_and_grad(f, argnums=argnums, has_aux=has_aux)
+
+    def grad(self, f: Callable[..., Any], argnums: Any = 0, has_aux: bool = False) -> Callable[..., Any]:
+        from . import autodiff
+
+        return autodiff.grad(f, argnums=argnums, has_aux=has_aux)
+
     def vectorized_value_and_grad(self, f: Callable[..., Any], argnums: Any = 0, vectorized_argnums: Any = 0, has_aux: bool = False) -> Callable[..., Any]:
-        raise NotImplementedError(
-            "gradients through the B200 engine (adjoint-state method) are the next scope row (SURVEY 8f-2)"
-        )
+        from . import autodiff
+
+        return autodiff.vectorized_value_and_grad(f, argnums=argnums, vectorized_argnums=vectorized_argnums, has_aux=has_aux)
 
     vvag = vectorized_value_and_grad
-
-    def value_and_grad(self, f: Callable[..., Any], argnums: Any = 0, has_aux: bool = False) -> Callable[..., Any]:
-        raise NotImplementedError(
-            "gradients through the B200 engine (adjoint-state method) are the next scope row (SURVEY 8f-2)"
-        )
-
-    grad = value_and_grad
 
 
 _INSTANCE: Optional[B200Backend] = None

@@ -41,6 +41,10 @@ gate_aliases = [
 ]
 
 
+# autodiff.py binds every new engine state to the Circuit that created it through this hook
+_STATE_HOOK: Optional[Callable[[Any, Any], None]] = None
+
+
 def is_sequence(x: Any) -> bool:
     return isinstance(x, (list, tuple, np.ndarray))
 
@@ -348,6 +352,8 @@ class Circuit:
                 st.load(src)
             self._state = st
             self._applied = 0
+            if _STATE_HOOK is not None:
+                _STATE_HOOK(self, st)
         if self._applied < len(self._ops):
             pending = self._ops[self._applied :]
             blocks = fuse(pending, self._ntot, kmax=self.fusion_kmax)

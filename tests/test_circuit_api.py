@@ -181,6 +181,26 @@ def test_mixed_measurement_circuit(eng):
         r = tc.templates.measurements.parameterized_measurements(c, s, onehot=False)
         np.testing.assert_allclose(r, v[i], atol=1e-5)
 
+    # the reference's own body: vvag over the structures, value and gradient pinned (:536-554)
+    def f(params, structures):
+        c = tc.Circuit(n)
+        for i in range(n):
+            c.H(i)
+        for j in range(2):
+            for i in range(n):
+                c.cnot(i, (i + 1) % n)
+            for i in range(n):
+                c.rz(i, theta=params[j, i])
+        obs = []
+        for i in range(n):
+            obs.append([tc.gates.Gate(sum([structures[i, k] * g.tensor for k, g in enumerate(tc.gates.pauli_gates)])), (i,)])
+        return tc.backend.real(c.expectation(*obs, reuse=False))
+
+    structures = np.eye(4)[np.eye(n, dtype=int)]  # onehot(eye(n), 4): [n, n, 4]
+    v, g = tc.backend.vvag(f, vectorized_argnums=1, argnums=0)(np.ones([2, n]), structures)
+    np.testing.assert_allclose(v, [0.157729, 0.157729, 0.157728, 0.085221], atol=1e-5)
+    np.testing.assert_allclose(g[0], [-0.378372, -0.624019, -0.491295, -0.378372], atol=1e-5)
+
 
 def test_circuit_replace_inputs(eng):
     # tests/test_circuit.py:571-580
@@ -815,3 +835,141 @@ def test_heisenberg_measurements(eng):
         want += (0.3 * o.expectation_ps(x=[i]) - 0.2 * o.expectation_ps(z=[i])).real
     got = tc.templates.measurements.heisenberg_measurements(c, g, hzz=0.8, hyy=0.6, hxx=-0.4, hx=0.3, hz=-0.2)
     np.testing.assert_allclose(got, want, atol=2e-5)
+
+
+# ---- gradients (backends/jax_backend.py:668-776; tests/test_backends.py:453-476) --------------------
+def _vqe_energy_oracle(params, n, nlayers):
+    o = OracleCircuit(n)
+    for i in range(n):
+        o.h(i)
+    for l in range(nlayers):
+        for i in range(n - 1):
+            o.rzz(i, i + 1, theta=params[2 * l, i])
+        for i in range(n):
+            o.rx(i, theta=params[2 * l + 1, i])
+    e = 0.0
+    for i in range(n):
+        e += o.expectation_ps(x=[i]).real
+    for i in range(n - 1):
+        e += 0.7 * o.expectation_ps(z=[i, i + 1]).real
+    return e
+
+
+def test_value_and_grad_vqe(eng, highp):
+    """K.value_and_grad of a VQE energy (rzz / rx layers, sum of <X_i> and <Z_i Z_i+1>) against
+    central differences of the float64 oracle."""
+    n, nlayers = 4, 2
+    K = tc.backend
+
+    def energy(params, scale):
+        c = tc.Circuit(n)
+        for i in range(n):
+            c.h(i)
+        for l in range(nlayers):
+            for i in range(n - 1):
+                c.rzz(i, i + 1, theta=params[2 * l, i])
+            for i in range(n):
+                c.rx(i, theta=params[2 * l + 1, i])
+        e = 0.0
+        for i in range(n):
+            e = e + c.expectation_ps(x=[i])
+        zz = tc.templates.measurements.pauli_sum_expectation(c, [[3 if q in (i, i + 1) else 0 for q in range(n)] for i in range(n - 1)])
+        return K.real(e) + scale * zz + 0.1 * K.sum(params**2)  # the last term: direct dependence
+
+    params = np.random.default_rng(3).uniform(0, 2, size=(2 * nlayers, n))
+    v, g = K.value_and_grad(energy)(params, 0.7)
+    want_v = _vqe_energy_oracle(params, n, nlayers) + 0.1 * np.sum(params**2)
+    np.testing.assert_allclose(v, want_v, atol=1e-9)
+    want_g = np.zeros_like(params)
+    h = 1e-6
+    for idx in np.ndindex(params.shape):
+        p1, p2 = params.copy(), params.copy()
+        p1[idx] += h
+        p2[idx] -= h
+        want_g[idx] = (_vqe_energy_oracle(p1, n, nlayers) - _vqe_energy_oracle(p2, n, nlayers)) / (2 * h) + 0.2 * params[idx]
+    np.testing.assert_allclose(g, want_g, atol=2e-7)
+    # grad alone, and the second argument (enters only the host arithmetic)
+    np.testing.assert_allclose(K.grad(energy)(params, 0.7), want_g, atol=2e-7)
+    v2, (g0, g1) = K.value_and_grad(energy, argnums=(0, 1))(params, 0.7)
+    o = OracleCircuit(n)
+    np.testing.assert_allclose(g0, want_g, atol=2e-7)
+    zz_val = (want_v - 0.1 * np.sum(params**2) - _vqe_energy_oracle_x_only(params, n, nlayers)) / 0.7
+    np.testing.assert_allclose(g1, zz_val, atol=1e-7)
+
+
+def _vqe_energy_oracle_x_only(params, n, nlayers):
+    o = OracleCircuit(n)
+    for i in range(n):
+        o.h(i)
+    for l in range(nlayers):
+        for i in range(n - 1):
+            o.rzz(i, i + 1, theta=params[2 * l, i])
+        for i in range(n):
+            o.rx(i, theta=params[2 * l + 1, i])
+    return sum(o.expectation_ps(x=[i]).real for i in range(n))
+
+
+def test_vvag_shared_and_vectorized_args(eng):
+    """vvag: values per batch element, gradient of the sum -- per element for the vectorised
+    argument, summed for the shared one (tests/test_backends.py:453-476 semantics)."""
+    n = 3
+    K = tc.backend
+
+    def f(x, w):
+        c = tc.Circuit(n)
+        for i in range(n):
+            c.ry(i, theta=x[i])
+        c.cnot(0, 1)
+        c.rzz(1, 2, theta=w[0])
+        c.rx(0, theta=w[1] * x[0])  # a parameter product: both arguments move this gate
+        return K.real(c.expectation_ps(z=[0, 2]) + 0.5 * c.expectation_ps(x=[1]))
+
+    def oracle(x, w):
+        o = OracleCircuit(n)
+        for i in range(n):
+            o.ry(i, theta=x[i])
+        o.cnot(0, 1)
+        o.rzz(1, 2, theta=w[0])
+        o.rx(0, theta=w[1] * x[0])
+        return (o.expectation_ps(z=[0, 2]) + 0.5 * o.expectation_ps(x=[1])).real
+
+    xs = np.random.default_rng(1).uniform(0, 3, size=(3, n))
+    w = np.array([0.4, 1.3])
+    vals, (gx, gw) = K.vvag(f, argnums=(0, 1), vectorized_argnums=0)(xs, w)
+    h = 1e-6
+    for b in range(3):
+        np.testing.assert_allclose(vals[b], oracle(xs[b], w), atol=2e-6)
+        for i in range(n):
+            e = np.zeros(n)
+            e[i] = h
+            np.testing.assert_allclose(gx[b, i], (oracle(xs[b] + e, w) - oracle(xs[b] - e, w)) / (2 * h), atol=2e-5)
+    for i in range(2):
+        e = np.zeros(2)
+        e[i] = h
+        want = sum((oracle(xs[b], w + e) - oracle(xs[b], w - e)) / (2 * h) for b in range(3))
+        np.testing.assert_allclose(gw[i], want, atol=5e-5)
+
+
+def test_ad(eng):
+    # tests/test_circuit.py:296-317 (universal_ad): scalar parameter, grad == value_and_grad
+    K = tc.backend
+
+    def forward(theta):
+        c = tc.Circuit(2)
+        c.R(0, theta=theta, alpha=0.5, phi=0.8)
+        return K.real(c.expectation((tc.gates.z(), [0])))
+
+    gg = K.jit(K.grad(forward))
+    vg = K.jit(K.value_and_grad(forward))
+    theta = tc.gates.num_to_tensor(1.0)
+    grad1 = gg(theta)
+    v2, grad2 = vg(theta)
+    assert grad1 == grad2
+
+    def want(t):
+        o = OracleCircuit(2)
+        o.r(0, theta=t, alpha=0.5, phi=0.8)
+        return o.expectation_ps(z=[0]).real
+
+    np.testing.assert_allclose(v2, want(1.0), atol=2e-6)
+    np.testing.assert_allclose(grad2, (want(1.0 + 1e-6) - want(1.0 - 1e-6)) / 2e-6, atol=2e-5)
