@@ -43,6 +43,7 @@ _MAX_BATCH_AMPS = 1 << 28
 class _Query:
     def __init__(self, circ: Any, fl: Sequence[int], sg: Sequence[int], ny: Sequence[int]):
         self.nqubits = circ._nqubits
+        self.key = (id(circ), len(circ._ops))  # queries on the same circuit prefix share their simulations
         self.ops = [(tuple(op.qubits), np.array(np.asarray(op.matrix), dtype=np.complex128)) for op in circ._ops]
         self.fl, self.sg, self.ny = list(fl), list(sg), list(ny)
         self.values: Optional[np.ndarray] = None  # complex [nterms]
@@ -151,7 +152,7 @@ def _shift_batch(q: _Query, base: _Query, shifts: List[Tuple[int, np.ndarray]], 
     difference of the query's expectation values with gate j replaced by M_j + D and M_j - D."""
     n = q.nqubits
     out = np.zeros((len(shifts), len(q.fl)), dtype=np.complex128)
-    per = max(1, _MAX_BATCH_AMPS >> n) // 2
+    per = max(1, (_MAX_BATCH_AMPS >> n) // 2)  # shifts per batched run (two states each)
     for c0 in range(0, len(shifts), per):
         chunk = shifts[c0 : c0 + per]
         B = 2 * len(chunk)
@@ -213,7 +214,12 @@ def value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0
             theta = args[i]
             g = np.zeros(theta.size)
             flat = theta.reshape(-1)
-            pending: List[List[Tuple[int, int, np.ndarray]]] = [[] for _ in base.queries]  # per query: (k, gate j, D)
+            # queries asked of the same circuit prefix (a loop of expectation_ps calls) form one group
+            groups: Dict[Any, List[int]] = {}
+            for qi, qb in enumerate(base.queries):
+                groups.setdefault(qb.key, []).append(qi)
+            leader = {qi: members[0] for members in groups.values() for qi in members}
+            pending: List[List[Tuple[int, int, np.ndarray]]] = [[] for _ in base.queries]  # per group leader: (k, gate j, D)
             for k in range(theta.size):
                 h = _H_PARAM * max(1.0, abs(flat[k]))
                 ap, am = list(args), list(args)
@@ -229,7 +235,7 @@ def value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0
                 for qi, (qp, qm, qb) in enumerate(zip(trp.queries, trm.queries, base.queries)):
                     if len(qp.ops) != len(qb.ops) or len(qm.ops) != len(qb.ops):
                         raise RuntimeError("value_and_grad: the circuit structure depends on the parameter values")
-                    if not np.any(dl_de[qi]):
+                    if leader[qi] != qi or not any(np.any(dl_de[m]) for m in groups[qb.key]):
                         continue
                     for j, ((_, Mp), (_, Mm)) in enumerate(zip(qp.ops, qm.ops)):
                         D = (Mp - Mm) / (2 * h)
@@ -238,9 +244,15 @@ def value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0
             for qi, lst in enumerate(pending):
                 if not lst:
                     continue
-                diff = _shift_batch(base.queries[qi], base.queries[qi], [(j, D) for _, j, D in lst], dtype)  # [nshift, nterms]
+                members = groups[base.queries[qi].key]
+                merged = _Query.__new__(_Query)  # all terms of the group in one batched evaluation
+                merged.nqubits, merged.ops = base.queries[qi].nqubits, base.queries[qi].ops
+                merged.fl = [x for m in members for x in base.queries[m].fl]
+                merged.sg = [x for m in members for x in base.queries[m].sg]
+                merged.ny = [x for m in members for x in base.queries[m].ny]
+                diff = _shift_batch(merged, merged, [(j, D) for _, j, D in lst], dtype)  # [nshift, nterms]
                 de = 0.5 * np.real(diff)  # d E_t / d theta through that gate
-                contrib = de @ dl_de[qi]
+                contrib = de @ np.concatenate([dl_de[m] for m in members])
                 for (k, _, _), c in zip(lst, contrib):
                     g[k] += c
             grads.append(g.reshape(theta.shape))
