@@ -973,3 +973,38 @@ def test_ad(eng):
 
     np.testing.assert_allclose(v2, want(1.0), atol=2e-6)
     np.testing.assert_allclose(grad2, (want(1.0 + 1e-6) - want(1.0 - 1e-6)) / 2e-6, atol=2e-5)
+
+
+def test_vqe_training_loop(eng):
+    """A VQE script as users write it against the reference (benchmarks/scripts/vqe_tc.py shape):
+    K.jit(K.value_and_grad(energy)) inside a gradient-descent loop lowers the TFIM energy."""
+    n, nlayers = 4, 2
+    K = tc.backend
+    g = tc.templates.graphs.Line1D(n, pbc=False)
+
+    def energy(params):
+        c = tc.Circuit(n)
+        for i in range(n):
+            c.h(i)
+        for l in range(nlayers):
+            for i in range(n - 1):
+                c.rzz(i, i + 1, theta=params[2 * l, i])
+            for i in range(n):
+                c.rx(i, theta=params[2 * l + 1, i])
+        return tc.templates.measurements.heisenberg_measurements(c, g, hzz=1.0, hxx=0.0, hyy=0.0, hx=-1.0)
+
+    vg = K.jit(K.value_and_grad(energy))
+    params = 0.1 * np.ones((2 * nlayers, n))
+    e0, _ = vg(params)
+    for _ in range(15):
+        e, grad = vg(params)
+        params = params - 0.1 * grad
+    e1, _ = vg(params)
+    assert e1 < e0 - 0.5, (e0, e1)
+    # exact ground energy of the open 4-site TFIM (J = 1, h = -1) bounds it from below
+    H = np.zeros((16, 16), dtype=complex)
+    for i in range(n - 1):
+        H += orc.pauli_string_matrix([3 if q in (i, i + 1) else 0 for q in range(n)])
+    for i in range(n):
+        H -= orc.pauli_string_matrix([1 if q == i else 0 for q in range(n)])
+    assert e1 > np.linalg.eigvalsh(H)[0] - 1e-4
