@@ -11,7 +11,7 @@ engine runs batched kernels; with several ranks (torchrun) the batch is sharded 
 
 from __future__ import annotations
 
-from typing import Any, Callable, Optional, Sequence, Tuple, Union
+from typing import Any, Callable, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 
@@ -192,6 +192,130 @@ class B200Backend:
 
     def norm(self, a: Any) -> Any:
         return np.linalg.norm(np.asarray(_np(a)))
+
+    # -- the rest of the small-tensor method table (abstract_backend.py:18-913, numpy_backend.py) --------
+    # Host glue for parameter-sized data, so that scripts written against the reference's backend
+    # object find the names they use; nothing here touches O(2^n) data.
+    def _u1(fn: Callable[..., Any]):  # type: ignore[misc]
+        def f(self, *a: Any, **k: Any) -> Any:
+            return fn(*[_np(x) for x in a], **k)
+
+        return f
+
+    acos = _u1(np.arccos)
+    acosh = _u1(np.arccosh)
+    asin = _u1(np.arcsin)
+    asinh = _u1(np.arcsinh)
+    atan = _u1(np.arctan)
+    atan2 = _u1(np.arctan2)
+    atanh = _u1(np.arctanh)
+    cosh = _u1(np.cosh)
+    sinh = _u1(np.sinh)
+    del _u1
+
+    def relu(self, a: Any) -> Any:
+        return np.maximum(_np(a), 0)
+
+    def sigmoid(self, a: Any) -> Any:
+        return 1.0 / (1.0 + np.exp(-_np(a)))
+
+    def softmax(self, a: Sequence[Any], axis: Optional[int] = None) -> Any:
+        a = np.asarray(_np(a))
+        e = np.exp(a - np.max(a, axis=axis, keepdims=True))
+        return e / np.sum(e, axis=axis, keepdims=True)
+
+    def std(self, a: Any, axis: Any = None, keepdims: bool = False) -> Any:
+        return np.std(np.asarray(_np(a)), axis=axis, keepdims=keepdims)
+
+    def tile(self, a: Any, rep: Any) -> Any:
+        return np.tile(np.asarray(_np(a)), np.asarray(rep))
+
+    def argmin(self, a: Any, axis: int = 0) -> Any:
+        return np.argmin(np.asarray(_np(a)), axis=axis)
+
+    def copy(self, a: Any) -> Any:
+        return np.array(np.asarray(_np(a)), copy=True)
+
+    def stop_gradient(self, a: Any) -> Any:
+        return a
+
+    def cond(self, pred: bool, true_fun: Callable[[], Any], false_fun: Callable[[], Any]) -> Any:
+        return true_fun() if pred else false_fun()
+
+    def switch(self, index: Any, branches: Sequence[Callable[[], Any]]) -> Any:
+        return branches[int(np.asarray(index))]()
+
+    def scan(self, f: Callable[[Any, Any], Any], xs: Any, init: Any) -> Any:
+        carry = init
+        for x in np.asarray(_np(xs)):
+            carry = f(carry, x)
+        return carry
+
+    def eigvalsh(self, a: Any) -> Any:
+        return np.linalg.eigvalsh(np.asarray(_np(a)))
+
+    def det(self, a: Any) -> Any:
+        return np.linalg.det(np.asarray(_np(a)))
+
+    def solve(self, A: Any, b: Any, **kws: Any) -> Any:
+        return np.linalg.solve(np.asarray(_np(A)), np.asarray(_np(b)))
+
+    def sqrtmh(self, a: Any) -> Any:
+        e, v = np.linalg.eigh(np.asarray(_np(a)))
+        return v @ np.diag(np.sqrt(e.astype(complex))) @ v.conj().T
+
+    def tree_map(self, f: Callable[..., Any], *pytrees: Any) -> Any:
+        t0 = pytrees[0]
+        if isinstance(t0, (list, tuple)):
+            return type(t0)(self.tree_map(f, *[p[i] for p in pytrees]) for i in range(len(t0)))
+        if isinstance(t0, dict):
+            return {k: self.tree_map(f, *[p[k] for p in pytrees]) for k in t0}
+        return f(*pytrees)
+
+    def tree_flatten(self, pytree: Any) -> Tuple[List[Any], Any]:
+        leaves: List[Any] = []
+
+        def go(t: Any) -> Any:
+            if isinstance(t, (list, tuple)):
+                return (type(t), [go(x) for x in t])
+            if isinstance(t, dict):
+                return (dict, {k: go(v) for k, v in t.items()})
+            leaves.append(t)
+            return None
+
+        return leaves, go(pytree)
+
+    def tree_unflatten(self, treedef: Any, leaves: Sequence[Any]) -> Any:
+        it = iter(leaves)
+
+        def go(d: Any) -> Any:
+            if d is None:
+                return next(it)
+            kind, sub = d
+            if kind is dict:
+                return {k: go(v) for k, v in sub.items()}
+            return kind(go(x) for x in sub)
+
+        return go(treedef)
+
+    def device(self, a: Any) -> str:
+        from .circuit import DeviceArray
+
+        return str(a.t.device) if isinstance(a, DeviceArray) else "cpu"
+
+    def device_move(self, a: Any, dev: Any) -> Any:
+        return a
+
+    def implicit_randc(self, a: Any, shape: Union[int, Sequence[int]], p: Optional[Any] = None) -> Any:
+        return self.stateful_randc(self.g, a, shape, p)
+
+    def stateful_randc(self, g: Any, a: Any, shape: Union[int, Sequence[int]], p: Optional[Any] = None) -> Any:
+        if isinstance(shape, int):
+            shape = (shape,)
+        if g is None:
+            g = self.g
+        pv = None if p is None else np.asarray(_np(p), dtype=np.float64)
+        return g.choice(np.asarray(_np(a)) if not isinstance(a, int) else a, size=shape, p=None if pv is None else pv / pv.sum())
 
     # -- randomness (abstract_backend.py:914-1122; numpy_backend.py:245-308) -------------------
     def set_random_state(self, seed: Optional[Any] = None, get_only: bool = False) -> Any:

@@ -1008,3 +1008,28 @@ def test_vqe_training_loop(eng):
     for i in range(n):
         H -= orc.pauli_string_matrix([1 if q == i else 0 for q in range(n)])
     assert e1 > np.linalg.eigvalsh(H)[0] - 1e-4
+
+
+def test_backend_small_tensor_table(eng):
+    # tests/test_backends.py (method table smoke checks): host glue the scripts call around circuits
+    K = tc.backend
+    np.testing.assert_allclose(K.softmax(np.array([1.0, 2.0, 3.0])).sum(), 1.0)
+    np.testing.assert_allclose(K.relu(np.array([-1.0, 2.0])), [0, 2])
+    np.testing.assert_allclose(K.sigmoid(np.array([0.0])), [0.5])
+    np.testing.assert_allclose(K.acos(K.cos(np.array([0.3]))), [0.3])
+    np.testing.assert_allclose(K.atan2(np.array([1.0]), np.array([1.0])), [np.pi / 4])
+    np.testing.assert_allclose(K.tile(np.array([1, 2]), [2]), [1, 2, 1, 2])
+    np.testing.assert_allclose(K.std(np.array([1.0, 3.0])), 1.0)
+    assert K.argmin(np.array([3, 1, 2])) == 1
+    assert K.cond(True, lambda: 1, lambda: 2) == 1 and K.switch(1, [lambda: 1, lambda: 2]) == 2
+    assert K.scan(lambda c, x: c + x, np.arange(4), 0) == 6
+    np.testing.assert_allclose(K.eigvalsh(np.diag([2.0, 1.0])), [1, 2])
+    np.testing.assert_allclose(K.sqrtmh(np.diag([4.0, 9.0])), np.diag([2.0, 3.0]), atol=1e-12)
+    leaves, td = K.tree_flatten({"a": [np.ones(2), 3.0], "b": (1,)})
+    assert len(leaves) == 3
+    back = K.tree_unflatten(td, leaves)
+    assert back["b"] == (1,) and back["a"][1] == 3.0
+    assert K.tree_map(lambda x, y: x + y, [1, (2, 3)], [10, (20, 30)]) == [11, (22, 33)]
+    K.set_random_state(7)
+    r = K.implicit_randc(4, shape=[100], p=np.array([0.0, 1.0, 0.0, 0.0]))
+    assert np.all(r == 1)
