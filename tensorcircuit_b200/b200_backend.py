@@ -420,6 +420,19 @@ class B200Backend:
 
     vvag = vectorized_value_and_grad
 
+    def _no_ad(name: str):  # type: ignore[misc]
+        def f(self, *a: Any, **k: Any) -> Any:
+            raise NotImplementedError("%s: only value_and_grad / grad / vvag of expectation-value losses are built (autodiff.py)" % name)
+
+        return f
+
+    jvp = _no_ad("jvp")
+    vjp = _no_ad("vjp")
+    jacfwd = _no_ad("jacfwd")
+    jacrev = _no_ad("jacrev")
+    hessian = _no_ad("hessian")
+    del _no_ad
+
 
 _INSTANCE: Optional[B200Backend] = None
 

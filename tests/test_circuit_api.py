@@ -1033,3 +1033,32 @@ def test_backend_small_tensor_table(eng):
     K.set_random_state(7)
     r = K.implicit_randc(4, shape=[100], p=np.array([0.0, 1.0, 0.0, 0.0]))
     assert np.all(r == 1)
+
+
+def test_value_and_grad_limits(eng):
+    """what the gradient does not cover fails loudly, not silently"""
+    K = tc.backend
+
+    def uses_state(p):
+        c = tc.Circuit(2)
+        c.rx(0, theta=p[0])
+        return K.real(K.sum(np.asarray(c.wavefunction())))
+
+    with pytest.raises(NotImplementedError):
+        K.value_and_grad(uses_state)(np.array([0.3]))
+
+    def uses_inputs(p):
+        c = tc.Circuit(1, inputs=np.array([1.0, 0.0]))
+        c.rx(0, theta=p[0])
+        return K.real(c.expectation_ps(z=[0]))
+
+    with pytest.raises(NotImplementedError):
+        K.value_and_grad(uses_inputs)(np.array([0.3]))
+    with pytest.raises(NotImplementedError):
+        K.hessian(lambda x: x)
+    with pytest.raises(ValueError):
+        K.value_and_grad(lambda p: p * np.ones(2))(np.array([0.3]))  # not a scalar loss
+    # a loss that does not touch a circuit at all still differentiates (direct dependence only)
+    v, g = K.value_and_grad(lambda p: K.sum(p**2))(np.array([1.0, 2.0]))
+    np.testing.assert_allclose(v, 5.0)
+    np.testing.assert_allclose(g, [2.0, 4.0], atol=1e-7)
