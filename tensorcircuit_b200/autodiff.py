@@ -44,7 +44,9 @@ class _Query:
     def __init__(self, circ: Any, fl: Sequence[int], sg: Sequence[int], ny: Sequence[int]):
         self.nqubits = circ._nqubits
         self.key = (id(circ), len(circ._ops))  # queries on the same circuit prefix share their simulations
-        self.ops = [(tuple(op.qubits), np.array(np.asarray(op.matrix), dtype=np.complex128)) for op in circ._ops]
+        # matrix [D, D], or [B, D, D] when the recording itself was run on a batch of nudged parameters
+        self.ops = [(tuple(op.qubits), np.array(op.matrix.a if isinstance(op.matrix, BatchArray) else np.asarray(op.matrix), dtype=np.complex128))
+                    for op in circ._ops]
         self.fl, self.sg, self.ny = list(fl), list(sg), list(ny)
         self.values: Optional[np.ndarray] = None  # complex [nterms]
 
@@ -52,9 +54,10 @@ class _Query:
 class _Trace:
     """Context shared by the recording / replaying state stand-ins."""
 
-    def __init__(self, replay: Optional[List[np.ndarray]] = None):
+    def __init__(self, replay: Optional[List[np.ndarray]] = None, value_batch: Optional[int] = None):
         self.queries: List[_Query] = []
-        self.replay = replay
+        self.replay = replay            # per query: complex [nterms], or [value_batch, nterms]
+        self.value_batch = value_batch  # replay a whole batch of nudged expectation values at once
 
 
 class _RecordingState:
@@ -85,14 +88,11 @@ class _RecordingState:
 
 
 class _ReplayState:
-    """No device at all: gates are only recorded by the Circuit, queries return stored values."""
-
-    batch = 1
+    """No device at all: gates are only recorded by the Circuit, queries return stored values
+    (tiled over the batch when the recording runs on a batch of nudged parameters)."""
 
     def __init__(self, nbits: int, dtype: str, batch: int, trace: _Trace):
-        if batch != 1:
-            raise NotImplementedError("value_and_grad of a function that vmaps internally")
-        self.nbits, self.dtype, self._trace, self._circ = nbits, dtype, trace, None
+        self.nbits, self.dtype, self._trace, self._circ, self.batch = nbits, dtype, trace, None, int(batch)
 
     def init_zero(self) -> None:
         pass
@@ -110,9 +110,10 @@ class _ReplayState:
         i = len(self._trace.queries)
         q = _Query(self._circ, fl, sg, ny)
         self._trace.queries.append(q)
-        if self._trace.replay is None or i >= len(self._trace.replay) or len(self._trace.replay[i]) != len(fl):
+        if self._trace.replay is None or i >= len(self._trace.replay) or np.shape(self._trace.replay[i])[-1] != len(fl):
             raise RuntimeError("value_and_grad: the structure of the function changed between evaluations")
-        return np.asarray(self._trace.replay[i], dtype=np.complex128)[None, :]
+        v = np.asarray(self._trace.replay[i], dtype=np.complex128)
+        return v if v.ndim == 2 else np.tile(v[None, :], (self.batch, 1))
 
     def __getattr__(self, name: str) -> Any:
         raise NotImplementedError("value_and_grad: %s() is not differentiable (only expectation values are)" % name)
@@ -129,7 +130,14 @@ def _run(f: Callable[..., Any], args: Sequence[Any], kws: Dict[str, Any], trace:
 
     old_hook = _circuit._STATE_HOOK
     _engine.DeviceState = factory  # type: ignore[assignment]
-    _circuit._STATE_HOOK = lambda circ, st: setattr(st, "_circ", circ)
+
+    def hook(circ: Any, st: Any) -> None:
+        st._circ = circ
+        if replay and trace.value_batch:  # queries must hand BatchArrays to the host arithmetic
+            circ._batch = trace.value_batch
+            st.batch = trace.value_batch
+
+    _circuit._STATE_HOOK = hook
     try:
         return f(*args, **kws)
     finally:
@@ -199,7 +207,37 @@ def value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0
 
         # 2. d loss / d (expectation value), by nudging one stored value at a time
         dl_de = [np.zeros(len(v)) for v in stored]
-        for qi, v in enumerate(stored):
+        nudged = False
+        try:  # all 2m nudges in ONE host pass: the expectation values become BatchArrays
+            m = sum(len(v) for v in stored)
+            if m:
+                vb = [np.tile(v[None, :], (2 * m, 1)) for v in stored]
+                steps = []
+                r = 0
+                for qi, v in enumerate(stored):
+                    for t in range(len(v)):
+                        st_ = _H_VALUE * max(1.0, abs(v[t]))
+                        vb[qi][2 * r, t] += st_
+                        vb[qi][2 * r + 1, t] -= st_
+                        steps.append(st_)
+                        r += 1
+                tr = _Trace(replay=vb, value_batch=2 * m)
+                outb = _run(f, args, kws, tr, replay=True)
+                if has_aux:
+                    outb = outb[0]
+                if len(tr.queries) != len(stored):
+                    raise RuntimeError("structure")
+                if isinstance(outb, BatchArray):
+                    lv = np.real(np.asarray(outb.a, dtype=np.complex128)).reshape(2 * m)
+                    d = (lv[0::2] - lv[1::2]) / (2 * np.asarray(steps))
+                    r = 0
+                    for qi, v in enumerate(stored):
+                        dl_de[qi][:] = d[r : r + len(v)]
+                        r += len(v)
+                nudged = True
+        except (TypeError, ValueError, NotImplementedError, RuntimeError, AttributeError, IndexError):
+            dl_de = [np.zeros(len(v)) for v in stored]
+        for qi, v in enumerate(stored if not nudged else []):
             for t in range(len(v)):
                 step = _H_VALUE * max(1.0, abs(v[t]))
                 up = [w.copy() for w in stored]
@@ -220,7 +258,40 @@ def value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0
                 groups.setdefault(qb.key, []).append(qi)
             leader = {qi: members[0] for members in groups.values() for qi in members}
             pending: List[List[Tuple[int, int, np.ndarray]]] = [[] for _ in base.queries]  # per group leader: (k, gate j, D)
-            for k in range(theta.size):
+            swept = False
+            try:  # all 2P nudged recordings in ONE host pass, the way vmap runs a batch of parameters
+                P = theta.size
+                hs = _H_PARAM * np.maximum(1.0, np.abs(flat))
+                tb = np.repeat(flat[None, :], 2 * P, axis=0)
+                tb[2 * np.arange(P), np.arange(P)] += hs
+                tb[2 * np.arange(P) + 1, np.arange(P)] -= hs
+                ab = list(args)
+                ab[i] = BatchArray(tb.reshape((2 * P,) + theta.shape))
+                tr = _Trace(replay=stored)
+                outb = _run(f, ab, kws, tr, replay=True)
+                if has_aux:
+                    outb = outb[0]
+                if len(tr.queries) != len(base.queries):
+                    raise RuntimeError("structure")
+                if isinstance(outb, BatchArray):
+                    lv = np.real(np.asarray(outb.a, dtype=np.complex128)).reshape(2 * P)
+                    g += (lv[0::2] - lv[1::2]) / (2 * hs)
+                for qi, (qt, qb) in enumerate(zip(tr.queries, base.queries)):
+                    if len(qt.ops) != len(qb.ops):
+                        raise RuntimeError("structure")
+                    if leader[qi] != qi or not any(np.any(dl_de[m]) for m in groups[qb.key]):
+                        continue
+                    for j, (_, Mb) in enumerate(qt.ops):
+                        if Mb.ndim != 3:
+                            continue  # this gate does not see the parameters
+                        Dall = (Mb[0::2] - Mb[1::2]) / (2 * hs)[:, None, None]
+                        for k in np.nonzero(np.abs(Dall).reshape(P, -1).max(axis=1) > 1e-12)[0]:
+                            pending[qi].append((int(k), j, Dall[k]))
+                swept = True
+            except (TypeError, ValueError, NotImplementedError, RuntimeError, AttributeError, IndexError):
+                g[:] = 0.0  # f is not batch-transparent (same requirement as vmap): one recording per nudge
+                pending = [[] for _ in base.queries]
+            for k in range(0 if not swept else theta.size, theta.size):
                 h = _H_PARAM * max(1.0, abs(flat[k]))
                 ap, am = list(args), list(args)
                 tp, tm = flat.copy(), flat.copy()
