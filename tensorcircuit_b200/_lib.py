@@ -36,7 +36,7 @@ def _load() -> ctypes.CDLL:
         except Exception as e:  # pragma: no cover
             raise ImportError(
                 "tensorcircuit_b200: %s is missing and could not be built (%s). "
-                "Run `python -m tensorcircuit_b200.build`; there is no CPU fallback." % (LIB_PATH, e)
+                "Run `python tensorcircuit_b200/build.py`; there is no CPU fallback." % (LIB_PATH, e)
             )
     lib = ctypes.CDLL(LIB_PATH)
     sig = {
