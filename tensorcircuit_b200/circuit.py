@@ -312,6 +312,42 @@ class Circuit:
         self._apply_qir(self, qir)
         return self
 
+    def prepend(self, c: "Circuit") -> "Circuit":
+        """abstractcircuit.py:1133-1146: ``c`` runs before the gates recorded so far."""
+        newc = type(self).from_qir(c.to_qir() + self.to_qir(), {"nqubits": self._nqubits, "inputs": self.inputs})
+        self.__dict__.update(newc.__dict__)
+        return self
+
+    def copy(self) -> "Circuit":
+        """abstractcircuit.py:1192-1195: a new circuit with the same record (and its own state)."""
+        return type(self).from_qir(self.to_qir(), {"nqubits": self._nqubits, "inputs": self.inputs})
+
+    def gate_count_by_condition(self, cond_func: Callable[[Dict[str, Any]], bool]) -> int:
+        """abstractcircuit.py:655-681"""
+        return sum(1 for d in self._qir if cond_func(d))
+
+    def _instruction(self, name: str, index: Any) -> None:
+        self._extra_qir.append({"index": index, "name": name, "gatef": name, "instruction": True, "pos": len(self._qir)})
+
+    def measure_instruction(self, *index: int) -> None:
+        """abstractcircuit.py:695-711: a flag for translators, no effect on the simulation."""
+        for ind in index:
+            self._instruction("measure", [ind])
+
+    def reset_instruction(self, *index: int) -> None:
+        """abstractcircuit.py:713-729"""
+        for ind in index:
+            self._instruction("reset", [ind])
+
+    def barrier_instruction(self, *index: Any) -> None:
+        """abstractcircuit.py:731-746"""
+        self._instruction("barrier", index)
+
+    def is_valid(self) -> bool:
+        """circuit.py:776-790 checks the wiring of the node graph; there is no graph here, the
+        record is valid by construction (arity and range are checked when a gate is applied)."""
+        return True
+
     def gate_count(self, gate_list: Optional[Union[str, Sequence[str]]] = None) -> int:
         if gate_list is None:
             return len(self._qir)
@@ -789,6 +825,8 @@ class Circuit:
             self.any(*index, unitary=BatchArray(sel), name="conditional")
         else:
             self.any(*index, unitary=mats[int(which)], name="conditional")
+
+    select_gate = conditional_gate
 
     def depolarizing2(self, index: int, *, px: float, py: float, pz: float, status: Optional[float] = None) -> float:
         """circuit.py:354-386: x / y / z / i chosen by status against px, px+py, px+py+pz."""

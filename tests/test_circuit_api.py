@@ -1062,3 +1062,31 @@ def test_value_and_grad_limits(eng):
     v, g = K.value_and_grad(lambda p: K.sum(p**2))(np.array([1.0, 2.0]))
     np.testing.assert_allclose(v, 5.0)
     np.testing.assert_allclose(g, [2.0, 4.0], atol=1e-7)
+
+
+def test_circuit_copy_prepend_instructions(eng):
+    # tests/test_circuit.py:1650-1655 (copy), abstractcircuit.py:1133-1146 (prepend), :655-746
+    c = tc.Circuit(2)
+    c.h(0)
+    c1 = c.copy()
+    c.rz(0, theta=0.1)
+    assert c1.gate_count() == 1 and c.gate_count() == 2
+    c2 = tc.Circuit(2)
+    c2.x(1)
+    c.prepend(c2)  # X(1) first, then H(0), rz(0)
+    assert [d["name"] for d in c.to_qir()] == ["x", "h", "rz"]
+    o = OracleCircuit(2)
+    o.x(1)
+    o.h(0)
+    o.rz(0, theta=0.1)
+    np.testing.assert_allclose(A(c.state()), o.state(), atol=1e-6)
+    assert c.gate_count_by_condition(lambda d: d["index"] == (0,)) == 2
+    c.measure_instruction(0, 1)
+    c.barrier_instruction(0, 1)
+    c.reset_instruction(1)
+    assert [d["name"] for d in c._extra_qir] == ["measure", "measure", "barrier", "reset"]
+    np.testing.assert_allclose(A(c.state()), o.state(), atol=1e-6)  # instructions do not touch the state
+    assert c.is_valid()
+    c.select_gate(1, [tc.gates.i(), tc.gates.x()], 0)
+    o.x(0)
+    np.testing.assert_allclose(A(c.state()), o.state(), atol=1e-6)
