@@ -1090,3 +1090,34 @@ def test_circuit_copy_prepend_instructions(eng):
     c.select_gate(1, [tc.gates.i(), tc.gates.x()], 0)
     o.x(0)
     np.testing.assert_allclose(A(c.state()), o.state(), atol=1e-6)
+
+
+def test_value_and_grad_has_aux_and_shared_parameter(eng):
+    """has_aux passes the auxiliary output through; one parameter feeding several gates (and a
+    non-linear loss) gets the sum of its gate derivatives."""
+    K = tc.backend
+
+    def f(t):
+        c = tc.Circuit(3)
+        for i in range(3):
+            c.ry(i, theta=t[0] * (i + 1))   # t[0] moves three gates
+        c.cnot(0, 1)
+        c.rzz(1, 2, theta=t[1] ** 2)         # non-linear use of t[1]
+        e = K.real(c.expectation_ps(z=[2]))
+        return (e - 0.3) ** 2, {"energy": e}  # non-linear host arithmetic + aux
+
+    def want(t):
+        o = OracleCircuit(3)
+        for i in range(3):
+            o.ry(i, theta=t[0] * (i + 1))
+        o.cnot(0, 1)
+        o.rzz(1, 2, theta=t[1] ** 2)
+        return (o.expectation_ps(z=[2]).real - 0.3) ** 2
+
+    t = np.array([0.4, 0.9])
+    (v, aux), g = K.value_and_grad(f, has_aux=True)(t)
+    np.testing.assert_allclose(v, want(t), atol=2e-6)
+    np.testing.assert_allclose(np.sqrt(v), abs(float(aux["energy"]) - 0.3), atol=2e-6)
+    h = 1e-6
+    fd = [(want(t + h * np.eye(2)[k]) - want(t - h * np.eye(2)[k])) / (2 * h) for k in range(2)]
+    np.testing.assert_allclose(g, fd, atol=3e-5)
