@@ -13,6 +13,9 @@ from . import _lib  # noqa: F401  (fails loudly when the CUDA library is missing
 from .cons import (  # noqa: F401
     contractor,
     dtypestr,
+    get_backend,
+    get_contractor,
+    get_dtype,
     npdtype,
     rdtypestr,
     runtime_backend,
@@ -37,6 +40,17 @@ from . import engine  # noqa: F401
 from . import parallel  # noqa: F401
 
 backend = _backend_module.get_backend()
+
+
+def about() -> None:
+    """tensorcircuit/about.py: versions of what the engine runs on"""
+    import platform
+
+    import numpy
+    import torch
+
+    print("tensorcircuit_b200 %s  (%s)" % (__version__, _lib.version()))
+    print("python %s, numpy %s, torch %s, cuda available: %s" % (platform.python_version(), numpy.__version__, torch.__version__, torch.cuda.is_available()))
 
 
 def __getattr__(name):  # live view of the mutable globals (set_dtype rebinds them in cons)

@@ -76,7 +76,18 @@ def set_dtype(dtype: Optional[str] = None, set_global: bool = True) -> Any:
     return dtype, rdtype
 
 
-get_dtype = set_dtype
+def get_dtype(dtype: Optional[str] = None) -> Any:
+    """cons.py:180: the (complex, real) dtype names without touching the global setting"""
+    return set_dtype(dtype, set_global=False)
+
+
+def get_backend(backend_name: Optional[str] = None) -> Any:
+    """backends/backend_factory.py:38-59: every name resolves to the one engine backend"""
+    return set_backend(backend_name, set_global=False)
+
+
+def get_contractor(method: Optional[str] = None, *args: Any, **kws: Any) -> Any:
+    return None
 
 
 def set_distributed(flag: bool = True) -> bool:
