@@ -253,7 +253,7 @@ def run_ours(args):
 
     # ---- device-resident leg -------------------------------------------------------------
     c0 = recipes.build(tc.Circuit(n), ops)
-    blocks = fuse(c0._ops, n, kmax=tc.Circuit.fusion_kmax)
+    blocks = c0._fuse(c0._ops, n)
     khist = {}
     for b in blocks:
         khist[len(b.bits)] = khist.get(len(b.bits), 0) + 1

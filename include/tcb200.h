@@ -40,6 +40,7 @@ extern "C" {
 #define TCB200_ERR_ARG (-1)         /* bad argument (null pointer, bit out of range, duplicate bit ...) */
 #define TCB200_ERR_UNSUPPORTED (-2) /* e.g. k > TCB200_MAX_K */
 #define TCB200_ERR_WORKSPACE (-3)   /* workspace too small */
+#define TCB200_ERR_CAPACITY (-4)    /* a gate pass holds more rounds / matrices than one launch carries: split it */
 #define TCB200_ERR_CUDA (-1000)     /* -(1000 + cudaError_t) */
 
 #define TCB200_MAX_K 5          /* widest dense fused block (2^5 x 2^5) */
@@ -47,6 +48,7 @@ extern "C" {
 #define TCB200_MAX_PASS_OPS 16  /* fused blocks executed by one staged pass */
 #define TCB200_MAX_PASS_K 4     /* widest block inside a staged multi-block pass */
 #define TCB200_MAX_TERMS 8      /* Pauli strings per expectation launch */
+#define TCB200_MAX_GATE_PASS_OPS 256 /* gates handed to one structure-aware gate pass */
 
 /* Library / build identification: "tcb200 <version> sm_100a". */
 const char* tcb200_version(void);
@@ -156,6 +158,39 @@ int tcb200_apply_rpass_host(void* state, int nbits, int dtype, int nrt, const in
                             const int* rt_bits, const int* rt_nsub, const int* sub_k,
                             const int* sub_bits, const double* sub_mats, int n_hi,
                             const int* tile_hi, int64_t batch, void* stream);
+
+/*
+ * Structure-aware staged pass ("gate pass"): the production kernel behind Circuit gate application.
+ * Same tile and same argument meaning as tcb200_apply_pass_host -- `nops` gates in program order,
+ * every bit inside the tile {low bits} U {tile_hi} -- but the library classifies each matrix
+ * (exact zeros) and treats the three classes of tensorcircuit/gates.py differently:
+ *   - permutation matrices of an affine bit map (x, cnot, swap, cx chains; any monomial gate on
+ *     <= 2 bits such as y, cy, iswap after its phases are split off): absorbed into the tile's
+ *     GF(2)-affine index map on the host -- no device instruction, undone by the write-back;
+ *   - diagonal gates on <= 4 bits (z, s, t, rz, phase, cz, cphase, rzz, crz ...): one 16-entry
+ *     table multiply, consecutive ones merged into one table;
+ *   - everything else on <= 3 bits: dense 2x2 / 4x4 / 8x8 in registers.
+ * Gates are scheduled into rounds: per round a thread loads 16 amplitudes (4 tile bits) once,
+ * applies every ready gate that lives on those bits (dependencies respected, gates on disjoint
+ * bits reordered freely), and stores them once.  Matrices travel in the kernel-parameter
+ * constant bank and reach the FMAs as uniform-register operands.
+ *
+ *   ops_k[nops] (1..4), ops_bits[sum k] ascending, ops_mats HOST complex128 [sum 4^k]
+ *   info8       optional HOST double[8]: rounds, gates absorbed into the index map, diagonal gates,
+ *               dense gates, rounds with shared-memory bank conflicts, rounds using 16-byte
+ *               accesses, real FMAs per amplitude, parameter-bank elements used
+ * Returns TCB200_ERR_CAPACITY when the gates need more than one launch can carry (48 rounds,
+ * 1280 matrix elements): the caller splits the run (same tile) and calls again.
+ * TCB200_ERR_UNSUPPORTED: dense gate wider than 3 bits, diagonal wider than 4, state below 4 bits.
+ * Replaces tensorcircuit/cons.py:605-623 for the run, as tcb200_apply_pass_host does.
+ */
+int tcb200_apply_gate_pass(void* state, int nbits, int dtype, int nops, const int* ops_k,
+                           const int* ops_bits, const double* ops_mats, int n_hi,
+                           const int* tile_hi, int64_t batch, double* info8, void* stream);
+
+/* Host-only dry run of the gate-pass scheduler (no device work): fills info8 as above. */
+int tcb200_gate_pass_info(int nbits, int dtype, int nops, const int* ops_k, const int* ops_bits,
+                          const double* ops_mats, int n_hi, const int* tile_hi, double* info8);
 
 /* Geometry the pass planner needs: log2 of the tile size (amplitudes) used by
  * tcb200_apply_pass / tcb200_apply_pass_host / tcb200_apply_rpass_host for `dtype`. */

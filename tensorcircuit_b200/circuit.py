@@ -19,7 +19,7 @@ import numpy as np
 
 from . import cons, gates
 from .batching import BatchArray, batch_of, is_batched
-from .fusion import GateOp, fuse
+from .fusion import GateOp, fuse, fuse_structured
 from .gates import Gate
 from .quantum import correlation_from_samples, ps2xyz, sample2all, sample_int2bin
 
@@ -111,6 +111,14 @@ class Circuit:
     # passes k=3 is the widest block that stays HBM-bound (measured).
     fusion_kmax = 2
     use_passes = True
+    # structure-aware fusion (fusion.fuse_structured): diagonal / permutation / dense classes
+    # kept apart so that the gate pass can treat them differently; dense-only fusion otherwise
+    structured_fusion = True
+
+    def _fuse(self, ops: Sequence[GateOp], ntot: int) -> List[Any]:
+        if self.structured_fusion and self.use_passes:
+            return fuse_structured(ops, ntot, kmax=self.fusion_kmax)
+        return fuse(ops, ntot, kmax=self.fusion_kmax)
 
     def __init__(
         self,
@@ -392,7 +400,7 @@ class Circuit:
                 _STATE_HOOK(self, st)
         if self._applied < len(self._ops):
             pending = self._ops[self._applied :]
-            blocks = fuse(pending, self._ntot, kmax=self.fusion_kmax)
+            blocks = self._fuse(pending, self._ntot)
             if self.use_passes and hasattr(self._state, "apply_planned"):
                 self._state.apply_planned(blocks)
             else:
@@ -611,7 +619,7 @@ class Circuit:
         for q, e in enumerate(readout_error):
             p0, p1 = float(np.real(e[0])), float(np.real(e[1]))
             ops.append(GateOp((q,), np.array([[p0, 1 - p1], [1 - p0, p1]], dtype=np.complex128), "readout"))
-        r.apply_planned(fuse(ops, self._nqubits, kmax=self.fusion_kmax)) if hasattr(r, "apply_planned") else r.apply_blocks(fuse(ops, self._nqubits, kmax=self.fusion_kmax))
+        r.apply_planned(self._fuse(ops, self._nqubits)) if hasattr(r, "apply_planned") else r.apply_blocks(self._fuse(ops, self._nqubits))
         r.sqrt_real_inplace()
         return r
 

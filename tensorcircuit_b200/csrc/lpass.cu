@@ -1,0 +1,632 @@
+// Structure-aware staged pass: host-side gate classification, round scheduling and index-map
+// tracking, the kernel, and the C ABI entry points (tcb200_apply_gate_pass / tcb200_gate_pass_info).
+//
+// Replaces, for a run of gates whose bits fit one tile, the per-gate tn.contract_between ->
+// tensordot of tensorcircuit/cons.py:605-623 and, for the structured gates of
+// tensorcircuit/gates.py:46-127, 826-865 (cnot / swap / x / cz / rzz / rz ...), the dense
+// multiplication by a table multiply (diagonal) or by nothing at all (affine permutations).
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <complex>
+#include <vector>
+
+#include "lpass.cuh"
+
+namespace tcb {
+
+typedef std::complex<double> cd;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// classified gates on tile-local logical bits
+// ------------------------------------------------------------------------------------------------
+enum { GK_DENSE = 0, GK_DIAG = 1, GK_LIN = 2 };
+
+struct GOp {
+    int kind;
+    int k;
+    int lb[4];          // logical tile bit of matrix index bit j
+    std::vector<cd> m;  // dense: D*D row-major; diag: D
+    int linv[4];        // lin: L^{-1} e_i as k-bit masks (the inverse map is y -> L^{-1} y ^ cinv)
+    int cinv;
+};
+
+// split one input gate into classified ops (appended to `out`); < 0 on error
+int classify(int k, const int* lb, const double* mat, std::vector<GOp>& out) {
+    const int D = 1 << k;
+    auto M = [&](int i, int j) { return cd(mat[2 * (i * D + j)], mat[2 * (i * D + j) + 1]); };
+    // monomial?  (exact zeros: gate matrices are built analytically on the host)
+    std::vector<int> perm(D, -1);
+    bool mono = true;
+    std::vector<char> rowused(D, 0);
+    for (int j = 0; j < D && mono; ++j) {
+        int cnt = 0, at = -1;
+        for (int i = 0; i < D; ++i)
+            if (M(i, j) != cd(0, 0)) {
+                ++cnt;
+                at = i;
+            }
+        if (cnt != 1 || rowused[at]) mono = false;
+        else {
+            perm[j] = at;
+            rowused[at] = 1;
+        }
+    }
+    if (mono) {
+        bool ident = true, allone = true;
+        for (int j = 0; j < D; ++j) {
+            if (perm[j] != j) ident = false;
+            if (M(perm[j], j) != cd(1, 0)) allone = false;
+        }
+        bool affine = false;
+        int lcol[4] = {0, 0, 0, 0};
+        const int c = perm[0];
+        if (!ident && k <= 3) {
+            affine = true;
+            for (int i = 0; i < k; ++i) lcol[i] = perm[1 << i] ^ c;
+            for (int j = 0; j < D && affine; ++j) {
+                int img = c;
+                for (int i = 0; i < k; ++i)
+                    if ((j >> i) & 1) img ^= lcol[i];
+                if (img != perm[j]) affine = false;
+            }
+        }
+        if (ident || affine) {
+            if (!allone) {
+                if (k > 4) return fail(TCB200_ERR_UNSUPPORTED, "diagonal gate of %d bits inside a gate pass (max 4)", k);
+                GOp g;
+                g.kind = GK_DIAG;
+                g.k = k;
+                for (int i = 0; i < k; ++i) g.lb[i] = lb[i];
+                g.m.resize(D);
+                for (int j = 0; j < D; ++j) g.m[j] = M(perm[j], j);
+                out.push_back(g);
+            }
+            if (!ident) {
+                GOp g;
+                g.kind = GK_LIN;
+                g.k = k;
+                for (int i = 0; i < k; ++i) g.lb[i] = lb[i];
+                std::vector<int> inv(D);
+                for (int j = 0; j < D; ++j) inv[perm[j]] = j;
+                g.cinv = inv[0];
+                for (int i = 0; i < k; ++i) g.linv[i] = inv[1 << i] ^ g.cinv;
+                out.push_back(g);
+            }
+            return 0;
+        }
+    }
+    if (k > 3) return fail(TCB200_ERR_UNSUPPORTED, "dense gate of %d bits inside a gate pass (max 3)", k);
+    GOp g;
+    g.kind = GK_DENSE;
+    g.k = k;
+    for (int i = 0; i < k; ++i) g.lb[i] = lb[i];
+    g.m.resize(D * D);
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) g.m[i * D + j] = M(i, j);
+    out.push_back(g);
+    return 0;
+}
+
+// rank of the vectors v[0..n) restricted to `mask` (GF(2))
+int gf2_rank(const uint32_t* v, int n, uint32_t mask) {
+    uint32_t basis[32];
+    int r = 0;
+    for (int i = 0; i < n; ++i) {
+        uint32_t x = v[i] & mask;
+        for (int j = 0; j < r; ++j)
+            if ((x ^ basis[j]) < x) x ^= basis[j];
+        if (x) {
+            basis[r++] = x;
+            // keep the basis reduced enough for the (x ^ b) < x test: sort descending
+            std::sort(basis, basis + r, [](uint32_t a, uint32_t b) { return a > b; });
+        }
+    }
+    return r;
+}
+
+template <typename Real>
+struct LPassParams {
+    typename CT<Real>::type* state;
+    TileGeom g;
+    int tb;      // log2(threads working on groups)
+    int stb;     // log2(blockDim.x)
+    int ngb;     // group-index bits: T - LP_RB
+    int nrounds;
+    LOut out;
+    LRound r[LP_MAX_ROUNDS];
+    ME<Real> m[LP_MAT_ELEMS];
+};
+
+template <typename Real>
+void put_elem(ME<Real>& e, cd z);
+template <>
+void put_elem<float>(ME<float>& e, cd z) {
+    e.re = (float)z.real();
+    e.pad = 0.f;
+    e.im0 = e.im1 = (float)z.imag();
+}
+template <>
+void put_elem<double>(ME<double>& e, cd z) {
+    e.re = z.real();
+    e.im0 = z.imag();
+}
+
+// ------------------------------------------------------------------------------------------------
+// round scheduler
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+struct Scheduler {
+    static constexpr int AMP = (int)sizeof(typename CT<Real>::type);
+    static constexpr bool C64 = AMP == 8;
+    int T = 0;
+    uint32_t col[LP_MAX_T];
+    uint32_t d = 0;
+    std::vector<GOp> ops;
+    std::vector<std::vector<int>> preds;
+    std::vector<char> done;
+    LPassParams<Real>* q = nullptr;
+    LPassInfo info;
+    int nmat = 0;
+
+    void init_layout() {
+        for (int t = 0; t < T; ++t) {
+            const uint32_t e = 1u << t;
+            col[t] = (C64 ? swz_amp<2>(e) : swz_amp<1>(e)) * (uint32_t)AMP;
+        }
+        d = 0;
+    }
+
+    void build_deps() {
+        const int n = (int)ops.size();
+        preds.assign(n, {});
+        int last[LP_MAX_T];
+        for (int t = 0; t < LP_MAX_T; ++t) last[t] = -1;
+        for (int i = 0; i < n; ++i) {
+            for (int j = 0; j < ops[i].k; ++j) {
+                const int p = last[ops[i].lb[j]];
+                if (p >= 0 && std::find(preds[i].begin(), preds[i].end(), p) == preds[i].end()) preds[i].push_back(p);
+            }
+            for (int j = 0; j < ops[i].k; ++j) last[ops[i].lb[j]] = i;
+        }
+        done.assign(n, 0);
+    }
+
+    bool ready(int i) const {
+        if (done[i]) return false;
+        for (int p : preds[i])
+            if (!done[p]) return false;
+        return true;
+    }
+
+    void apply_lin(const GOp& g) {
+        uint32_t nc[4];
+        for (int i = 0; i < g.k; ++i) {
+            uint32_t c = 0;
+            for (int s = 0; s < g.k; ++s)
+                if ((g.linv[i] >> s) & 1) c ^= col[g.lb[s]];
+            nc[i] = c;
+        }
+        for (int s = 0; s < g.k; ++s)
+            if ((g.cinv >> s) & 1) d ^= col[g.lb[s]];
+        for (int i = 0; i < g.k; ++i) col[g.lb[i]] = nc[i];
+    }
+
+    // bank-select bits of a byte offset for the access width in use
+    static uint32_t bank_mask(bool wide) { return wide ? 0x70u : 0x78u; }
+
+    bool vec_possible(const int* R, int nr) const {
+        if (!C64) return false;
+        bool has0 = false;
+        for (int i = 0; i < nr; ++i)
+            if (R[i] == 0) has0 = true;
+        if (!has0 || col[0] != 8u || (d & 8u)) return false;
+        for (int t = 1; t < T; ++t)
+            if (col[t] & 8u) return false;
+        return true;
+    }
+
+    int emit_round(std::vector<int>& R, const std::vector<int>& members) {
+        if (q->nrounds >= LP_MAX_ROUNDS) return fail(TCB200_ERR_CAPACITY, "gate pass needs more than %d rounds", LP_MAX_ROUNDS);
+        // ---- filler bits ----
+        bool inR[LP_MAX_T] = {false};
+        for (int b : R) inR[b] = true;
+        if ((int)R.size() < LP_RB && C64 && !inR[0]) {
+            // logical bit 0 as a filler makes 16-byte accesses possible when its column is pure
+            std::vector<int> R2 = R;
+            R2.push_back(0);
+            if (vec_possible(R2.data(), (int)R2.size())) {
+                R.push_back(0);
+                inR[0] = true;
+            }
+        }
+        while ((int)R.size() < LP_RB) {
+            const bool wide = !C64 || vec_possible(R.data(), (int)R.size());
+            const uint32_t mask = bank_mask(wide);
+            int best = -1, best_rank = -1;
+            for (int t = T - 1; t >= 0; --t) {
+                if (inR[t]) continue;
+                uint32_t gc[LP_MAX_T];
+                int ng = 0;
+                for (int u = 0; u < T; ++u)
+                    if (!inR[u] && u != t) gc[ng++] = col[u];
+                const int rk = gf2_rank(gc, ng, mask);
+                if (rk > best_rank) {
+                    best_rank = rk;
+                    best = t;
+                }
+            }
+            R.push_back(best);
+            inR[best] = true;
+        }
+        std::sort(R.begin(), R.end());
+        const bool vec = vec_possible(R.data(), LP_RB);
+        const bool wide = !C64 || vec;
+        LRound& r = q->r[q->nrounds++];
+        memset(&r, 0, sizeof(r));
+        r.d = d;
+        for (int p = 0; p < LP_RB; ++p) r.rcol[p] = col[R[p]];
+        // ---- lane order of the group bits: independent bank columns first ----
+        const int ngb = T - LP_RB;
+        int gl[LP_MAX_T];
+        int ng = 0;
+        for (int t = 0; t < T; ++t)
+            if (!inR[t]) gl[ng++] = t;
+        const uint32_t mask = bank_mask(wide);
+        const int need = wide ? 3 : 4;
+        uint32_t chosen[LP_MAX_T];
+        int order[LP_MAX_T];
+        bool used[LP_MAX_T] = {false};
+        int no = 0;
+        for (int i = 0; i < ng && no < need; ++i) {
+            chosen[no] = col[gl[i]];
+            if (gf2_rank(chosen, no + 1, mask) == no + 1) {
+                order[no++] = gl[i];
+                used[i] = true;
+            }
+        }
+        if (no < need && ngb >= need) info.conflicts++;
+        for (int i = 0; i < ng; ++i)
+            if (!used[i]) order[no++] = gl[i];
+        for (int i = 0; i < ngb; ++i) r.gcol[i] = col[order[i]];
+        if (vec) info.vec_rounds++;
+        // ---- micro-ops ----
+        int nc = 0;
+        int last_dg = -1;  // matrix offset of a diagonal table the next diagonal op can merge into
+        cd dgtab[16];
+        for (int oi : members) {
+            const GOp& g = ops[oi];
+            int pos[4];
+            for (int j = 0; j < g.k; ++j) pos[j] = (int)(std::find(R.begin(), R.end(), g.lb[j]) - R.begin());
+            if (g.kind == GK_DIAG) {
+                cd tab[16];
+                for (int x = 0; x < 16; ++x) {
+                    int idx = 0;
+                    for (int j = 0; j < g.k; ++j) idx |= ((x >> pos[j]) & 1) << j;
+                    tab[x] = g.m[idx];
+                }
+                if (last_dg >= 0) {  // consecutive diagonal ops: one table (product kept in double)
+                    for (int x = 0; x < 16; ++x) {
+                        dgtab[x] *= tab[x];
+                        put_elem<Real>(q->m[last_dg + x], dgtab[x]);
+                    }
+                    continue;
+                }
+                if (nmat + 16 > LP_MAT_ELEMS) return fail(TCB200_ERR_CAPACITY, "gate pass matrices exceed the parameter bank");
+                if (nc >= LP_MAX_CODES) return fail(TCB200_ERR_CAPACITY, "more than %d micro-ops in a round", LP_MAX_CODES);
+                for (int x = 0; x < 16; ++x) {
+                    dgtab[x] = tab[x];
+                    put_elem<Real>(q->m[nmat + x], tab[x]);
+                }
+                r.code[nc++] = LOP_DG | ((uint32_t)nmat << 8);
+                last_dg = nmat;
+                nmat += 16;
+                info.fma_per_amp += 4;
+                continue;
+            }
+            last_dg = -1;
+            // dense: sort the positions ascending and permute the matrix index bits to match
+            const int k = g.k, D = 1 << k;
+            int srt[4];
+            for (int j = 0; j < k; ++j) srt[j] = j;
+            std::sort(srt, srt + k, [&](int a, int b) { return pos[a] < pos[b]; });
+            auto remap = [&](int i) {  // index in sorted-position order -> index in the op's own order
+                int o = 0;
+                for (int s = 0; s < k; ++s)
+                    if ((i >> s) & 1) o |= 1 << srt[s];
+                return o;
+            };
+            if (nmat + D * D > LP_MAT_ELEMS) return fail(TCB200_ERR_CAPACITY, "gate pass matrices exceed the parameter bank");
+            if (nc >= LP_MAX_CODES) return fail(TCB200_ERR_CAPACITY, "more than %d micro-ops in a round", LP_MAX_CODES);
+            for (int i = 0; i < D; ++i)
+                for (int j = 0; j < D; ++j) put_elem<Real>(q->m[nmat + i * D + j], g.m[remap(i) * D + remap(j)]);
+            uint32_t opc = 0;
+            const int p0 = pos[srt[0]], p1 = k > 1 ? pos[srt[1]] : 0, p2 = k > 2 ? pos[srt[2]] : 0;
+            if (k == 1) opc = LOP_G1 + (uint32_t)p0;
+            else if (k == 2) {
+                static const int pair_index[4][4] = {{-1, 0, 1, 2}, {-1, -1, 3, 4}, {-1, -1, -1, 5}, {-1, -1, -1, -1}};
+                opc = LOP_G2 + (uint32_t)pair_index[p0][p1];
+            } else {
+                const int e = 6 - p0 - p1 - p2;  // the position left out
+                opc = LOP_G3 + (uint32_t)e;
+            }
+            r.code[nc++] = opc | ((uint32_t)nmat << 8);
+            nmat += D * D;
+            info.fma_per_amp += 4.0 * D;
+        }
+        r.ncodes = (uint32_t)nc | (vec ? 0x100u : 0u);
+        info.rounds++;
+        return 0;
+    }
+
+    int run() {
+        const int n = (int)ops.size();
+        int remaining = n;
+        while (remaining > 0) {
+            // index-map ops that are ready cost nothing: apply them all
+            bool again = true;
+            while (again) {
+                again = false;
+                for (int i = 0; i < n; ++i)
+                    if (ops[i].kind == GK_LIN && ready(i)) {
+                        apply_lin(ops[i]);
+                        done[i] = 1;
+                        --remaining;
+                        info.nlin++;
+                        again = true;
+                    }
+            }
+            if (remaining == 0) break;
+            // open a round with the first ready op, then add ready ops while <= LP_RB bits are touched
+            std::vector<int> R, members;
+            int budget = LP_MAX_CODES;
+            for (;;) {
+                int best = -1, best_new = 99;
+                for (int i = 0; i < n; ++i) {
+                    if (ops[i].kind == GK_LIN || !ready(i)) continue;
+                    int nnew = 0;
+                    for (int j = 0; j < ops[i].k; ++j)
+                        if (std::find(R.begin(), R.end(), ops[i].lb[j]) == R.end()) ++nnew;
+                    if ((int)R.size() + nnew > LP_RB) continue;
+                    if (nnew < best_new) {
+                        best_new = nnew;
+                        best = i;
+                        if (nnew == 0) break;
+                    }
+                }
+                if (best < 0 || budget == 0) break;
+                for (int j = 0; j < ops[best].k; ++j)
+                    if (std::find(R.begin(), R.end(), ops[best].lb[j]) == R.end()) R.push_back(ops[best].lb[j]);
+                members.push_back(best);
+                done[best] = 1;
+                --remaining;
+                --budget;
+                if (ops[best].kind == GK_DIAG) info.ndiag++;
+                else info.ndense++;
+            }
+            if (members.empty()) return fail(TCB200_ERR_ARG, "gate pass scheduler made no progress");
+            const int rc = emit_round(R, members);
+            if (rc) return rc;
+        }
+        q->out.d = d;
+        for (int t = 0; t < T; ++t) q->out.col[t] = col[t];
+        bool vec = C64 && col[0] == 8u && !(d & 8u);
+        for (int t = 1; t < T && vec; ++t)
+            if (col[t] & 8u) vec = false;
+        q->out.vec = vec ? 1u : 0u;
+        info.mat_elems = nmat;
+        return 0;
+    }
+};
+
+// parameter block of one gate pass; 0 on success
+template <typename Real>
+int fill_lpass(LPassParams<Real>& q, LPassInfo& info, void* state, int nbits, int nops, const int* ops_k, const int* ops_bits,
+               const double* mats, int n_hi, const int* tile_hi) {
+    using C = typename CT<Real>::type;
+    q.state = static_cast<C*>(state);
+    const int tile_bits = pass_tile_bits(sizeof(Real) == 4 ? TCB200_C64 : TCB200_C128);
+    if (tile_bits > LP_MAX_T) return fail(TCB200_ERR_UNSUPPORTED, "pass tile of 2^%d amplitudes exceeds the gate-pass limit 2^%d", tile_bits, LP_MAX_T);
+    int rc = make_geom_hi(nbits, tile_bits, nbits <= tile_bits ? 0 : n_hi, tile_hi, &q.g);
+    if (rc) return rc;
+    if (q.g.T < LP_RB) return fail(TCB200_ERR_UNSUPPORTED, "gate pass needs a state of at least %d bits", LP_RB);
+    Scheduler<Real> s;
+    s.T = q.g.T;
+    s.q = &q;
+    memset(&s.info, 0, sizeof(s.info));
+    s.init_layout();
+    const int* b = ops_bits;
+    const double* mp = mats;
+    for (int o = 0; o < nops; ++o) {
+        const int k = ops_k[o];
+        if (k < 1 || k > 4) return fail(TCB200_ERR_UNSUPPORTED, "gate of %d bits inside a gate pass", k);
+        int lb[4];
+        for (int i = 0; i < k; ++i) {
+            if (b[i] < 0 || b[i] >= nbits) return fail(TCB200_ERR_ARG, "bit %d out of range", b[i]);
+            if (i > 0 && b[i] <= b[i - 1]) return fail(TCB200_ERR_ARG, "bits must be strictly ascending");
+            lb[i] = local_bit(q.g, b[i]);
+            if (lb[i] < 0) return fail(TCB200_ERR_ARG, "bit %d is not inside the tile", b[i]);
+        }
+        rc = classify(k, lb, mp, s.ops);
+        if (rc) return rc;
+        b += k;
+        mp += 2ll << (2 * k);
+    }
+    q.nrounds = 0;
+    q.ngb = q.g.T - LP_RB;
+    q.tb = q.ngb < 8 ? q.ngb : 8;
+    // staging threads: one 16-byte unit per lane per iteration, at least a warp
+    const int units_log = q.g.T - (sizeof(C) == 8 ? 1 : 0);
+    q.stb = q.tb;
+    if (q.stb < 5) q.stb = 5;
+    if (q.stb > units_log && units_log >= 5) q.stb = units_log;
+    s.build_deps();
+    rc = s.run();
+    if (rc) return rc;
+    info = s.info;
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(256, sizeof(Real) == 4 ? 3 : 2) lpass_kernel(const __grid_constant__ LPassParams<Real> p) {
+    using C = typename CT<Real>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    C* tile = reinterpret_cast<C*>(smem_raw);
+    __shared__ uint64_t rowoff[256];
+
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    if (tid < (1 << p.g.h)) rowoff[tid] = row_offset(p.g, tid);
+    C* vec = p.state + ((uint64_t)blockIdx.y << p.g.n);
+    const uint64_t base = tile_base(p.g, blockIdx.x);
+    __syncthreads();
+    stage_in<C, SWZ_SW>(p.g, vec, base, tile, rowoff, tid, nthr);
+    cp_async_wait_all();
+    __syncthreads();
+    const bool worker = (tid >> p.tb) == 0;
+    for (int r = 0; r < p.nrounds; ++r) {
+        if (worker) lround_thread<C, Real>(smem_raw, p.r[r], p.m, (uint32_t)tid, p.tb, p.ngb);
+        __syncthreads();
+    }
+    lstage_out_thread<C>(p.g, vec, base, smem_raw, rowoff, p.out, tid, nthr, p.stb);
+}
+
+template <typename Real>
+static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, const int* ops_bits, const double* mats, int n_hi,
+                        const int* tile_hi, int64_t batch, cudaStream_t st, LPassInfo* info_out) {
+    using C = typename CT<Real>::type;
+    static thread_local LPassParams<Real>* tp = nullptr;
+    if (!tp) tp = new LPassParams<Real>();
+    LPassParams<Real>& q = *tp;
+    LPassInfo info;
+    int rc = fill_lpass<Real>(q, info, state, nbits, nops, ops_k, ops_bits, mats, n_hi, tile_hi);
+    if (rc) return rc;
+    if (info_out) *info_out = info;
+    if (!state) return 0;  // dry run (tcb200_gate_pass_info)
+    const uint64_t ntiles = 1ull << (nbits - q.g.T);
+    if (ntiles > 0x7fffffffull) return fail(TCB200_ERR_UNSUPPORTED, "state too large for one grid");
+    if (batch < 1 || batch > 65535) return fail(TCB200_ERR_ARG, "batch=%lld out of range", (long long)batch);
+    size_t smem = (size_t)sizeof(C) << q.g.T;
+    if (smem < 16) smem = 16;
+    static bool attr = false;
+    if (!attr) {
+        TCB_CUDA(cudaFuncSetAttribute(lpass_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        attr = true;
+    }
+    dim3 grid((unsigned)ntiles, (unsigned)batch);
+    dim3 block(1u << q.stb);
+    lpass_kernel<Real><<<grid, block, smem, st>>>(q);
+    TCB_LAUNCH_CHECK("lpass_kernel");
+    return 0;
+}
+
+#ifdef TCB200_EMU
+// tests/emu only: the same parameter block and the same __host__ __device__ bodies on the CPU
+template <typename Real>
+static int emu_lpass(void* state, int nbits, int nops, const int* ops_k, const int* ops_bits, const double* mats, int n_hi,
+                     const int* tile_hi, LPassInfo* info_out) {
+    using C = typename CT<Real>::type;
+    LPassParams<Real>* q = new LPassParams<Real>();
+    LPassInfo info;
+    int rc = fill_lpass<Real>(*q, info, state, nbits, nops, ops_k, ops_bits, mats, n_hi, tile_hi);
+    if (rc) {
+        delete q;
+        return rc;
+    }
+    if (info_out) *info_out = info;
+    const int nthr = 1 << q->stb;
+    const size_t bytes = (size_t)sizeof(C) << q->g.T;
+    unsigned char* tile = static_cast<unsigned char*>(aligned_alloc(128, bytes < 128 ? 128 : bytes));
+    uint64_t rowoff[256];
+    for (int r = 0; r < (1 << q->g.h); ++r) rowoff[r] = row_offset(q->g, r);
+    C* vec = static_cast<C*>(state);
+    const uint64_t ntiles = 1ull << (nbits - q->g.T);
+    for (uint64_t t = 0; t < ntiles; ++t) {
+        const uint64_t base = tile_base(q->g, t);
+        for (int tid = 0; tid < nthr; ++tid) stage_in<C, SWZ_SW>(q->g, vec, base, reinterpret_cast<C*>(tile), rowoff, tid, nthr);
+        for (int r = 0; r < q->nrounds; ++r)
+            for (int tid = 0; tid < (1 << q->tb); ++tid) lround_thread<C, Real>(tile, q->r[r], q->m, (uint32_t)tid, q->tb, q->ngb);
+        for (int tid = 0; tid < nthr; ++tid) lstage_out_thread<C>(q->g, vec, base, tile, rowoff, q->out, tid, nthr, q->stb);
+    }
+    free(tile);
+    delete q;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int emu_apply_gate_pass(void* state, int nbits, int dtype, int nops, const int* ops_k,
+                                                                           const int* ops_bits, const double* ops_mats, int n_hi,
+                                                                           const int* tile_hi, double* info8) {
+    LPassInfo info;
+    memset(&info, 0, sizeof(info));
+    int rc;
+    if (dtype == TCB200_C64) rc = emu_lpass<float>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, &info);
+    else rc = emu_lpass<double>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, &info);
+    if (info8) {
+        info8[0] = info.rounds; info8[1] = info.nlin; info8[2] = info.ndiag; info8[3] = info.ndense;
+        info8[4] = info.conflicts; info8[5] = info.vec_rounds; info8[6] = info.fma_per_amp; info8[7] = info.mat_elems;
+    }
+    return rc;
+}
+#endif
+
+}  // namespace tcb
+
+using namespace tcb;
+
+static int gate_pass_args(int nbits, int dtype, int nops, const int* ops_k, const int* ops_bits, const double* ops_mats) {
+    if (!ops_k || !ops_bits || !ops_mats) return fail(TCB200_ERR_ARG, "NULL argument");
+    if (dtype != TCB200_C64 && dtype != TCB200_C128) return fail(TCB200_ERR_ARG, "bad dtype %d", dtype);
+    if (nops < 1 || nops > TCB200_MAX_GATE_PASS_OPS) return fail(TCB200_ERR_ARG, "nops=%d out of range", nops);
+    if (nbits < 1 || nbits > 40) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
+    return 0;
+}
+
+static void info_to_array(const LPassInfo& info, double* info8) {
+    if (!info8) return;
+    info8[0] = info.rounds;
+    info8[1] = info.nlin;
+    info8[2] = info.ndiag;
+    info8[3] = info.ndense;
+    info8[4] = info.conflicts;
+    info8[5] = info.vec_rounds;
+    info8[6] = info.fma_per_amp;
+    info8[7] = info.mat_elems;
+}
+
+extern "C" {
+
+int tcb200_apply_gate_pass(void* state, int nbits, int dtype, int nops, const int* ops_k, const int* ops_bits,
+                           const double* ops_mats, int n_hi, const int* tile_hi, int64_t batch, double* info8, void* stream) {
+    if (!state) return fail(TCB200_ERR_ARG, "state is NULL");
+    int rc = gate_pass_args(nbits, dtype, nops, ops_k, ops_bits, ops_mats);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LPassInfo info;
+    memset(&info, 0, sizeof(info));
+    if (dtype == TCB200_C64) rc = launch_lpass<float>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, batch, st, &info);
+    else rc = launch_lpass<double>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, batch, st, &info);
+    if (rc == 0) info_to_array(info, info8);
+    return rc;
+}
+
+int tcb200_gate_pass_info(int nbits, int dtype, int nops, const int* ops_k, const int* ops_bits, const double* ops_mats,
+                          int n_hi, const int* tile_hi, double* info8) {
+    int rc = gate_pass_args(nbits, dtype, nops, ops_k, ops_bits, ops_mats);
+    if (rc) return rc;
+    LPassInfo info;
+    memset(&info, 0, sizeof(info));
+    if (dtype == TCB200_C64) rc = launch_lpass<float>(nullptr, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, 1, nullptr, &info);
+    else rc = launch_lpass<double>(nullptr, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, 1, nullptr, &info);
+    if (rc == 0) info_to_array(info, info8);
+    return rc;
+}
+
+}  // extern "C"

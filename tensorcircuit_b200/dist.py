@@ -29,7 +29,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .fusion import Block
+from .fusion import Block, matrix_kind
 
 _SWAP = np.eye(4, dtype=np.complex128)[[0, 2, 1, 3]]
 
@@ -149,13 +149,14 @@ class DistState:
         order = list(np.argsort(pb))
         m = permute_matrix_bits(m, order)
         bits = tuple(sorted(pb))
-        return Block(qubits=tuple(self.nloc - 1 - b for b in bits), bits=bits, matrix=m, batched=False, ngates=blk.ngates)
+        return Block(qubits=tuple(self.nloc - 1 - b for b in bits), bits=bits, matrix=m, batched=False, ngates=blk.ngates,
+                     kind=matrix_kind(m))
 
     def _run_local(self, lb: Block) -> None:
         if len(lb.bits) == 0:
             # global phase for this rank: fold into a 1-bit diagonal block
             ph = complex(np.asarray(lb.matrix).reshape(-1)[0])
-            lb = Block(qubits=(self.nloc - 1,), bits=(0,), matrix=np.eye(2, dtype=np.complex128) * ph, batched=False, ngates=lb.ngates)
+            lb = Block(qubits=(self.nloc - 1,), bits=(0,), matrix=np.eye(2, dtype=np.complex128) * ph, batched=False, ngates=lb.ngates, kind="diag")
         self.local.apply_block(lb)
         self.stats["local_passes"] += 1
 
@@ -168,7 +169,7 @@ class DistState:
         for lb in batch:
             if len(lb.bits) == 0:  # pure rank phase: fold into a 1-bit diagonal block
                 ph = complex(np.asarray(lb.matrix).reshape(-1)[0])
-                lb = Block(qubits=(self.nloc - 1,), bits=(0,), matrix=np.eye(2, dtype=np.complex128) * ph, batched=False, ngates=lb.ngates)
+                lb = Block(qubits=(self.nloc - 1,), bits=(0,), matrix=np.eye(2, dtype=np.complex128) * ph, batched=False, ngates=lb.ngates, kind="diag")
             fixed.append(lb)
         if self.use_passes and hasattr(self.local, "apply_planned"):
             self.stats["local_passes"] += int(self.local.apply_planned(fixed))
@@ -182,7 +183,7 @@ class DistState:
     def _swap_local_bits(self, pa: int, pb: int) -> None:
         """Exchange two physical local bits (one local pass) and update the map."""
         lo, hi = sorted((pa, pb))
-        self.local.apply_block(Block(qubits=(self.nloc - 1 - hi, self.nloc - 1 - lo), bits=(lo, hi), matrix=_SWAP, batched=False, ngates=0))
+        self.local.apply_block(Block(qubits=(self.nloc - 1 - hi, self.nloc - 1 - lo), bits=(lo, hi), matrix=_SWAP, batched=False, ngates=0, kind="perm"))
         la, lb = self.logical_at(pa), self.logical_at(pb)
         self.phys[la], self.phys[lb] = pb, pa
         self.stats["swap_passes"] += 1

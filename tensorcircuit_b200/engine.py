@@ -16,13 +16,14 @@ import torch
 
 from . import _lib
 from ._lib import check, lib
-from .fusion import Block, plan_passes, plan_regtiles, tile_hi_fixpoint  # noqa: F401
+from .fusion import KIND_DENSE, KIND_PERM, Block, plan_passes, plan_regtiles, tile_hi_fixpoint  # noqa: F401
 
 _TORCH_C = {"complex64": torch.complex64, "complex128": torch.complex128}
 _DT = {"complex64": _lib.C64, "complex128": _lib.C128}
 
 # counters the benchmark reads (bytes are algorithmic: one read + one write per pass)
-STATS = {"apply_launches": 0, "apply_bytes": 0, "expect_launches": 0, "sample_launches": 0}
+STATS = {"apply_launches": 0, "apply_bytes": 0, "expect_launches": 0, "sample_launches": 0,
+         "gate_pass_rounds": 0, "gate_pass_fma_per_amp": 0.0, "gate_pass_free_gates": 0, "gate_pass_conflict_rounds": 0}
 
 
 def reset_stats() -> None:
@@ -143,12 +144,20 @@ class DeviceState:
     # the shorter rows cost some HBM efficiency per pass.
     pass_max_hi = int(os.environ.get("TCB200_PASS_MAX_HI", "8"))
 
+    # The structure-aware gate pass (tcb200_apply_gate_pass) is the production path; the older
+    # dense multi-block pass (cpass) stays reachable with TCB200_GATE_PASS=0 and serves batched
+    # (vmap) matrices and states below 4 qubits.
+    use_gate_pass = os.environ.get("TCB200_GATE_PASS", "1") != "0"
+    gate_pass_max_ops = int(os.environ.get("TCB200_GATE_PASS_MAX_OPS", "200"))
+
     def apply_planned(self, blocks: Sequence[Block]) -> int:
-        """Run ``blocks`` as staged multi-block passes (fusion.plan_passes): each pass is one HBM
-        read + write of the state however many blocks it holds.  Returns the number of passes."""
+        """Run ``blocks`` as staged passes (fusion.plan_passes): each pass is one HBM read + write
+        of the state however many blocks it holds.  Returns the number of launches."""
         if not blocks:
             return 0
         T = lib.tcb200_pass_tile_bits(self.dt)
+        if self.use_gate_pass and self.nbits >= 4 and not any(b.batched for b in blocks):
+            return self._apply_gate_planned(blocks, T)
         mat_elems = (12 * 1024) // self.amp_bytes
         passes = plan_passes([b.bits for b in blocks], self.nbits, T, max_hi=self.pass_max_hi,
                              max_ops=_lib.MAX_PASS_OPS, max_mat_elems=mat_elems, max_pass_k=_lib.MAX_PASS_K)
@@ -167,6 +176,65 @@ class DeviceState:
                 self.apply_pass_host(blks, p.tile_hi)
                 nlaunch += 1
         return nlaunch
+
+    def _apply_gate_planned(self, blocks: Sequence[Block], T: int) -> int:
+        """Pass plan for the gate pass: permutation blocks are free (weight 0, no parameter-bank
+        space), diagonal blocks take a 16-entry table, dense blocks wider than 3 bits run alone
+        through the single-block kernel."""
+        cost = [0 if b.kind == KIND_PERM else (4 ** len(b.bits) if b.kind == KIND_DENSE else 16) for b in blocks]
+        weight = [0.0 if b.kind == KIND_PERM else 1.0 for b in blocks]
+        passes = plan_passes([b.bits for b in blocks], self.nbits, T, max_hi=self.pass_max_hi, max_ops=self.gate_pass_max_ops,
+                             max_mat_elems=_lib.GATE_PASS_MAT_ELEMS, max_pass_k=4, block_cost=cost, block_weight=weight)
+        nlaunch = 0
+        for p in passes:
+            blks = [blocks[i] for i in p.block_ids]
+            if len(blks) == 1 and (len(blks[0].bits) > 3 and blks[0].kind == KIND_DENSE or len(blks[0].bits) > 4):
+                self.apply_block(blks[0])
+                nlaunch += 1
+            else:
+                nlaunch += self.apply_gate_pass(blks, p.tile_hi)
+        return nlaunch
+
+    def apply_gate_pass(self, blocks: Sequence[Block], tile_hi: Sequence[int]) -> int:
+        """One structure-aware staged pass (include/tcb200.h: tcb200_apply_gate_pass).  A run that
+        exceeds one launch's capacity is split in two on the same tile."""
+        if any(len(b.bits) > 3 and b.kind == KIND_DENSE for b in blocks):
+            # a dense block wider than the register tile handles: it runs alone, in order
+            n = 0
+            run: List[Block] = []
+            for b in blocks:
+                if len(b.bits) > 3 and b.kind == KIND_DENSE:
+                    if run:
+                        n += self.apply_gate_pass(run, tile_hi)
+                        run = []
+                    self.apply_block(b)
+                    n += 1
+                else:
+                    run.append(b)
+            if run:
+                n += self.apply_gate_pass(run, tile_hi)
+            return n
+        ks = np.asarray([len(b.bits) for b in blocks], dtype=np.int32)
+        bits = np.asarray([x for b in blocks for x in b.bits], dtype=np.int32)
+        mats = np.ascontiguousarray(np.concatenate([np.asarray(b.matrix, dtype=np.complex128).reshape(-1) for b in blocks]))
+        hi = np.asarray(list(tile_hi) if len(tile_hi) else [0], dtype=np.int32)
+        info = np.zeros(8, dtype=np.float64)
+        rc = self._gate_pass_call(len(blocks), ks, bits, mats, len(tile_hi), hi, info)
+        if rc == _lib.ERR_CAPACITY and len(blocks) > 1:
+            h = len(blocks) // 2
+            return self.apply_gate_pass(blocks[:h], tile_hi) + self.apply_gate_pass(blocks[h:], tile_hi)
+        check(rc)
+        STATS["apply_launches"] += 1
+        STATS["apply_bytes"] += 2 * self.amp_bytes * (self.batch << self.nbits)
+        STATS["gate_pass_rounds"] += int(info[0])
+        STATS["gate_pass_free_gates"] += int(info[1])
+        STATS["gate_pass_conflict_rounds"] += int(info[4])
+        STATS["gate_pass_fma_per_amp"] += float(info[6])
+        return 1
+
+    def _gate_pass_call(self, nops: int, ks: np.ndarray, bits: np.ndarray, mats: np.ndarray, n_hi: int, hi: np.ndarray, info: np.ndarray) -> int:
+        return lib.tcb200_apply_gate_pass(_ptr(self.buf), self.nbits, self.dt, nops, _lib.iptr(ks), _lib.iptr(bits), _lib.dptr(mats.view(np.float64)),
+                                          n_hi, _lib.iptr(hi), self.batch, _lib.dptr(info), _stream())
 
     # Register tiles (several gates per shared-memory round trip) pay off when many gates pile up
     # on the same <= 4 qubits inside a pass (nearest-neighbour ladders); on the random-matching

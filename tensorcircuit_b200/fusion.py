@@ -51,6 +51,7 @@ class Block:
     batched: bool
     ngates: int
     diagonal: bool = False
+    kind: str = "dense"  # 'dense' | 'diag' | 'perm' | 'mono' (fuse_structured)
 
 
 def embed_apply(block_m: np.ndarray, block_qubits: Sequence[int], g: np.ndarray, gq: Sequence[int]) -> np.ndarray:
@@ -183,6 +184,135 @@ def fuse(ops: Sequence[GateOp], nqubits: int, kmax: int = 4) -> List[Block]:
     return blocks
 
 
+# ------------------------------------------------------------------------------------------------
+# structure-aware fusion (diagonal / permutation / dense gate classes)
+# ------------------------------------------------------------------------------------------------
+# The gate pass (csrc/lpass.cu, tcb200_apply_gate_pass) treats three classes of matrices
+# differently: permutation matrices of an affine bit map (x, cnot, swap ...; any monomial matrix
+# on <= 2 qubits once its phases are split off) cost nothing -- they only rewrite the tile's
+# index map; diagonal matrices (z, s, t, rz, cz, rzz, cphase ...) cost one table multiply that
+# consecutive diagonals share; everything else is a dense 2^k x 2^k multiply (2 * 2^k packed
+# FMA per amplitude).  Fusion therefore merges gates only when the merged block is not dearer
+# than its parts: r(a) r(b) cnot(a,b) r'(a) r'(b) becomes ONE 4x4 (8 packed FMA per amplitude
+# for four 1-qubit gates' worth of work), a bare cnot stays a free permutation, an rzz next to
+# an rx stays a shared table instead of turning the pair into a dense 4x4.
+# Classes follow tensorcircuit/gates.py:46-127 (constant matrices), :579-636 (rx/ry/rz),
+# :826-865 (rzz/rxx/ryy via exponential_gate_unity).
+
+KIND_DENSE, KIND_DIAG, KIND_PERM, KIND_MONO = "dense", "diag", "perm", "mono"
+
+
+def matrix_kind(m: Any) -> str:
+    """Class of a gate matrix by its exact zero pattern (batched: the union over the batch)."""
+    a = _raw(m)
+    nz = (a != 0)
+    if a.ndim == 3:
+        nz = nz.any(axis=0)
+    D = nz.shape[-1]
+    if not nz[~np.eye(D, dtype=bool)].any():
+        return KIND_DIAG
+    if D <= 4 and (nz.sum(axis=0) == 1).all() and (nz.sum(axis=1) == 1).all():
+        vals = a[..., nz]
+        return KIND_PERM if np.all(vals == 1) else KIND_MONO
+    return KIND_DENSE
+
+
+def _kind_cost(kind: str, k: int) -> int:
+    """packed FMA per amplitude the gate pass spends on a block of this class"""
+    if kind == KIND_DENSE:
+        return 2 << k
+    if kind == KIND_PERM:
+        return 0
+    return 2  # one table multiply
+
+
+def _combine_kinds(kinds: Sequence[str]) -> str:
+    if KIND_DENSE in kinds:
+        return KIND_DENSE
+    if all(k == KIND_DIAG for k in kinds):
+        return KIND_DIAG
+    if all(k == KIND_PERM for k in kinds):
+        return KIND_PERM
+    return KIND_MONO
+
+
+def plan_structure_kinds(gate_qubits: Sequence[Tuple[int, ...]], gate_kinds: Sequence[str], kmax: int) -> FusionPlan:
+    """Cost-aware greedy fusion.  A gate merges with the blocks that are currently the latest on
+    its qubits when (i) each of them is still the latest block on ALL of its own qubits (so it
+    commutes forward to the merge point), (ii) the union stays within ``kmax`` qubits (2 for
+    monomial / diagonal results) and (iii) the merged block costs no more than the parts."""
+    key = ("kinds", tuple(gate_qubits), tuple(gate_kinds), kmax)
+    hit = _PLAN_CACHE.get(key)
+    if hit is not None:
+        return hit
+    groups: List[List[int]] = []
+    bq: List[set] = []
+    bkind: List[str] = []
+    last: Dict[int, int] = {}
+    for gi, (qs, kg) in enumerate(zip(gate_qubits, gate_kinds)):
+        if len(qs) > MAX_BLOCK_K:
+            raise ValueError("gate on %d qubits exceeds the widest supported block (%d)" % (len(qs), MAX_BLOCK_K))
+        sq = set(qs)
+        tops = sorted({last[q] for q in qs if q in last})
+        target = -1
+        if tops and all(all(last[q] == b for q in bq[b]) for b in tops):
+            union = set(sq)
+            for b in tops:
+                union |= bq[b]
+            kind_m = _combine_kinds([bkind[b] for b in tops] + [kg])
+            limit = kmax if kind_m == KIND_DENSE else 2
+            parts = sum(_kind_cost(bkind[b], len(bq[b])) for b in tops) + _kind_cost(kg, len(qs))
+            if len(union) <= max(limit, len(qs)) and len(union) <= MAX_BLOCK_K and _kind_cost(kind_m, len(union)) <= parts:
+                target = tops[-1]
+                for b in tops[:-1]:  # earlier blocks commute forward into the merge point
+                    groups[target] = groups[b] + groups[target]
+                    groups[b] = []
+                    bq[b] = set()
+                groups[target] = sorted(groups[target])
+                bq[target] = union
+                bkind[target] = kind_m
+        if target < 0:
+            groups.append([])
+            bq.append(set(sq))
+            bkind.append(kg)
+            target = len(groups) - 1
+        groups[target].append(gi)
+        for q in bq[target]:
+            last[q] = target
+    keep = [i for i in range(len(groups)) if groups[i]]
+    plan = FusionPlan([groups[i] for i in keep], [tuple(sorted(bq[i])) for i in keep])
+    if len(_PLAN_CACHE) > 256:
+        _PLAN_CACHE.clear()
+    _PLAN_CACHE[key] = plan
+    return plan
+
+
+def fuse_structured(ops: Sequence[GateOp], nqubits: int, kmax: int = 2) -> List[Block]:
+    """Structure-aware fusion of ``ops`` (program order) for the gate pass: blocks carry ``kind``
+    ('dense' / 'diag' / 'perm' / 'mono') computed from the fused matrix."""
+    if not ops:
+        return []
+    kinds = [matrix_kind(op.matrix) for op in ops]
+    plan = plan_structure_kinds([op.qubits for op in ops], kinds, kmax)
+    blocks: List[Block] = []
+    for grp, qs in zip(plan.groups, plan.block_qubits):
+        k = len(qs)
+        D = 1 << k
+        qlist = list(qs)
+        if len(grp) == 1 and tuple(ops[grp[0]].qubits) == tuple(qs) and not is_batched(ops[grp[0]].matrix):
+            m = np.asarray(ops[grp[0]].matrix, dtype=np.complex128)
+        else:
+            m = np.eye(D, dtype=np.complex128)
+            for gi in grp:
+                op = ops[gi]
+                m = embed_apply(m, qlist, _raw(op.matrix), list(op.qubits))
+        batched = m.ndim == 3
+        bits = tuple(sorted(nqubits - 1 - q for q in qs))
+        kind = matrix_kind(m)
+        blocks.append(Block(qubits=qs, bits=bits, matrix=m, batched=batched, ngates=len(grp), diagonal=kind == KIND_DIAG, kind=kind))
+    return blocks
+
+
 def clear_plan_cache() -> None:
     _PLAN_CACHE.clear()
     _PASS_CACHE.clear()
@@ -261,7 +391,8 @@ _PASS_CACHE: Dict[Any, List[Pass]] = {}
 
 
 def plan_passes(block_bits: Sequence[Tuple[int, ...]], nbits: int, tile_bits: int, max_hi: int = 6,
-                max_ops: int = 16, max_mat_elems: int = 1536, max_pass_k: int = 4, nseeds: int = 8) -> List[Pass]:
+                max_ops: int = 16, max_mat_elems: int = 1536, max_pass_k: int = 4, nseeds: int = 8,
+                block_cost: Optional[Sequence[int]] = None, block_weight: Optional[Sequence[float]] = None) -> List[Pass]:
     """List scheduling of fused blocks into tile passes, with a one-pass lookahead.
 
     A tile holds the ``tile_bits - h`` lowest index bits plus ``h <= max_hi`` gathered high bits;
@@ -273,7 +404,11 @@ def plan_passes(block_bits: Sequence[Tuple[int, ...]], nbits: int, tile_bits: in
     earliest seed).  On the config-4 recipe at n = 34 that gives 37 passes instead of 45.  The
     plan depends only on the bit structure and is cached."""
     max_hi = max(0, min(max_hi, tile_bits - 4))  # keep rows of >= 16 amplitudes contiguous
-    key = (tuple(block_bits), nbits, tile_bits, max_hi, max_ops, max_mat_elems, max_pass_k, nseeds)
+    # block_cost: parameter-bank elements per block (default 4^k); block_weight: what "fullest
+    # pass" counts (default 1 per block; the gate pass gives free permutation blocks weight 0)
+    cost = list(block_cost) if block_cost is not None else [1 << (2 * len(b)) for b in block_bits]
+    weight = list(block_weight) if block_weight is not None else [1.0] * len(block_bits)
+    key = (tuple(block_bits), nbits, tile_bits, max_hi, max_ops, max_mat_elems, max_pass_k, nseeds, tuple(cost), tuple(weight))
     hit = _PASS_CACHE.get(key)
     if hit is not None:
         return hit
@@ -309,7 +444,7 @@ def plan_passes(block_bits: Sequence[Tuple[int, ...]], nbits: int, tile_bits: in
                         best, best_hi, best_score = i, [], (0, i)
                         break
                     continue
-                if mat + (1 << (2 * k)) > max_mat_elems:
+                if mat + cost[i] > max_mat_elems:
                     continue
                 hi = tile_hi_fixpoint(list(used | set(bits)), tile_bits, nbits)
                 if len(hi) > max_hi:
@@ -331,7 +466,7 @@ def plan_passes(block_bits: Sequence[Tuple[int, ...]], nbits: int, tile_bits: in
             cur.append(best)
             used |= set(block_bits[best])
             cur_hi = best_hi
-            mat += 1 << (2 * len(block_bits[best]))
+            mat += cost[best]
             ready.remove(best)
             for s_ in succs[best]:
                 indeg[s_] -= 1
@@ -349,7 +484,7 @@ def plan_passes(block_bits: Sequence[Tuple[int, ...]], nbits: int, tile_bits: in
         best_fill = None
         for seed in ready[: max(1, nseeds)]:
             f = fill(seed, indeg, ready)
-            if best_fill is None or len(f[0]) > len(best_fill[0]):
+            if best_fill is None or sum(weight[i] for i in f[0]) > sum(weight[i] for i in best_fill[0]):
                 best_fill = f
         if best_fill is None or not best_fill[0]:
             raise RuntimeError("pass planner made no progress")

@@ -67,6 +67,25 @@ class FakeState:
             self.apply_block(b)
 
     pass_max_hi = 6
+    use_gate_pass = True
+    gate_pass_max_ops = 200
+    apply_gate_pass = engine.DeviceState.apply_gate_pass
+    _apply_gate_planned = engine.DeviceState._apply_gate_planned
+
+    def _gate_pass_call(self, nops, ks, bits, mats, n_hi, hi, info):
+        st = self.np[0].copy() if self.batch > 1 else None
+        for r in range(self.batch):
+            rc = self._lib.emu_apply_gate_pass(self.np[r].ctypes.data_as(ctypes.c_void_p), self.nbits, self.dt, nops, _ip(ks), _ip(bits),
+                                               mats.view(np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n_hi, _ip(hi),
+                                               info.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+            if rc:
+                assert r == 0
+                if rc != -4:
+                    raise engine._lib.EngineError("emu gate pass: %s" % self._lib.emu_last_error().decode())
+                return rc
+        del st
+        return 0
+
     regtile_max_gates = 2  # pair mode, as the engine; tests override it to cover the generic path
 
     def apply_planned(self, blocks):
@@ -76,6 +95,9 @@ class FakeState:
         if not blocks:
             return 0
         T = self._lib.emu_pass_tile_bits(self.dt)
+        if self.use_gate_pass and self.nbits >= 4 and not any(b.batched for b in blocks):
+            # the engine's own planning code, with the launch replaced by the emulated kernel
+            return self._apply_gate_planned(blocks, T)
         passes = plan_passes([b.bits for b in blocks], self.nbits, T, max_hi=self.pass_max_hi, max_ops=16,
                              max_mat_elems=(12 * 1024) // self.amp_bytes, max_pass_k=4)
         assert sorted(i for p in passes for i in p.block_ids) == list(range(len(blocks)))

@@ -24,9 +24,10 @@ def _build_emu():
     # apply.cu is compiled with -DTCB200_EMU only here: that adds the CPU execution of the
     # register-tile pass (same parameter block and device functions as rpass_kernel)
     srcs = [os.path.join(EMU_DIR, "emu.cu"), os.path.join(ROOT, "tensorcircuit_b200", "csrc", "abi.cu"),
-            os.path.join(ROOT, "tensorcircuit_b200", "csrc", "apply.cu"), os.path.join(ROOT, "tensorcircuit_b200", "csrc", "tpass.cu"),
+            os.path.join(ROOT, "tensorcircuit_b200", "csrc", "apply.cu"), os.path.join(ROOT, "tensorcircuit_b200", "csrc", "lpass.cu"),
+            os.path.join(ROOT, "tensorcircuit_b200", "csrc", "tpass.cu"),
             os.path.join(ROOT, "tensorcircuit_b200", "csrc", "expect.cu")]
-    deps = srcs + [os.path.join(ROOT, "tensorcircuit_b200", "csrc", "common.cuh"), os.path.join(ROOT, "include", "tcb200.h")]
+    deps = srcs + [os.path.join(ROOT, "tensorcircuit_b200", "csrc", "common.cuh"), os.path.join(ROOT, "tensorcircuit_b200", "csrc", "lpass.cuh"), os.path.join(ROOT, "include", "tcb200.h")]
     if os.path.exists(EMU_LIB) and all(os.path.getmtime(EMU_LIB) > os.path.getmtime(d) for d in deps):
         return
     os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
