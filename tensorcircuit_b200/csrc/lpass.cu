@@ -136,7 +136,9 @@ struct LPassParams {
     int stb;     // log2(blockDim.x)
     int ngb;     // group-index bits: T - LP_RB
     int nrounds;
+    int fast;    // production shape: 256 threads, 16 staging units per thread (LStage valid)
     LOut out;
+    LStage stage;
     LRound r[LP_MAX_ROUNDS];
     ME<Real> m[LP_MAT_ELEMS];
 };
@@ -467,6 +469,25 @@ int fill_lpass(LPassParams<Real>& q, LPassInfo& info, void* state, int nbits, in
     rc = s.run();
     if (rc) return rc;
     info = s.info;
+    // ---- staging constants of the production shape ----
+    constexpr int APU = 16 / (int)sizeof(C);
+    constexpr int SH = APU == 2 ? 1 : 0;
+    q.fast = (q.stb == 8 && units_log == 12) ? 1 : 0;
+    if (q.fast) {
+        auto goff_of = [&](uint32_t e) {  // amplitude offset of tile-local element e
+            return row_offset(q.g, e >> q.g.lrow) + (uint64_t)(e & ((1u << q.g.lrow) - 1u));
+        };
+        for (int b = 0; b < 9; ++b) q.stage.bit_off[b] = goff_of(1u << b);
+        for (int i = 0; i < LP_FAST_ITERS; ++i) {
+            const uint32_t u = (uint32_t)i << 8;
+            q.stage.goff[i] = goff_of(u * APU);
+            q.stage.sin[i] = swz_unit(u) << 4;
+            uint32_t x = 0;
+            for (int t = 0; t < 4; ++t)
+                if ((i >> t) & 1) x ^= q.out.col[8 + t + SH];
+            q.stage.sout[i] = x;
+        }
+    }
     return 0;
 }
 
@@ -499,6 +520,25 @@ __global__ void __launch_bounds__(256, sizeof(Real) == 4 ? 3 : 2) lpass_kernel(c
     lstage_out_thread<C>(p.g, vec, base, smem_raw, rowoff, p.out, tid, nthr, p.stb);
 }
 
+// production shape (LPassParams::fast): 256 threads, one 64 KiB tile, host-precomputed staging
+// constants, compile-time loop structure -- no shared-memory row table, no per-unit index math
+template <typename Real>
+__global__ void __launch_bounds__(256, sizeof(Real) == 4 ? 3 : 2) lpass_fast_kernel(const __grid_constant__ LPassParams<Real> p) {
+    using C = typename CT<Real>::type;
+    constexpr int NIT = sizeof(C) == 8 ? 2 : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t tid = threadIdx.x;
+    C* vec = p.state + ((uint64_t)blockIdx.y << p.g.n) + tile_base(p.g, blockIdx.x);
+    lstage_in_fast<C>(p.stage, vec, smem_raw, tid);
+    cp_async_wait_all();
+    __syncthreads();
+    for (int r = 0; r < p.nrounds; ++r) {
+        lround_thread_fast<C, Real, NIT>(smem_raw, p.r[r], p.m, tid);
+        __syncthreads();
+    }
+    lstage_out_fast<C>(p.stage, p.out, vec, smem_raw, tid);
+}
+
 template <typename Real>
 static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, const int* ops_bits, const double* mats, int n_hi,
                         const int* tile_hi, int64_t batch, cudaStream_t st, LPassInfo* info_out) {
@@ -519,11 +559,13 @@ static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, cons
     static bool attr = false;
     if (!attr) {
         TCB_CUDA(cudaFuncSetAttribute(lpass_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        TCB_CUDA(cudaFuncSetAttribute(lpass_fast_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
         attr = true;
     }
     dim3 grid((unsigned)ntiles, (unsigned)batch);
     dim3 block(1u << q.stb);
-    lpass_kernel<Real><<<grid, block, smem, st>>>(q);
+    if (q.fast) lpass_fast_kernel<Real><<<grid, block, smem, st>>>(q);
+    else lpass_kernel<Real><<<grid, block, smem, st>>>(q);
     TCB_LAUNCH_CHECK("lpass_kernel");
     return 0;
 }
@@ -551,6 +593,14 @@ static int emu_lpass(void* state, int nbits, int nops, const int* ops_k, const i
     const uint64_t ntiles = 1ull << (nbits - q->g.T);
     for (uint64_t t = 0; t < ntiles; ++t) {
         const uint64_t base = tile_base(q->g, t);
+        if (q->fast) {  // the bodies of lpass_fast_kernel
+            constexpr int NIT = sizeof(C) == 8 ? 2 : 1;
+            for (int tid = 0; tid < 256; ++tid) lstage_in_fast<C>(q->stage, vec + base, tile, (uint32_t)tid);
+            for (int r = 0; r < q->nrounds; ++r)
+                for (int tid = 0; tid < 256; ++tid) lround_thread_fast<C, Real, NIT>(tile, q->r[r], q->m, (uint32_t)tid);
+            for (int tid = 0; tid < 256; ++tid) lstage_out_fast<C>(q->stage, q->out, vec + base, tile, (uint32_t)tid);
+            continue;
+        }
         for (int tid = 0; tid < nthr; ++tid) stage_in<C, SWZ_SW>(q->g, vec, base, reinterpret_cast<C*>(tile), rowoff, tid, nthr);
         for (int r = 0; r < q->nrounds; ++r)
             for (int tid = 0; tid < (1 << q->tb); ++tid) lround_thread<C, Real>(tile, q->r[r], q->m, (uint32_t)tid, q->tb, q->ngb);

@@ -66,6 +66,17 @@ struct LOut {                    // index map at the end of the pass, for the wr
     uint32_t vec;                // complex64: (x, x^1) share one aligned 16-byte unit
 };
 
+// Staging constants of the production shape (256 threads, 16 units of 16 bytes per thread: the
+// 64 KiB tile).  Thread `tid` owns the units tid + 256 i; everything that depends on i alone is
+// precomputed on the host, so that a unit costs one add, one XOR and the copy itself.
+constexpr int LP_FAST_ITERS = 16;
+struct LStage {
+    uint64_t goff[LP_FAST_ITERS];   // amplitude offset of unit (i << 8) relative to the tile base
+    uint64_t bit_off[9];            // amplitude offset of bit b of the thread's element index tid * APU
+    uint32_t sin[LP_FAST_ITERS];    // stage-in: byte offset of unit (i << 8) in the staging swizzle
+    uint32_t sout[LP_FAST_ITERS];   // write-back: byte-offset XOR of unit (i << 8) under the final index map
+};
+
 // ---- complex arithmetic against a parameter-bank element ---------------------------------------
 template <typename C, typename Real>
 TCB_HD C me_mul(const ME<Real>& m, const C v) {
@@ -191,12 +202,15 @@ TCB_HD void lp_dispatch(C* v, uint32_t code, const ME<Real>* mats) {
 }
 
 // ---- one group: load 16, run the round's micro-ops, store 16 -----------------------------------
-template <typename C, typename Real, bool VEC>
-TCB_HD void lround_group(unsigned char* tile, uint32_t b, const LRound& R, const ME<Real>* mats) {
+// `vec` (complex64, rcol[0] == 8): (j, j+1) is one aligned 16-byte unit.  It is a run-time flag
+// on purpose: the micro-op dispatch -- by far the largest piece of code -- must exist once in the
+// kernel, or the instruction cache thrashes (four copies were 230 KB of SASS).
+template <typename C, typename Real>
+TCB_HD void lround_group(unsigned char* tile, uint32_t b, const LRound& R, const ME<Real>* mats, const bool vec) {
     const uint32_t c0 = R.rcol[0], c1 = R.rcol[1], c2 = R.rcol[2], c3 = R.rcol[3];
     const uint32_t nc = R.ncodes & 0xffu;
     C v[16];
-    if (VEC) {  // complex64, rcol[0] == 8: (j, j+1) is one aligned 16-byte unit
+    if (sizeof(C) == 8 && vec) {
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
             const uint32_t off = ((j & 2) ? c1 : 0u) ^ ((j & 4) ? c2 : 0u) ^ ((j & 8) ? c3 : 0u);
@@ -212,8 +226,9 @@ TCB_HD void lround_group(unsigned char* tile, uint32_t b, const LRound& R, const
             v[j] = *reinterpret_cast<const C*>(tile + (b ^ off));
         }
     }
+#pragma unroll 1
     for (uint32_t o = 0; o < nc; ++o) lp_dispatch<C, Real>(v, R.code[o], mats);
-    if (VEC) {
+    if (sizeof(C) == 8 && vec) {
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
             const uint32_t off = ((j & 2) ? c1 : 0u) ^ ((j & 4) ? c2 : 0u) ^ ((j & 8) ? c3 : 0u);
@@ -242,14 +257,14 @@ TCB_HD void lround_thread(unsigned char* tile, const LRound& R, const ME<Real>* 
         if (i < tb) b ^= (0u - ((tid >> i) & 1u)) & R.gcol[i];
     const uint32_t nit = 1u << (ngb - tb);
     const bool vec = sizeof(C) == 8 && ((R.ncodes >> 8) & 1u);
+#pragma unroll 1
     for (uint32_t it = 0; it < nit; ++it) {
         if (it > 0) {
             int z = 0;
             while (!((it >> z) & 1u)) ++z;
             b ^= R.gcol[tb + z];
         }
-        if (vec) lround_group<C, Real, true>(tile, b, R, mats);
-        else lround_group<C, Real, false>(tile, b, R, mats);
+        lround_group<C, Real>(tile, b, R, mats, vec);
     }
 }
 
@@ -289,6 +304,71 @@ TCB_HD void lstage_out_thread(const TileGeom& g, C* vec, uint64_t base, const un
             qc[1 % APU] = *reinterpret_cast<const C*>(tile + (a ^ L.col[0]));
         }
         *reinterpret_cast<Unit16*>(vec + gi) = q;
+    }
+}
+
+// ---- production shape: 256 threads, compile-time loop structure ---------------------------------
+// NIT = groups per thread per round (2 for the 2^13-amplitude complex64 tile, 1 for complex128)
+template <typename C, typename Real, int NIT>
+TCB_HD void lround_thread_fast(unsigned char* tile, const LRound& R, const ME<Real>* mats, uint32_t tid) {
+    uint32_t b = R.d;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b ^= (0u - ((tid >> i) & 1u)) & R.gcol[i];
+    const bool vec = sizeof(C) == 8 && ((R.ncodes >> 8) & 1u);
+#pragma unroll 1
+    for (int it = 0; it < NIT; ++it) {
+        if (it > 0) b ^= R.gcol[8];
+        lround_group<C, Real>(tile, b, R, mats, vec);
+    }
+}
+
+// amplitude offset (relative to the tile base) of the thread's first element tid * APU
+template <int APU>
+TCB_HD uint64_t lstage_thread_goff(const LStage& S, uint32_t tid) {
+    const uint32_t e = tid * APU;
+    uint64_t o = 0;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) o += ((e >> b) & 1u) ? S.bit_off[b] : 0ull;
+    return o;
+}
+
+template <typename C>
+TCB_HD void lstage_in_fast(const LStage& S, const C* vec_base, unsigned char* tile, uint32_t tid) {
+    constexpr int APU = 16 / (int)sizeof(C);
+    const C* g = vec_base + lstage_thread_goff<APU>(S, tid);
+    const uint32_t s0 = swz_unit(tid) << 4;
+#pragma unroll
+    for (int i = 0; i < LP_FAST_ITERS; ++i) {
+#if defined(__CUDA_ARCH__)
+        cp_async16(tile + (s0 ^ S.sin[i]), g + S.goff[i]);
+#else
+        *reinterpret_cast<Unit16*>(tile + (s0 ^ S.sin[i])) = *reinterpret_cast<const Unit16*>(g + S.goff[i]);
+#endif
+    }
+}
+
+template <typename C>
+TCB_HD void lstage_out_fast(const LStage& S, const LOut& L, C* vec_base, const unsigned char* tile, uint32_t tid) {
+    constexpr int APU = 16 / (int)sizeof(C);
+    constexpr int SH = APU == 2 ? 1 : 0;
+    C* g = vec_base + lstage_thread_goff<APU>(S, tid);
+    uint32_t a = L.d;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a ^= (0u - ((tid >> i) & 1u)) & L.col[i + SH];
+    const bool vec = APU == 1 || L.vec;
+    const uint32_t c0 = L.col[0];
+#pragma unroll
+    for (int i = 0; i < LP_FAST_ITERS; ++i) {
+        const uint32_t ai = a ^ S.sout[i];
+        Unit16 q;
+        if (vec) {
+            q = *reinterpret_cast<const Unit16*>(tile + ai);
+        } else {
+            C* qc = reinterpret_cast<C*>(&q);
+            qc[0] = *reinterpret_cast<const C*>(tile + ai);
+            qc[1 % APU] = *reinterpret_cast<const C*>(tile + (ai ^ c0));
+        }
+        *reinterpret_cast<Unit16*>(g + S.goff[i]) = q;
     }
 }
 

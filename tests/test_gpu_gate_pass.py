@@ -172,13 +172,13 @@ def test_gate_pass_matches_dense_pass_at_n26():
     rc = recipes.random_circuit(n, depth, 5)
     c1 = tc.Circuit(n)
     recipes.build(c1, rc)
-    s1 = c1._sync()
+    s1 = c1._ensure_state()
     old = DeviceState.use_gate_pass
     try:
         DeviceState.use_gate_pass = False
         c2 = tc.Circuit(n)
         recipes.build(c2, rc)
-        s2 = c2._sync()
+        s2 = c2._ensure_state()
     finally:
         DeviceState.use_gate_pass = old
     d = (s1.buf - s2.buf).abs().max().item()

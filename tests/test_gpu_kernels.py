@@ -458,6 +458,7 @@ def test_tma_pass_many_tiles_per_cta(monkeypatch):
     """2^24 amplitudes = 2048 tiles over 148 persistent CTAs: the ring wraps ~14 times per CTA
     (mbarrier phases, buffer hand-over between bulk stores and loads)."""
     monkeypatch.setenv("TCB200_TMA", "1")
+    monkeypatch.setattr(DeviceState, "use_gate_pass", False)  # the opt-in pipeline sits behind the dense pass
     n, dtype = 24, "complex64"
     c = tc.Circuit(n)
     ops = orc.random_circuit(n, 4, seed=11)
