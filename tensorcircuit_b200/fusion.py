@@ -202,10 +202,15 @@ def fuse(ops: Sequence[GateOp], nqubits: int, kmax: int = 4) -> List[Block]:
 KIND_DENSE, KIND_DIAG, KIND_PERM, KIND_MONO = "dense", "diag", "perm", "mono"
 
 
+# entries below this magnitude are rounding residue of the gate formulas (cos(pi/2) = 6e-17 in
+# iswap, rx(pi) ...): they are treated as exact zeros -- six orders below the complex128 tolerance
+SNAP_EPS = 1e-15
+
+
 def matrix_kind(m: Any) -> str:
-    """Class of a gate matrix by its exact zero pattern (batched: the union over the batch)."""
+    """Class of a gate matrix by its zero pattern (batched: the union over the batch)."""
     a = _raw(m)
-    nz = (a != 0)
+    nz = np.abs(a) > SNAP_EPS
     if a.ndim == 3:
         nz = nz.any(axis=0)
     D = nz.shape[-1]
@@ -213,7 +218,7 @@ def matrix_kind(m: Any) -> str:
         return KIND_DIAG
     if D <= 4 and (nz.sum(axis=0) == 1).all() and (nz.sum(axis=1) == 1).all():
         vals = a[..., nz]
-        return KIND_PERM if np.all(vals == 1) else KIND_MONO
+        return KIND_PERM if np.all(np.abs(vals - 1) <= SNAP_EPS) else KIND_MONO
     return KIND_DENSE
 
 
@@ -249,13 +254,35 @@ def plan_structure_kinds(gate_qubits: Sequence[Tuple[int, ...]], gate_kinds: Seq
     bq: List[set] = []
     bkind: List[str] = []
     last: Dict[int, int] = {}
+    # next gate on each qubit after gate gi (lookahead credit of the inner merge below)
+    ng = len(gate_qubits)
+    nxt_on: List[Dict[int, int]] = [dict() for _ in range(ng)]
+    seen: Dict[int, int] = {}
+    for gi in range(ng - 1, -1, -1):
+        for q in gate_qubits[gi]:
+            if q in seen:
+                nxt_on[gi][q] = seen[q]
+        for q in gate_qubits[gi]:
+            seen[q] = gi
+
+    def merge_into(target: int, others: Sequence[int], union: set, kind_m: str) -> None:
+        for b in others:  # earlier blocks commute forward into the merge point
+            groups[target] = groups[b] + groups[target]
+            groups[b] = []
+            bq[b] = set()
+        groups[target] = sorted(groups[target])
+        bq[target] = union
+        bkind[target] = kind_m
+
     for gi, (qs, kg) in enumerate(zip(gate_qubits, gate_kinds)):
         if len(qs) > MAX_BLOCK_K:
             raise ValueError("gate on %d qubits exceeds the widest supported block (%d)" % (len(qs), MAX_BLOCK_K))
         sq = set(qs)
         tops = sorted({last[q] for q in qs if q in last})
+        ontop = [b for b in tops if all(last[q] == b for q in bq[b])]
         target = -1
-        if tops and all(all(last[q] == b for q in bq[b]) for b in tops):
+        if tops and len(ontop) == len(tops):
+            # full merge: every block that is the latest on one of the gate's qubits joins
             union = set(sq)
             for b in tops:
                 union |= bq[b]
@@ -264,13 +291,29 @@ def plan_structure_kinds(gate_qubits: Sequence[Tuple[int, ...]], gate_kinds: Seq
             parts = sum(_kind_cost(bkind[b], len(bq[b])) for b in tops) + _kind_cost(kg, len(qs))
             if len(union) <= max(limit, len(qs)) and len(union) <= MAX_BLOCK_K and _kind_cost(kind_m, len(union)) <= parts:
                 target = tops[-1]
-                for b in tops[:-1]:  # earlier blocks commute forward into the merge point
-                    groups[target] = groups[b] + groups[target]
-                    groups[b] = []
-                    bq[b] = set()
-                groups[target] = sorted(groups[target])
-                bq[target] = union
-                bkind[target] = kind_m
+                merge_into(target, tops[:-1], union, kind_m)
+        if target < 0 and len(qs) == 2 and len(qs) <= kmax:
+            # inner merge: only the blocks that live entirely on the gate's own qubits join (the
+            # other latest blocks simply stay in front).  Worth it when a dense 1-qubit block is
+            # upgraded to a dense 2-qubit block that the following 1-qubit gates then join for
+            # free (lookahead: 4 packed FMA of credit per qubit whose next gate is such a gate).
+            inner = [b for b in ontop if bq[b] <= sq]
+            if inner and any(bkind[b] == KIND_DENSE for b in inner):
+                kind_m = _combine_kinds([bkind[b] for b in inner] + [kg])
+                parts = sum(_kind_cost(bkind[b], len(bq[b])) for b in inner) + _kind_cost(kg, len(qs))
+                credit = 0
+                for q in qs:
+                    j = nxt_on[gi].get(q)
+                    if j is not None and len(gate_qubits[j]) == 1 and gate_kinds[j] == KIND_DENSE:
+                        credit += _kind_cost(KIND_DENSE, 1)
+                if _kind_cost(kind_m, len(sq)) <= parts + credit:
+                    # the merged block holds the gate, which must follow the latest blocks that
+                    # are NOT merged: it becomes a new block at the end, the inner ones move into it
+                    groups.append([])
+                    bq.append(set())
+                    bkind.append(kind_m)
+                    target = len(groups) - 1
+                    merge_into(target, inner, set(sq), kind_m)
         if target < 0:
             groups.append([])
             bq.append(set(sq))
@@ -309,6 +352,11 @@ def fuse_structured(ops: Sequence[GateOp], nqubits: int, kmax: int = 2) -> List[
         batched = m.ndim == 3
         bits = tuple(sorted(nqubits - 1 - q for q in qs))
         kind = matrix_kind(m)
+        if kind != KIND_DENSE and not batched:
+            # hand the library exact zeros / ones: it classifies by exact comparison
+            m = np.where(np.abs(m) > SNAP_EPS, m, 0)
+            if kind == KIND_PERM:
+                m = np.where(m != 0, 1.0 + 0j, 0)
         blocks.append(Block(qubits=qs, bits=bits, matrix=m, batched=batched, ngates=len(grp), diagonal=kind == KIND_DIAG, kind=kind))
     return blocks
 
@@ -392,7 +440,8 @@ _PASS_CACHE: Dict[Any, List[Pass]] = {}
 
 def plan_passes(block_bits: Sequence[Tuple[int, ...]], nbits: int, tile_bits: int, max_hi: int = 6,
                 max_ops: int = 16, max_mat_elems: int = 1536, max_pass_k: int = 4, nseeds: int = 8,
-                block_cost: Optional[Sequence[int]] = None, block_weight: Optional[Sequence[float]] = None) -> List[Pass]:
+                block_cost: Optional[Sequence[int]] = None, block_weight: Optional[Sequence[float]] = None,
+                jitter_seed: Optional[int] = None) -> List[Pass]:
     """List scheduling of fused blocks into tile passes, with a one-pass lookahead.
 
     A tile holds the ``tile_bits - h`` lowest index bits plus ``h <= max_hi`` gathered high bits;
@@ -408,7 +457,10 @@ def plan_passes(block_bits: Sequence[Tuple[int, ...]], nbits: int, tile_bits: in
     # pass" counts (default 1 per block; the gate pass gives free permutation blocks weight 0)
     cost = list(block_cost) if block_cost is not None else [1 << (2 * len(b)) for b in block_bits]
     weight = list(block_weight) if block_weight is not None else [1.0] * len(block_bits)
-    key = (tuple(block_bits), nbits, tile_bits, max_hi, max_ops, max_mat_elems, max_pass_k, nseeds, tuple(cost), tuple(weight))
+    # jitter_seed: break the greedy's ties (equal number of new gathered bits) at random instead of
+    # in program order -- plan_passes_best keeps the best of several such plans
+    jit = np.random.default_rng(jitter_seed) if jitter_seed is not None else None
+    key = (tuple(block_bits), nbits, tile_bits, max_hi, max_ops, max_mat_elems, max_pass_k, nseeds, tuple(cost), tuple(weight), jitter_seed)
     hit = _PASS_CACHE.get(key)
     if hit is not None:
         return hit
@@ -449,10 +501,10 @@ def plan_passes(block_bits: Sequence[Tuple[int, ...]], nbits: int, tile_bits: in
                 hi = tile_hi_fixpoint(list(used | set(bits)), tile_bits, nbits)
                 if len(hi) > max_hi:
                     continue
-                score = (len(hi) - len(cur_hi), i)
+                score = (len(hi) - len(cur_hi), i if jit is None else float(jit.random()))
                 if best_score is None or score < best_score:
                     best, best_score, best_hi = i, score, hi
-                    if score[0] <= 0:
+                    if score[0] <= 0 and jit is None:
                         break
             if best < 0:
                 if cur:
