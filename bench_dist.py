@@ -18,15 +18,30 @@ import torch.distributed as dist
 def run_dist(args, tc, rank, world, local):
     from bench import METRIC, UNIT, SEED, ClockSampler, measured_peak, workload_config
     from tensorcircuit_b200 import _lib, recipes
+    from tensorcircuit_b200 import engine
     from tensorcircuit_b200.dist import DistState
-    from tensorcircuit_b200.fusion import fuse
 
     g = int(round(math.log2(world)))
     n = args.n if args.n else min(36, 34 + g)
     ops = recipes.random_circuit(n, args.depth, SEED)
     ngates = len(ops)
     c0 = recipes.build(tc.Circuit(n), ops)
-    blocks = fuse(c0._ops, n, kmax=tc.Circuit.fusion_kmax)
+    blocks = c0._fuse(c0._ops, n)
+
+    # ---- parity of the distributed path before anything is timed: the same recipe at n = 22 on
+    # the sharded state against the oracle (rank 0 holds the oracle; every rank checks its shard)
+    from oracle import tc_oracle as orc
+
+    n_par = 22
+    ops_par = recipes.random_circuit(n_par, 6, SEED)
+    c_par = recipes.build(tc.Circuit(n_par), ops_par)
+    ds_par = DistState(n_par, "complex64")
+    ds_par.init_zero()
+    ds_par.run(c_par._fuse(c_par._ops, n_par))
+    got = ds_par.gather_state()
+    ref = orc.run_gatelist(n_par, ops_par).state()
+    dist_parity = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+    del ds_par, got, ref, c_par
     shots = args.shots
     u = np.random.default_rng(4).random(shots)
     u_host = torch.from_numpy(u).pin_memory()
@@ -107,6 +122,23 @@ def run_dist(args, tc, rank, world, local):
     del c_last
     gc.collect()
 
+    # BASELINE config 3 with the batch sharded over the ranks (north star: batched config at 2/4/8 GPUs)
+    cfg3 = None
+    if not getattr(args, "no_configs", False):
+        try:
+            tc.set_distributed(False)
+            from bench import config3_vmap
+
+            sync()  # backend.vmap splits the batch over the ranks of the default group by itself
+            cfg3 = config3_vmap(tc, engine, recipes, torch, B=1024, rank=rank, world=world)
+            sync()
+            w = torch.tensor([cfg3["wall_ms"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(w, op=dist.ReduceOp.MAX)
+            cfg3["wall_ms"] = float(w.item())
+            cfg3["states_per_s"] = 1024 / (cfg3["wall_ms"] * 1e-3)
+        except Exception as e:
+            cfg3 = {"config": "config3_vmap sharded", "failed": repr(e)}
+
     if rank == 0:
         value = args.steps * ngates * float(2**n) / (total_ms * 1e-3)
         peak, peak_src = measured_peak()
@@ -120,7 +152,7 @@ def run_dist(args, tc, rank, world, local):
             "dtype": "c64", "data": "synthetic",
             "config": dict(workload_config(world, n, args.depth, shots), recorded_gates=ngates, fused_blocks=len(blocks),
                            shard_gib=shard_bytes / 2**30, exchange="double-buffered all_to_all" if shard_bytes * 2 < 150 * 2**30 else "chunked all_to_all through staging"),
-            "roofline": {"bound": "hbm", "kernel": "cpass_kernel (staged local passes between remaps)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "lpass_fast_kernel (structure-aware gate passes on the shard between remaps)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": None},
             "remap": {"per_step": stats["remaps"] / args.steps, "bytes_per_rank_per_remap": (stats["remap_bytes"] / stats["remaps"]) if stats["remaps"] else 0,
                       "ms_per_remap": (stats["remap_ms"] / stats["remaps"]) if stats["remaps"] else 0, "nvlink_gbs_per_direction": remap_gbs,
@@ -133,6 +165,10 @@ def run_dist(args, tc, rank, world, local):
                             "ms": 1e3 * exp_s, "energy": energy},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "checks": {"norm2": norm2, "sample_min": int(s.min()), "sample_max": int(s.max())},
+            "checks": {"norm2": norm2, "sample_min": int(s.min()), "sample_max": int(s.max()),
+                       "dist_parity_relerr": dist_parity, "dist_parity_what": "config-5 recipe at n=22 depth 6 on the sharded state (remaps included) vs the oracle, relative l2 error; tolerance 1e-5"},
+            "gate_pass": {"rounds_per_step": engine.STATS["gate_pass_rounds"] / max(1, args.steps + args.warmup + 1), "fma_per_amplitude_per_step": engine.STATS["gate_pass_fma_per_amp"] / max(1, args.steps + args.warmup + 1)},
         }
+        if cfg3 is not None:
+            line["configs"] = [cfg3]
         print(json.dumps(line))

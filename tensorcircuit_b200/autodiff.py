@@ -27,6 +27,7 @@ the parameter values (the same restriction ``jit`` has in the reference)."""
 
 from __future__ import annotations
 
+import hashlib
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -43,10 +44,18 @@ _MAX_BATCH_AMPS = 1 << 28
 class _Query:
     def __init__(self, circ: Any, fl: Sequence[int], sg: Sequence[int], ny: Sequence[int]):
         self.nqubits = circ._nqubits
-        self.key = (id(circ), len(circ._ops))  # queries on the same circuit prefix share their simulations
+        self.circ = circ  # strong reference: the circuit (and its id) outlives the trace
         # matrix [D, D], or [B, D, D] when the recording itself was run on a batch of nudged parameters
         self.ops = [(tuple(op.qubits), np.array(op.matrix.a if isinstance(op.matrix, BatchArray) else np.asarray(op.matrix), dtype=np.complex128))
                     for op in circ._ops]
+        # queries on the same gate sequence share their shifted simulations.  The key is the gate
+        # CONTENT (qubits + matrix bytes), not the circuit object: sample_expectation_ps appends and
+        # removes basis rotations on one circuit, and ids are reused after garbage collection.
+        h = hashlib.blake2b(digest_size=16)
+        for qubits, M in self.ops:
+            h.update(repr((qubits, M.shape)).encode())
+            h.update(np.ascontiguousarray(M).tobytes())
+        self.key = (self.nqubits, len(self.ops), h.digest())
         self.fl, self.sg, self.ny = list(fl), list(sg), list(ny)
         self.values: Optional[np.ndarray] = None  # complex [nterms]
 
@@ -234,7 +243,7 @@ def value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0
                     for qi, v in enumerate(stored):
                         dl_de[qi][:] = d[r : r + len(v)]
                         r += len(v)
-                nudged = True
+                    nudged = True  # otherwise: fall through to one replay per nudged value
         except (TypeError, ValueError, NotImplementedError, RuntimeError, AttributeError, IndexError):
             dl_de = [np.zeros(len(v)) for v in stored]
         for qi, v in enumerate(stored if not nudged else []):

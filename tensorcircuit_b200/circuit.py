@@ -655,35 +655,54 @@ class Circuit:
         if noise_conf is not None:
             raise NotImplementedError("noise_conf is outside the statevector hot path")
         x, y, z = list(x or []), list(y or []), list(z or [])
+        for i in x + y + z:  # validate before anything is mutated
+            if not -self._nqubits <= int(i) < self._nqubits:
+                raise ValueError("qubit index %d out of range" % i)
+        if shots is None and readout_error is None:
+            # exact value: the rotated Z string IS the original Pauli string -- no rotation, no
+            # mutation of the cached state, and the query stays differentiable
+            r = self.expectation_ps(x=x, y=y, z=z)
+            return r.real if is_batched(r) else np.real(r)
         n_ops, n_qir = len(self._ops), len(self._qir)
         self._ensure_state()
+        done: List[Tuple[str, int]] = []  # rotations that actually reached the record
         try:
             for i in x:
                 self.h(i)
+                done.append(("h", i))
             for i in y:
                 self.rx(i, theta=np.pi / 2)
-            if shots is None:
-                if readout_error is None:
-                    r = self.expectation_ps(z=x + y + z)
-                    r = r.real if is_batched(r) else np.real(r)
-                else:  # sum_e p'_e (-1)^{bits}: the same diagonal string on the noisy distribution
-                    _, sign, _ = self._pauli_masks([], [], x + y + z)
-                    rs = self._readout_state(readout_error)
-                    r = float(np.real(rs.expectation_terms([0], [sign], [0])[0, 0]))
+                done.append(("rx", i))
+            if shots is None:  # sum_e p'_e (-1)^{bits}: the diagonal string on the noisy distribution
+                _, sign, _ = self._pauli_masks([], [], x + y + z)
+                rs = self._readout_state(readout_error)
+                r = float(np.real(rs.expectation_terms([0], [sign], [0])[0, 0]))
             else:
                 s = self.sample(batch=int(shots), allow_state=True, readout_error=readout_error, random_generator=random_generator,
                                 status=status, format="sample_bin")
                 r = correlation_from_samples(x + y + z, np.asarray(s), self._nqubits)
         finally:
-            # undo the basis rotation on the device state and drop it from the record
-            for i in reversed(y):
-                self.rx(i, theta=-np.pi / 2)
-            for i in reversed(x):
-                self.h(i)
-            self._ensure_state()
-            del self._ops[n_ops:]
-            del self._qir[n_qir:]
-            self._applied = n_ops
+            try:
+                # undo exactly the rotations that were applied to the device state
+                applied = self._applied - n_ops  # gates of `done` already executed on the device
+                for name, i in reversed(done[:max(0, applied)]):
+                    if name == "h":
+                        self.h(i)
+                    else:
+                        self.rx(i, theta=-np.pi / 2)
+                if applied > 0:
+                    # run only the inverses: the not-yet-applied forward rotations are dropped
+                    pending = self._ops[n_ops + len(done):]
+                    st = self._state
+                    blocks = self._fuse(pending, self._ntot)
+                    if self.use_passes and hasattr(st, "apply_planned"):
+                        st.apply_planned(blocks)
+                    else:
+                        st.apply_blocks(blocks)
+            finally:
+                del self._ops[n_ops:]
+                del self._qir[n_qir:]
+                self._applied = n_ops
         return r
 
     sexpps = sample_expectation_ps

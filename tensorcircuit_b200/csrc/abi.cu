@@ -30,9 +30,9 @@ int cuda_fail(cudaError_t e, const char* what) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // -------------------------------------------------------------------------------------------
-int make_geom_hi(int nbits, int tile_bits, int n_hi, const int* tile_hi, TileGeom* g) {
+int make_geom_hi(int nbits, int tile_bits, int n_hi, const int* tile_hi, TileGeom* g, int max_hi) {
     if (nbits < 1 || nbits > 62) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
-    if (n_hi < 0 || n_hi > 8) return fail(TCB200_ERR_ARG, "n_hi=%d out of range", n_hi);
+    if (n_hi < 0 || n_hi > max_hi) return fail(TCB200_ERR_ARG, "n_hi=%d out of range (max %d)", n_hi, max_hi);
     memset(g, 0, sizeof(*g));
     g->n = nbits;
     if (nbits <= tile_bits) {  // whole vector is one tile

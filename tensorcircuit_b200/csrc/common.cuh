@@ -189,7 +189,8 @@ struct TileGeom {
     int T;      // log2(tile amplitudes)
     int h;      // gathered high bits
     int lrow;   // T - h: log2(row length)
-    int hb[8];  // ascending
+    int hb[10];  // ascending (the kernels with a shared-memory row table take h <= 8; the gate pass's
+                 // production shape addresses rows through host constants and takes 9)
 };
 
 TCB_HD uint64_t tile_base(const TileGeom& g, uint64_t t) {
@@ -889,7 +890,7 @@ TCB_HD uint64_t tma_box_offset(const TmaPlan& tp, uint32_t c) {
 // fall into the contiguous low part.  Returns <0 on error.
 int make_geom(int nbits, int tile_bits, int k, const int* bits, TileGeom* g);
 // Tile with explicitly requested gathered bits.
-int make_geom_hi(int nbits, int tile_bits, int n_hi, const int* tile_hi, TileGeom* g);
+int make_geom_hi(int nbits, int tile_bits, int n_hi, const int* tile_hi, TileGeom* g, int max_hi = 8);
 // Fill the GroupMap for a block with the given ascending global bits inside geometry g.
 int make_group_map(const TileGeom& g, int apu, int k, const int* bits, GroupMap* gm, int swz_mode = SWZ_SW);
 // Persistent TMA pipeline for a multi-block pass (tpass.cu).  0: launched; > 0: not eligible

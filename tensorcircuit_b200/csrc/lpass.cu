@@ -432,7 +432,10 @@ int fill_lpass(LPassParams<Real>& q, LPassInfo& info, void* state, int nbits, in
     q.state = static_cast<C*>(state);
     const int tile_bits = pass_tile_bits(sizeof(Real) == 4 ? TCB200_C64 : TCB200_C128);
     if (tile_bits > LP_MAX_T) return fail(TCB200_ERR_UNSUPPORTED, "pass tile of 2^%d amplitudes exceeds the gate-pass limit 2^%d", tile_bits, LP_MAX_T);
-    int rc = make_geom_hi(nbits, tile_bits, nbits <= tile_bits ? 0 : n_hi, tile_hi, &q.g);
+    // 9 gathered bits (128-byte rows of complex64) only in the production shape, whose staging does
+    // not go through the 256-entry shared-memory row table
+    const bool fast_shape = nbits > tile_bits && tile_bits - (sizeof(C) == 8 ? 1 : 0) == 12;
+    int rc = make_geom_hi(nbits, tile_bits, nbits <= tile_bits ? 0 : n_hi, tile_hi, &q.g, fast_shape ? 9 : 8);
     if (rc) return rc;
     if (q.g.T < LP_RB) return fail(TCB200_ERR_UNSUPPORTED, "gate pass needs a state of at least %d bits", LP_RB);
     Scheduler<Real> s;

@@ -149,6 +149,9 @@ class DeviceState:
     # (vmap) matrices and states below 4 qubits.
     use_gate_pass = os.environ.get("TCB200_GATE_PASS", "1") != "0"
     gate_pass_max_ops = int(os.environ.get("TCB200_GATE_PASS_MAX_OPS", "200"))
+    # gathered bits of a gate pass: 9 (128-byte rows for complex64) only in the production shape
+    # (state larger than one 64 KiB tile), 8 otherwise
+    gate_pass_max_hi = int(os.environ.get("TCB200_GATE_PASS_MAX_HI", "9"))
 
     def apply_planned(self, blocks: Sequence[Block]) -> int:
         """Run ``blocks`` as staged passes (fusion.plan_passes): each pass is one HBM read + write
@@ -183,7 +186,8 @@ class DeviceState:
         through the single-block kernel."""
         cost = [0 if b.kind == KIND_PERM else (4 ** len(b.bits) if b.kind == KIND_DENSE else 16) for b in blocks]
         weight = [0.0 if b.kind == KIND_PERM else 1.0 for b in blocks]
-        passes = plan_passes([b.bits for b in blocks], self.nbits, T, max_hi=self.pass_max_hi, max_ops=self.gate_pass_max_ops,
+        max_hi = min(self.gate_pass_max_hi, 9 if (self.nbits > T and T - (1 if self.amp_bytes == 8 else 0) == 12) else 8)
+        passes = plan_passes([b.bits for b in blocks], self.nbits, T, max_hi=max_hi, max_ops=self.gate_pass_max_ops,
                              max_mat_elems=_lib.GATE_PASS_MAT_ELEMS, max_pass_k=4, block_cost=cost, block_weight=weight)
         nlaunch = 0
         for p in passes:

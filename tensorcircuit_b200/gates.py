@@ -250,8 +250,13 @@ def _s(v: Any) -> Any:
     """scalar parameter -> complex scalar or batched scalar that broadcasts against matrices"""
     v = num_to_tensor(v)
     if is_batched(v):
-        return v.reshape([1, 1]) if v.ndim == 0 else v
-    return v.reshape(()) if v.size == 1 else v
+        if v.size != 1:
+            raise ValueError("gate parameter must be a scalar per batch element, got shape %r" % (tuple(v.shape),))
+        return v.reshape([1, 1])
+    if v.size != 1:
+        # a vector angle would broadcast silently into a non-unitary matrix (n == 2) or fail later
+        raise ValueError("gate parameter must be a scalar, got shape %r" % (tuple(np.shape(v)),))
+    return v.reshape(())
 
 
 def phase_gate(theta: float = 0) -> Gate:

@@ -49,11 +49,27 @@ def example_block(c: Circuit, param: Tensor, nlayers: int = 2, is_split: bool = 
     return c
 
 
+def _sizen(x: Any) -> int:
+    """number of entries as user code sees them (a vmap batch axis does not count)"""
+    sh = x.shape if hasattr(x, "shape") else np.shape(x)
+    return int(np.prod(sh, dtype=np.int64)) if len(sh) else 1
+
+
 def QAOA_block(c: Circuit, g: Any, paramzz: Tensor, paramx: Tensor, **kws: Any) -> Circuit:
-    """blocks.py:84-110: exp(-i paramzz w_ij Z_i Z_j) on graph edges, then rx(paramx) on nodes."""
+    """blocks.py:84-110: exp(-i theta Z_i Z_j) on graph edges, then rx on nodes.  A single angle is
+    shared by all edges (scaled by the edge weight) / all nodes; otherwise edge i takes
+    paramzz[i] and node i takes paramx[i], as in the reference."""
     zz = np.kron(np.diag([1.0, -1.0]), np.diag([1.0, -1.0]))
-    for e1, e2 in g.edges:
-        c.exp1(e1, e2, unitary=zz, theta=paramzz * g[e1][e2].get("weight", 1.0), **kws)
-    for n in g.nodes:
-        c.rx(n, theta=paramx)
+    if _sizen(paramzz) == 1:
+        for e1, e2 in g.edges:
+            c.exp1(e1, e2, unitary=zz, theta=paramzz * g[e1][e2].get("weight", 1.0), **kws)
+    else:
+        for i, (e1, e2) in enumerate(g.edges):
+            c.exp1(e1, e2, unitary=zz, theta=paramzz[i], **kws)
+    if _sizen(paramx) == 1:
+        for n in g.nodes:
+            c.rx(n, theta=paramx)
+    else:
+        for i, n in enumerate(g.nodes):
+            c.rx(n, theta=paramx[i])
     return c

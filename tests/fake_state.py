@@ -69,6 +69,7 @@ class FakeState:
     pass_max_hi = 6
     use_gate_pass = True
     gate_pass_max_ops = 200
+    gate_pass_max_hi = 6
     apply_gate_pass = engine.DeviceState.apply_gate_pass
     _apply_gate_planned = engine.DeviceState._apply_gate_planned
 

@@ -1121,3 +1121,119 @@ def test_value_and_grad_has_aux_and_shared_parameter(eng):
     h = 1e-6
     fd = [(want(t + h * np.eye(2)[k]) - want(t - h * np.eye(2)[k])) / (2 * h) for k in range(2)]
     np.testing.assert_allclose(g, fd, atol=3e-5)
+
+
+def test_value_and_grad_sample_expectation_two_bases(eng, highp):
+    """queries on the same circuit in different measurement bases must not share a shifted
+    simulation (advisor finding: the group key was (id(circ), len(ops)))"""
+    import gc
+
+    K = tc.backend
+
+    def f(t):
+        c = tc.Circuit(3)
+        for i in range(3):
+            c.ry(i, theta=t[i])
+            c.rz(i, theta=t[3 + i])
+        c.cnot(0, 1)
+        c.cnot(1, 2)
+        e = c.sample_expectation_ps(x=[0]) + 2.0 * c.sample_expectation_ps(y=[0]) + 0.5 * c.sample_expectation_ps(x=[1])
+        gc.collect()
+        return e
+
+    def want(t):
+        o = OracleCircuit(3)
+        for i in range(3):
+            o.ry(i, theta=t[i])
+            o.rz(i, theta=t[3 + i])
+        o.cnot(0, 1)
+        o.cnot(1, 2)
+        return (o.expectation_ps(x=[0]) + 2.0 * o.expectation_ps(y=[0]) + 0.5 * o.expectation_ps(x=[1])).real
+
+    t = np.array([0.3, 0.7, 1.1, 0.5, 0.2, 0.9])
+    v, g = K.value_and_grad(f)(t)
+    np.testing.assert_allclose(v, want(t), atol=1e-9)
+    h = 1e-6
+    fd = [(want(t + h * np.eye(6)[k]) - want(t - h * np.eye(6)[k])) / (2 * h) for k in range(6)]
+    np.testing.assert_allclose(g, fd, atol=2e-6)
+
+
+def test_value_and_grad_subcircuits_in_a_loop(eng, highp):
+    """several circuits built (and dropped) inside the loss: object ids may be reused"""
+    import gc
+
+    K = tc.backend
+
+    def f(t):
+        e = 0.0
+        for k in range(3):
+            c = tc.Circuit(2)
+            c.rx(0, theta=t[k])
+            c.cnot(0, 1)
+            c.ry(1, theta=t[(k + 1) % 3])
+            e = e + (k + 1) * K.real(c.expectation_ps(z=[1]))
+            del c
+            gc.collect()
+        return e
+
+    def want(t):
+        e = 0.0
+        for k in range(3):
+            o = OracleCircuit(2)
+            o.rx(0, theta=t[k])
+            o.cnot(0, 1)
+            o.ry(1, theta=t[(k + 1) % 3])
+            e += (k + 1) * o.expectation_ps(z=[1]).real
+        return e
+
+    t = np.array([0.4, 1.3, 0.8])
+    v, g = K.value_and_grad(f)(t)
+    np.testing.assert_allclose(v, want(t), atol=1e-9)
+    h = 1e-6
+    fd = [(want(t + h * np.eye(3)[k]) - want(t - h * np.eye(3)[k])) / (2 * h) for k in range(3)]
+    np.testing.assert_allclose(g, fd, atol=2e-6)
+
+
+def test_qaoa_block_per_edge_parameters(eng):
+    """templates/blocks.py:84-110: vector paramzz / paramx index edges / nodes"""
+    import networkx as nx
+
+    g = nx.Graph()
+    g.add_edge(0, 1, weight=1.0)
+    g.add_edge(1, 2, weight=2.0)
+    pz, px = np.array([0.3, 0.8]), np.array([0.2, 0.5, 0.9])
+    c = tc.Circuit(3)
+    for i in range(3):
+        c.h(i)
+    tc.templates.blocks.QAOA_block(c, g, pz, px)
+    o = OracleCircuit(3)
+    for i in range(3):
+        o.h(i)
+    zz = np.kron(np.diag([1.0, -1.0]), np.diag([1.0, -1.0]))
+    for i, (a, b) in enumerate(g.edges):
+        o.exp1(a, b, unitary=zz, theta=pz[i])
+    for i, nd in enumerate(g.nodes):
+        o.rx(nd, theta=px[i])
+    np.testing.assert_allclose(A(c.state()), o.state(), atol=1e-6)
+    # a shared scalar angle is scaled by the edge weight
+    c2 = tc.Circuit(3)
+    tc.templates.blocks.QAOA_block(c2, g, 0.4, 0.7)
+    o2 = OracleCircuit(3)
+    for a, b in g.edges:
+        o2.exp1(a, b, unitary=zz, theta=0.4 * g[a][b]["weight"])
+    for nd in g.nodes:
+        o2.rx(nd, theta=0.7)
+    np.testing.assert_allclose(A(c2.state()), o2.state(), atol=1e-6)
+    with pytest.raises(ValueError):
+        tc.Circuit(2).rx(0, theta=np.array([0.1, 0.2]))
+
+
+def test_sample_expectation_ps_bad_index_leaves_record_clean(eng):
+    c = tc.Circuit(3)
+    c.h(0)
+    c.cnot(0, 1)
+    n_ops, n_qir = len(c._ops), len(c._qir)
+    with pytest.raises(ValueError):
+        c.sample_expectation_ps(x=[0, 7], shots=16, status=np.random.default_rng(0).random(16))
+    assert len(c._ops) == n_ops and len(c._qir) == n_qir
+    np.testing.assert_allclose(c.sample_expectation_ps(x=[0, 1]), 1.0, atol=1e-6)
