@@ -21,6 +21,7 @@ from . import cons, gates
 from .batching import BatchArray, batch_of, is_batched
 from .fusion import GateOp, fuse, fuse_structured
 from .gates import Gate
+from .lazy import LazyScalar, TermPool
 from .quantum import correlation_from_samples, ps2xyz, sample2all, sample_int2bin
 
 Tensor = Any
@@ -150,6 +151,7 @@ class Circuit:
         self._state = None  # DeviceState
         self._applied = 0
         self._batch: Optional[int] = None
+        self._pool: Optional[TermPool] = None  # expectation terms registered on the current state (lazy.py)
         self.state_tensor = None  # kept for source compatibility (basecircuit.py:245)
 
     # ------------------------------------------------------------------------------------
@@ -171,6 +173,7 @@ class Circuit:
             ir_dict.update(gate_dict)
         else:
             ir_dict = gate_dict
+        self._close_pool()  # pending expectation terms belong to the state before this gate
         self._qir.append(ir_dict)
         assert len(index) == len(set(index))
         index = tuple([i if i >= 0 else self._nqubits + i for i in index])
@@ -369,8 +372,21 @@ class Circuit:
             s[d["name"]] = s.get(d["name"], 0) + 1
         return s
 
+    def _close_pool(self) -> None:
+        """Evaluate the expectation terms registered so far (one launch group) and start afresh:
+        called whenever the state is about to change."""
+        if self._pool is not None:
+            self._pool.flush()
+            self._pool.closed = True
+            self._pool = None
+
+    # Deferred evaluation of expectation_ps on unbatched circuits (lazy.py): a Python loop over
+    # the terms of a Hamiltonian costs one launch group instead of one launch + sync per term.
+    lazy_expectation = True
+
     def replace_inputs(self, inputs: Tensor) -> None:
         """basecircuit.py:805-822: same circuit, new initial state."""
+        self._close_pool()
         self.inputs = inputs
         self._state = None
         self._applied = 0
@@ -505,7 +521,11 @@ class Circuit:
             d = ps2xyz(list(ps))
             x, y, z = d.get("x"), d.get("y"), d.get("z")
         fl, sg, ny = self._pauli_masks(x or [], y or [], z or [])
-        st = self._ensure_state()
+        st = self._ensure_state()  # (a state hook may turn the circuit into a batched one: autodiff replays)
+        if self._batch is None and self.lazy_expectation:
+            if self._pool is None:
+                self._pool = TermPool(self)
+            return LazyScalar([(self._pool, self._pool.add(fl, sg, ny), 1.0 + 0.0j)], 0j, "c", self._dtype)
         r = st.expectation_terms([fl], [sg], [ny])
         if self._batch is None:
             return _np_scalar(r[0, 0], self._dtype)

@@ -1237,3 +1237,52 @@ def test_sample_expectation_ps_bad_index_leaves_record_clean(eng):
         c.sample_expectation_ps(x=[0, 7], shots=16, status=np.random.default_rng(0).random(16))
     assert len(c._ops) == n_ops and len(c._qir) == n_qir
     np.testing.assert_allclose(c.sample_expectation_ps(x=[0, 1]), 1.0, atol=1e-6)
+
+
+def test_expectation_ps_loop_is_coalesced(eng):
+    """The reference idiom -- a Python loop over c.expectation_ps (examples/vqe_parallel_pmap.py:
+    28-34) -- evaluates all its terms in ONE group when the energy is finally read (lazy.py)."""
+    K = tc.backend
+    n = 8
+    rng = np.random.default_rng(3)
+    th = rng.uniform(0, 2 * np.pi, size=(2, n))
+
+    def build(cls):
+        c = cls(n)
+        for i in range(n):
+            c.ry(i, theta=th[0, i])
+        for i in range(n - 1):
+            c.cnot(i, i + 1)
+        for i in range(n):
+            c.rx(i, theta=th[1, i])
+        return c
+
+    c = build(tc.Circuit)
+    st = c._ensure_state()
+    calls = []
+    orig = st.expectation_terms
+    st.expectation_terms = lambda fl, sg, ny: (calls.append(len(fl)), orig(fl, sg, ny))[1]
+    e = 0.0
+    for i in range(n):
+        e += -1.0 * c.expectation_ps(x=[i])
+    for i in range(n - 1):
+        e = e + c.expectation_ps(z=[i, i + 1]) * 0.5
+    e = K.real(e) / 2
+    assert calls == []  # nothing evaluated yet
+    o = build(OracleCircuit)
+    want = (sum(-o.expectation_ps(x=[i]).real for i in range(n)) + 0.5 * sum(o.expectation_ps(z=[i, i + 1]).real for i in range(n - 1))) / 2
+    np.testing.assert_allclose(float(e), want, atol=2e-5)
+    assert calls == [2 * n - 1]  # one group for all terms
+    # a value read before further gates stays valid; the new gate flushes what is pending
+    a = c.expectation_ps(z=[0])
+    c.x(0)
+    b = c.expectation_ps(z=[0])
+    np.testing.assert_allclose(float(np.real(a)), o.expectation_ps(z=[0]).real, atol=2e-5)
+    np.testing.assert_allclose(float(np.real(b)), -o.expectation_ps(z=[0]).real, atol=2e-5)
+    # eager mode agrees term by term
+    c2 = build(tc.Circuit)
+    c2.lazy_expectation = False
+    v = c2.expectation_ps(x=[1], z=[2])
+    assert isinstance(v, np.ndarray)
+    np.testing.assert_allclose(v, o.expectation_ps(x=[1], z=[2]), atol=2e-5)
+    np.testing.assert_allclose(build(tc.Circuit).expectation_ps(x=[1], z=[2]), v, atol=1e-7)
