@@ -188,6 +188,20 @@ int tcb200_apply_gate_pass(void* state, int nbits, int dtype, int nops, const in
                            const int* ops_bits, const double* ops_mats, int n_hi,
                            const int* tile_hi, int64_t batch, double* info8, void* stream);
 
+/*
+ * The same gate pass for backend.vmap (tensorcircuit/backends/jax_backend.py:718-730): gate i
+ * carries either one matrix shared by the batch (ops_batched[i] == 0) or one per batch element
+ * (ops_batched[i] != 0: ops_mats holds [batch][4^k] for it).  Classification uses the union of
+ * the non-zero patterns over the batch, so one schedule serves every element; batch element b
+ * (grid.y) reads its own matrices from `workspace` (DEVICE, tcb200_gate_pass_batched_workspace_bytes),
+ * which the call fills through pinned staging on `stream`.
+ */
+size_t tcb200_gate_pass_batched_workspace_bytes(int dtype, int64_t batch);
+int tcb200_apply_gate_pass_batched(void* state, int nbits, int dtype, int nops, const int* ops_k,
+                                   const int* ops_bits, const double* ops_mats, const int* ops_batched,
+                                   int n_hi, const int* tile_hi, int64_t batch, void* workspace,
+                                   size_t ws_bytes, double* info8, void* stream);
+
 /* Host-only dry run of the gate-pass scheduler (no device work): fills info8 as above. */
 int tcb200_gate_pass_info(int nbits, int dtype, int nops, const int* ops_k, const int* ops_bits,
                           const double* ops_mats, int n_hi, const int* tile_hi, double* info8);

@@ -57,6 +57,8 @@ def _load() -> ctypes.CDLL:
         "tcb200_apply_pass": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_void_p, c_int64, c_int, POINTER(c_int), c_int64, c_void_p]),
         "tcb200_apply_pass_host": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_double), c_int, POINTER(c_int), c_int64, c_void_p]),
         "tcb200_apply_gate_pass": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_double), c_int, POINTER(c_int), c_int64, POINTER(c_double), c_void_p]),
+        "tcb200_gate_pass_batched_workspace_bytes": (c_size_t, [c_int, c_int64]),
+        "tcb200_apply_gate_pass_batched": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_double), POINTER(c_int), c_int, POINTER(c_int), c_int64, c_void_p, c_size_t, POINTER(c_double), c_void_p]),
         "tcb200_gate_pass_info": (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_double), c_int, POINTER(c_int), POINTER(c_double)]),
         "tcb200_apply_rpass_host": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_double), c_int, POINTER(c_int), c_int64, c_void_p]),
         "tcb200_pass_tile_bits": (c_int, [c_int]),
@@ -88,7 +90,7 @@ lib = _load()
 EXPORTS = [
     "tcb200_version", "tcb200_last_error", "tcb200_launch_count", "tcb200_tma_pass_count", "tcb200_init_zero", "tcb200_load_c128",
     "tcb200_set_zero", "tcb200_copy_rows",
-    "tcb200_apply_dense", "tcb200_apply_dense_batched", "tcb200_apply_diag", "tcb200_apply_pass", "tcb200_apply_pass_host", "tcb200_apply_rpass_host", "tcb200_apply_gate_pass", "tcb200_gate_pass_info",
+    "tcb200_apply_dense", "tcb200_apply_dense_batched", "tcb200_apply_diag", "tcb200_apply_pass", "tcb200_apply_pass_host", "tcb200_apply_rpass_host", "tcb200_apply_gate_pass", "tcb200_gate_pass_info", "tcb200_gate_pass_batched_workspace_bytes", "tcb200_apply_gate_pass_batched",
     "tcb200_pass_tile_bits", "tcb200_norm2", "tcb200_reduce_workspace_bytes", "tcb200_masked_norm2_workspace_bytes", "tcb200_masked_norm2", "tcb200_probability_state", "tcb200_probability",
     "tcb200_expect_pauli", "tcb200_expect_workspace_bytes", "tcb200_expect_tile_bits",
     "tcb200_expect_z_max_terms", "tcb200_expect_z_min_bits", "tcb200_expect_z_workspace_bytes", "tcb200_expect_z", "tcb200_sample",

@@ -28,16 +28,24 @@ enum { GK_DENSE = 0, GK_DIAG = 1, GK_LIN = 2 };
 struct GOp {
     int kind;
     int k;
+    int bm;             // matrices held: 1 (shared by the batch) or the batch size (vmap)
     int lb[4];          // logical tile bit of matrix index bit j
-    std::vector<cd> m;  // dense: D*D row-major; diag: D
+    std::vector<cd> m;  // per held matrix -- dense: D*D row-major; diag: D
     int linv[4];        // lin: L^{-1} e_i as k-bit masks (the inverse map is y -> L^{-1} y ^ cinv)
     int cinv;
 };
 
-// split one input gate into classified ops (appended to `out`); < 0 on error
-int classify(int k, const int* lb, const double* mat, std::vector<GOp>& out) {
+// split one input gate into classified ops (appended to `out`); < 0 on error.  `mat` holds bm
+// matrices (bm > 1: one per vmap batch element); the class is that of the union of their
+// non-zero patterns, so that one schedule serves the whole batch.
+int classify(int k, const int* lb, const double* mat, int bm, std::vector<GOp>& out) {
     const int D = 1 << k;
-    auto M = [&](int i, int j) { return cd(mat[2 * (i * D + j)], mat[2 * (i * D + j) + 1]); };
+    auto M = [&](int b, int i, int j) { return cd(mat[2 * (((size_t)b * D + i) * D + j)], mat[2 * (((size_t)b * D + i) * D + j) + 1]); };
+    auto any_nz = [&](int i, int j) {
+        for (int b = 0; b < bm; ++b)
+            if (M(b, i, j) != cd(0, 0)) return true;
+        return false;
+    };
     // monomial?  (exact zeros: gate matrices are built analytically on the host)
     std::vector<int> perm(D, -1);
     bool mono = true;
@@ -45,7 +53,7 @@ int classify(int k, const int* lb, const double* mat, std::vector<GOp>& out) {
     for (int j = 0; j < D && mono; ++j) {
         int cnt = 0, at = -1;
         for (int i = 0; i < D; ++i)
-            if (M(i, j) != cd(0, 0)) {
+            if (any_nz(i, j)) {
                 ++cnt;
                 at = i;
             }
@@ -59,7 +67,8 @@ int classify(int k, const int* lb, const double* mat, std::vector<GOp>& out) {
         bool ident = true, allone = true;
         for (int j = 0; j < D; ++j) {
             if (perm[j] != j) ident = false;
-            if (M(perm[j], j) != cd(1, 0)) allone = false;
+            for (int b = 0; b < bm; ++b)
+                if (M(b, perm[j], j) != cd(1, 0)) allone = false;
         }
         bool affine = false;
         int lcol[4] = {0, 0, 0, 0};
@@ -80,15 +89,18 @@ int classify(int k, const int* lb, const double* mat, std::vector<GOp>& out) {
                 GOp g;
                 g.kind = GK_DIAG;
                 g.k = k;
+                g.bm = bm;
                 for (int i = 0; i < k; ++i) g.lb[i] = lb[i];
-                g.m.resize(D);
-                for (int j = 0; j < D; ++j) g.m[j] = M(perm[j], j);
+                g.m.resize((size_t)bm * D);
+                for (int b = 0; b < bm; ++b)
+                    for (int j = 0; j < D; ++j) g.m[(size_t)b * D + j] = M(b, perm[j], j);
                 out.push_back(g);
             }
             if (!ident) {
                 GOp g;
                 g.kind = GK_LIN;
                 g.k = k;
+                g.bm = 1;
                 for (int i = 0; i < k; ++i) g.lb[i] = lb[i];
                 std::vector<int> inv(D);
                 for (int j = 0; j < D; ++j) inv[perm[j]] = j;
@@ -103,10 +115,12 @@ int classify(int k, const int* lb, const double* mat, std::vector<GOp>& out) {
     GOp g;
     g.kind = GK_DENSE;
     g.k = k;
+    g.bm = bm;
     for (int i = 0; i < k; ++i) g.lb[i] = lb[i];
-    g.m.resize(D * D);
-    for (int i = 0; i < D; ++i)
-        for (int j = 0; j < D; ++j) g.m[i * D + j] = M(i, j);
+    g.m.resize((size_t)bm * D * D);
+    for (int b = 0; b < bm; ++b)
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) g.m[((size_t)b * D + i) * D + j] = M(b, i, j);
     out.push_back(g);
     return 0;
 }
@@ -137,6 +151,8 @@ struct LPassParams {
     int ngb;     // group-index bits: T - LP_RB
     int nrounds;
     int fast;    // production shape: 256 threads, 16 staging units per thread (LStage valid)
+    const ME<Real>* bmats;  // vmap: DEVICE [batch][bstride] matrix elements (nullptr: shared matrices in m[])
+    int bstride;
     LOut out;
     LStage stage;
     LRound r[LP_MAX_ROUNDS];
@@ -147,8 +163,7 @@ template <typename Real>
 void put_elem(ME<Real>& e, cd z);
 template <>
 void put_elem<float>(ME<float>& e, cd z) {
-    e.re = (float)z.real();
-    e.pad = 0.f;
+    e.re = e.pad = (float)z.real();  // (re, re, im, im): both FFMA2 operand pairs as loaded
     e.im0 = e.im1 = (float)z.imag();
 }
 template <>
@@ -173,6 +188,14 @@ struct Scheduler {
     LPassParams<Real>* q = nullptr;
     LPassInfo info;
     int nmat = 0;
+    int batch = 1;                 // > 1: per-element matrices go to `blob` ([batch][LP_MAT_ELEMS])
+    ME<Real>* blob = nullptr;
+
+    // element `idx` of the parameter bank, for batch element b
+    void put(int idx, int b, cd z) {
+        if (blob) put_elem<Real>(blob[(size_t)b * LP_MAT_ELEMS + idx], z);
+        else put_elem<Real>(q->m[idx], z);
+    }
 
     void init_layout() {
         for (int t = 0; t < T; ++t) {
@@ -298,31 +321,34 @@ struct Scheduler {
         // ---- micro-ops ----
         int nc = 0;
         int last_dg = -1;  // matrix offset of a diagonal table the next diagonal op can merge into
-        cd dgtab[16];
+        const int nb = blob ? batch : 1;
+        std::vector<cd> dgtab((size_t)nb * 16);
         for (int oi : members) {
             const GOp& g = ops[oi];
             int pos[4];
             for (int j = 0; j < g.k; ++j) pos[j] = (int)(std::find(R.begin(), R.end(), g.lb[j]) - R.begin());
             if (g.kind == GK_DIAG) {
-                cd tab[16];
-                for (int x = 0; x < 16; ++x) {
+                const int D = 1 << g.k;
+                auto entry = [&](int b, int x) {
                     int idx = 0;
                     for (int j = 0; j < g.k; ++j) idx |= ((x >> pos[j]) & 1) << j;
-                    tab[x] = g.m[idx];
-                }
+                    return g.m[(size_t)(g.bm > 1 ? b : 0) * D + idx];
+                };
                 if (last_dg >= 0) {  // consecutive diagonal ops: one table (product kept in double)
-                    for (int x = 0; x < 16; ++x) {
-                        dgtab[x] *= tab[x];
-                        put_elem<Real>(q->m[last_dg + x], dgtab[x]);
-                    }
+                    for (int b = 0; b < nb; ++b)
+                        for (int x = 0; x < 16; ++x) {
+                            dgtab[(size_t)b * 16 + x] *= entry(b, x);
+                            put(last_dg + x, b, dgtab[(size_t)b * 16 + x]);
+                        }
                     continue;
                 }
                 if (nmat + 16 > LP_MAT_ELEMS) return fail(TCB200_ERR_CAPACITY, "gate pass matrices exceed the parameter bank");
                 if (nc >= LP_MAX_CODES) return fail(TCB200_ERR_CAPACITY, "more than %d micro-ops in a round", LP_MAX_CODES);
-                for (int x = 0; x < 16; ++x) {
-                    dgtab[x] = tab[x];
-                    put_elem<Real>(q->m[nmat + x], tab[x]);
-                }
+                for (int b = 0; b < nb; ++b)
+                    for (int x = 0; x < 16; ++x) {
+                        dgtab[(size_t)b * 16 + x] = entry(b, x);
+                        put(nmat + x, b, dgtab[(size_t)b * 16 + x]);
+                    }
                 r.code[nc++] = LOP_DG | ((uint32_t)nmat << 8);
                 last_dg = nmat;
                 nmat += 16;
@@ -343,8 +369,11 @@ struct Scheduler {
             };
             if (nmat + D * D > LP_MAT_ELEMS) return fail(TCB200_ERR_CAPACITY, "gate pass matrices exceed the parameter bank");
             if (nc >= LP_MAX_CODES) return fail(TCB200_ERR_CAPACITY, "more than %d micro-ops in a round", LP_MAX_CODES);
-            for (int i = 0; i < D; ++i)
-                for (int j = 0; j < D; ++j) put_elem<Real>(q->m[nmat + i * D + j], g.m[remap(i) * D + remap(j)]);
+            for (int b = 0; b < nb; ++b) {
+                const cd* gm = g.m.data() + (size_t)(g.bm > 1 ? b : 0) * D * D;
+                for (int i = 0; i < D; ++i)
+                    for (int j = 0; j < D; ++j) put(nmat + i * D + j, b, gm[remap(i) * D + remap(j)]);
+            }
             uint32_t opc = 0;
             const int p0 = pos[srt[0]], p1 = k > 1 ? pos[srt[1]] : 0, p2 = k > 2 ? pos[srt[2]] : 0;
             if (k == 1) opc = LOP_G1 + (uint32_t)p0;
@@ -427,9 +456,12 @@ struct Scheduler {
 // parameter block of one gate pass; 0 on success
 template <typename Real>
 int fill_lpass(LPassParams<Real>& q, LPassInfo& info, void* state, int nbits, int nops, const int* ops_k, const int* ops_bits,
-               const double* mats, int n_hi, const int* tile_hi) {
+               const double* mats, int n_hi, const int* tile_hi, const int* ops_batched = nullptr, int batch = 1,
+               ME<Real>* blob = nullptr) {
     using C = typename CT<Real>::type;
     q.state = static_cast<C*>(state);
+    q.bmats = nullptr;
+    q.bstride = 0;
     const int tile_bits = pass_tile_bits(sizeof(Real) == 4 ? TCB200_C64 : TCB200_C128);
     if (tile_bits > LP_MAX_T) return fail(TCB200_ERR_UNSUPPORTED, "pass tile of 2^%d amplitudes exceeds the gate-pass limit 2^%d", tile_bits, LP_MAX_T);
     // 9 gathered bits (128-byte rows of complex64) only in the production shape, whose staging does
@@ -443,6 +475,8 @@ int fill_lpass(LPassParams<Real>& q, LPassInfo& info, void* state, int nbits, in
     s.q = &q;
     memset(&s.info, 0, sizeof(s.info));
     s.init_layout();
+    s.batch = batch;
+    s.blob = blob;
     const int* b = ops_bits;
     const double* mp = mats;
     for (int o = 0; o < nops; ++o) {
@@ -455,10 +489,11 @@ int fill_lpass(LPassParams<Real>& q, LPassInfo& info, void* state, int nbits, in
             lb[i] = local_bit(q.g, b[i]);
             if (lb[i] < 0) return fail(TCB200_ERR_ARG, "bit %d is not inside the tile", b[i]);
         }
-        rc = classify(k, lb, mp, s.ops);
+        const int bm = (ops_batched && ops_batched[o]) ? batch : 1;
+        rc = classify(k, lb, mp, bm, s.ops);
         if (rc) return rc;
         b += k;
-        mp += 2ll << (2 * k);
+        mp += (size_t)bm * (2ll << (2 * k));
     }
     q.nrounds = 0;
     q.ngb = q.g.T - LP_RB;
@@ -499,8 +534,10 @@ int fill_lpass(LPassParams<Real>& q, LPassInfo& info, void* state, int nbits, in
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
-template <typename Real>
-__global__ void __launch_bounds__(256, sizeof(Real) == 4 ? 3 : 2) lpass_kernel(const __grid_constant__ LPassParams<Real> p) {
+// BATCHED (vmap): batch element blockIdx.y reads its own matrices from global memory
+// (p.bmats + blockIdx.y * p.bstride; warp-uniform, L1-resident loads) instead of the parameter bank
+template <typename Real, bool BATCHED>
+__global__ void __launch_bounds__(256, (sizeof(Real) == 4 && !BATCHED) ? 3 : 2) lpass_kernel(const __grid_constant__ LPassParams<Real> p) {
     using C = typename CT<Real>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     C* tile = reinterpret_cast<C*>(smem_raw);
@@ -517,7 +554,7 @@ __global__ void __launch_bounds__(256, sizeof(Real) == 4 ? 3 : 2) lpass_kernel(c
     __syncthreads();
     const bool worker = (tid >> p.tb) == 0;
     for (int r = 0; r < p.nrounds; ++r) {
-        if (worker) lround_thread<C, Real>(smem_raw, p.r[r], p.m, (uint32_t)tid, p.tb, p.ngb);
+        if (worker) lround_thread<C, Real>(smem_raw, p.r[r], BATCHED ? p.bmats + (size_t)blockIdx.y * p.bstride : p.m, (uint32_t)tid, p.tb, p.ngb);
         __syncthreads();
     }
     lstage_out_thread<C>(p.g, vec, base, smem_raw, rowoff, p.out, tid, nthr, p.stb);
@@ -525,8 +562,8 @@ __global__ void __launch_bounds__(256, sizeof(Real) == 4 ? 3 : 2) lpass_kernel(c
 
 // production shape (LPassParams::fast): 256 threads, one 64 KiB tile, host-precomputed staging
 // constants, compile-time loop structure -- no shared-memory row table, no per-unit index math
-template <typename Real>
-__global__ void __launch_bounds__(256, sizeof(Real) == 4 ? 3 : 2) lpass_fast_kernel(const __grid_constant__ LPassParams<Real> p) {
+template <typename Real, bool BATCHED>
+__global__ void __launch_bounds__(256, (sizeof(Real) == 4 && !BATCHED) ? 3 : 2) lpass_fast_kernel(const __grid_constant__ LPassParams<Real> p) {
     using C = typename CT<Real>::type;
     constexpr int NIT = sizeof(C) == 8 ? 2 : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -536,21 +573,57 @@ __global__ void __launch_bounds__(256, sizeof(Real) == 4 ? 3 : 2) lpass_fast_ker
     cp_async_wait_all();
     __syncthreads();
     for (int r = 0; r < p.nrounds; ++r) {
-        lround_thread_fast<C, Real, NIT>(smem_raw, p.r[r], p.m, tid);
+        lround_thread_fast<C, Real, NIT>(smem_raw, p.r[r], BATCHED ? p.bmats + (size_t)blockIdx.y * p.bstride : p.m, tid);
         __syncthreads();
     }
     lstage_out_fast<C>(p.stage, p.out, vec, smem_raw, tid);
 }
 
+// pinned staging + events for the per-element matrix blobs of batched passes (two buffers, so that
+// the host can fill the blob of pass i + 1 while the copy of pass i is still in flight)
+struct BlobStage {
+    void* host[2] = {nullptr, nullptr};
+    size_t cap[2] = {0, 0};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int next = 0;
+};
+
 template <typename Real>
 static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, const int* ops_bits, const double* mats, int n_hi,
-                        const int* tile_hi, int64_t batch, cudaStream_t st, LPassInfo* info_out) {
+                        const int* tile_hi, int64_t batch, cudaStream_t st, LPassInfo* info_out, const int* ops_batched = nullptr,
+                        void* workspace = nullptr, size_t ws_bytes = 0) {
     using C = typename CT<Real>::type;
     static thread_local LPassParams<Real>* tp = nullptr;
     if (!tp) tp = new LPassParams<Real>();
     LPassParams<Real>& q = *tp;
     LPassInfo info;
-    int rc = fill_lpass<Real>(q, info, state, nbits, nops, ops_k, ops_bits, mats, n_hi, tile_hi);
+    bool batched = false;
+    if (ops_batched)
+        for (int o = 0; o < nops; ++o) batched = batched || ops_batched[o] != 0;
+    ME<Real>* blob = nullptr;
+    static thread_local BlobStage bs;
+    int slot = 0;
+    const size_t blob_bytes = (size_t)batch * LP_MAT_ELEMS * sizeof(ME<Real>);
+    if (batched && state) {
+        if (batch < 1 || batch > 65535) return fail(TCB200_ERR_ARG, "batch=%lld out of range", (long long)batch);
+        if (!workspace || ws_bytes < blob_bytes) return fail(TCB200_ERR_WORKSPACE, "batched gate pass needs %zu bytes of workspace", blob_bytes);
+        slot = bs.next;
+        bs.next ^= 1;
+        if (bs.cap[slot] < blob_bytes) {
+            if (bs.host[slot]) TCB_CUDA(cudaFreeHost(bs.host[slot]));
+            TCB_CUDA(cudaMallocHost(&bs.host[slot], blob_bytes));
+            bs.cap[slot] = blob_bytes;
+        }
+        if (!bs.ev[slot]) TCB_CUDA(cudaEventCreateWithFlags(&bs.ev[slot], cudaEventDisableTiming));
+        else TCB_CUDA(cudaEventSynchronize(bs.ev[slot]));  // the copy that last used this buffer is done
+        blob = static_cast<ME<Real>*>(bs.host[slot]);
+    }
+    std::vector<ME<Real>> dry;
+    if (batched && !state) {  // dry run
+        dry.resize((size_t)batch * LP_MAT_ELEMS);
+        blob = dry.data();
+    }
+    int rc = fill_lpass<Real>(q, info, state, nbits, nops, ops_k, ops_bits, mats, n_hi, tile_hi, ops_batched, (int)batch, blob);
     if (rc) return rc;
     if (info_out) *info_out = info;
     if (!state) return 0;  // dry run (tcb200_gate_pass_info)
@@ -561,14 +634,30 @@ static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, cons
     if (smem < 16) smem = 16;
     static bool attr = false;
     if (!attr) {
-        TCB_CUDA(cudaFuncSetAttribute(lpass_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-        TCB_CUDA(cudaFuncSetAttribute(lpass_fast_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        TCB_CUDA(cudaFuncSetAttribute(lpass_kernel<Real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        TCB_CUDA(cudaFuncSetAttribute(lpass_fast_kernel<Real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        TCB_CUDA(cudaFuncSetAttribute(lpass_kernel<Real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        TCB_CUDA(cudaFuncSetAttribute(lpass_fast_kernel<Real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
         attr = true;
     }
     dim3 grid((unsigned)ntiles, (unsigned)batch);
     dim3 block(1u << q.stb);
-    if (q.fast) lpass_fast_kernel<Real><<<grid, block, smem, st>>>(q);
-    else lpass_kernel<Real><<<grid, block, smem, st>>>(q);
+    if (batched) {
+        // only the used prefix of every element's blob travels
+        const size_t used = (size_t)info.mat_elems * sizeof(ME<Real>);
+        if (used) {
+            TCB_CUDA(cudaMemcpy2DAsync(workspace, LP_MAT_ELEMS * sizeof(ME<Real>), blob, LP_MAT_ELEMS * sizeof(ME<Real>), used, (size_t)batch,
+                                       cudaMemcpyHostToDevice, st));
+        }
+        TCB_CUDA(cudaEventRecord(bs.ev[slot], st));
+        q.bmats = static_cast<const ME<Real>*>(workspace);
+        q.bstride = LP_MAT_ELEMS;
+        if (q.fast) lpass_fast_kernel<Real, true><<<grid, block, smem, st>>>(q);
+        else lpass_kernel<Real, true><<<grid, block, smem, st>>>(q);
+    } else {
+        if (q.fast) lpass_fast_kernel<Real, false><<<grid, block, smem, st>>>(q);
+        else lpass_kernel<Real, false><<<grid, block, smem, st>>>(q);
+    }
     TCB_LAUNCH_CHECK("lpass_kernel");
     return 0;
 }
@@ -577,11 +666,16 @@ static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, cons
 // tests/emu only: the same parameter block and the same __host__ __device__ bodies on the CPU
 template <typename Real>
 static int emu_lpass(void* state, int nbits, int nops, const int* ops_k, const int* ops_bits, const double* mats, int n_hi,
-                     const int* tile_hi, LPassInfo* info_out) {
+                     const int* tile_hi, LPassInfo* info_out, const int* ops_batched = nullptr, int batch = 1) {
     using C = typename CT<Real>::type;
     LPassParams<Real>* q = new LPassParams<Real>();
     LPassInfo info;
-    int rc = fill_lpass<Real>(*q, info, state, nbits, nops, ops_k, ops_bits, mats, n_hi, tile_hi);
+    bool batched = false;
+    if (ops_batched)
+        for (int o = 0; o < nops; ++o) batched = batched || ops_batched[o] != 0;
+    std::vector<ME<Real>> blob;
+    if (batched) blob.resize((size_t)batch * LP_MAT_ELEMS);
+    int rc = fill_lpass<Real>(*q, info, state, nbits, nops, ops_k, ops_bits, mats, n_hi, tile_hi, ops_batched, batch, batched ? blob.data() : nullptr);
     if (rc) {
         delete q;
         return rc;
@@ -592,26 +686,45 @@ static int emu_lpass(void* state, int nbits, int nops, const int* ops_k, const i
     unsigned char* tile = static_cast<unsigned char*>(aligned_alloc(128, bytes < 128 ? 128 : bytes));
     uint64_t rowoff[256];
     for (int r = 0; r < (1 << q->g.h); ++r) rowoff[r] = row_offset(q->g, r);
-    C* vec = static_cast<C*>(state);
     const uint64_t ntiles = 1ull << (nbits - q->g.T);
-    for (uint64_t t = 0; t < ntiles; ++t) {
-        const uint64_t base = tile_base(q->g, t);
-        if (q->fast) {  // the bodies of lpass_fast_kernel
-            constexpr int NIT = sizeof(C) == 8 ? 2 : 1;
-            for (int tid = 0; tid < 256; ++tid) lstage_in_fast<C>(q->stage, vec + base, tile, (uint32_t)tid);
+    for (int be = 0; be < batch; ++be) {
+        C* vec = static_cast<C*>(state) + ((uint64_t)be << nbits);
+        const ME<Real>* mm = batched ? blob.data() + (size_t)be * LP_MAT_ELEMS : q->m;
+        for (uint64_t t = 0; t < ntiles; ++t) {
+            const uint64_t base = tile_base(q->g, t);
+            if (q->fast) {  // the bodies of lpass_fast_kernel
+                constexpr int NIT = sizeof(C) == 8 ? 2 : 1;
+                for (int tid = 0; tid < 256; ++tid) lstage_in_fast<C>(q->stage, vec + base, tile, (uint32_t)tid);
+                for (int r = 0; r < q->nrounds; ++r)
+                    for (int tid = 0; tid < 256; ++tid) lround_thread_fast<C, Real, NIT>(tile, q->r[r], mm, (uint32_t)tid);
+                for (int tid = 0; tid < 256; ++tid) lstage_out_fast<C>(q->stage, q->out, vec + base, tile, (uint32_t)tid);
+                continue;
+            }
+            for (int tid = 0; tid < nthr; ++tid) stage_in<C, SWZ_SW>(q->g, vec, base, reinterpret_cast<C*>(tile), rowoff, tid, nthr);
             for (int r = 0; r < q->nrounds; ++r)
-                for (int tid = 0; tid < 256; ++tid) lround_thread_fast<C, Real, NIT>(tile, q->r[r], q->m, (uint32_t)tid);
-            for (int tid = 0; tid < 256; ++tid) lstage_out_fast<C>(q->stage, q->out, vec + base, tile, (uint32_t)tid);
-            continue;
+                for (int tid = 0; tid < (1 << q->tb); ++tid) lround_thread<C, Real>(tile, q->r[r], mm, (uint32_t)tid, q->tb, q->ngb);
+            for (int tid = 0; tid < nthr; ++tid) lstage_out_thread<C>(q->g, vec, base, tile, rowoff, q->out, tid, nthr, q->stb);
         }
-        for (int tid = 0; tid < nthr; ++tid) stage_in<C, SWZ_SW>(q->g, vec, base, reinterpret_cast<C*>(tile), rowoff, tid, nthr);
-        for (int r = 0; r < q->nrounds; ++r)
-            for (int tid = 0; tid < (1 << q->tb); ++tid) lround_thread<C, Real>(tile, q->r[r], q->m, (uint32_t)tid, q->tb, q->ngb);
-        for (int tid = 0; tid < nthr; ++tid) lstage_out_thread<C>(q->g, vec, base, tile, rowoff, q->out, tid, nthr, q->stb);
     }
     free(tile);
     delete q;
     return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int emu_apply_gate_pass_batched(void* state, int nbits, int dtype, int nops, const int* ops_k,
+                                                                                   const int* ops_bits, const double* ops_mats,
+                                                                                   const int* ops_batched, int n_hi, const int* tile_hi,
+                                                                                   int batch, double* info8) {
+    LPassInfo info;
+    memset(&info, 0, sizeof(info));
+    int rc;
+    if (dtype == TCB200_C64) rc = emu_lpass<float>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, &info, ops_batched, batch);
+    else rc = emu_lpass<double>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, &info, ops_batched, batch);
+    if (info8) {
+        info8[0] = info.rounds; info8[1] = info.nlin; info8[2] = info.ndiag; info8[3] = info.ndense;
+        info8[4] = info.conflicts; info8[5] = info.vec_rounds; info8[6] = info.fma_per_amp; info8[7] = info.mat_elems;
+    }
+    return rc;
 }
 
 extern "C" __attribute__((visibility("default"))) int emu_apply_gate_pass(void* state, int nbits, int dtype, int nops, const int* ops_k,
@@ -666,6 +779,29 @@ int tcb200_apply_gate_pass(void* state, int nbits, int dtype, int nops, const in
     memset(&info, 0, sizeof(info));
     if (dtype == TCB200_C64) rc = launch_lpass<float>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, batch, st, &info);
     else rc = launch_lpass<double>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, batch, st, &info);
+    if (rc == 0) info_to_array(info, info8);
+    return rc;
+}
+
+size_t tcb200_gate_pass_batched_workspace_bytes(int dtype, int64_t batch) {
+    (void)dtype;
+    return (size_t)(batch < 1 ? 1 : batch) * LP_MAT_ELEMS * 16;
+}
+
+int tcb200_apply_gate_pass_batched(void* state, int nbits, int dtype, int nops, const int* ops_k, const int* ops_bits,
+                                   const double* ops_mats, const int* ops_batched, int n_hi, const int* tile_hi, int64_t batch,
+                                   void* workspace, size_t ws_bytes, double* info8, void* stream) {
+    if (!state) return fail(TCB200_ERR_ARG, "state is NULL");
+    if (!ops_batched) return fail(TCB200_ERR_ARG, "ops_batched is NULL");
+    int rc = gate_pass_args(nbits, dtype, nops, ops_k, ops_bits, ops_mats);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LPassInfo info;
+    memset(&info, 0, sizeof(info));
+    if (dtype == TCB200_C64)
+        rc = launch_lpass<float>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, batch, st, &info, ops_batched, workspace, ws_bytes);
+    else
+        rc = launch_lpass<double>(state, nbits, nops, ops_k, ops_bits, ops_mats, n_hi, tile_hi, batch, st, &info, ops_batched, workspace, ws_bytes);
     if (rc == 0) info_to_array(info, info8);
     return rc;
 }

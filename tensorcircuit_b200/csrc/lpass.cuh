@@ -45,7 +45,7 @@ template <typename Real>
 struct ME;
 template <>
 struct alignas(16) ME<float> {
-    float re, pad, im0, im1;  // im0 == im1: the (im, im) pair of the second FFMA2
+    float re, pad, im0, im1;  // pad == re, im0 == im1: the (re, re) / (im, im) operand pairs of the two FFMA2
 };
 template <>
 struct alignas(16) ME<double> {

@@ -159,7 +159,7 @@ class DeviceState:
         if not blocks:
             return 0
         T = lib.tcb200_pass_tile_bits(self.dt)
-        if self.use_gate_pass and self.nbits >= 4 and not any(b.batched for b in blocks):
+        if self.use_gate_pass and self.nbits >= 4:
             return self._apply_gate_planned(blocks, T)
         mat_elems = (12 * 1024) // self.amp_bytes
         passes = plan_passes([b.bits for b in blocks], self.nbits, T, max_hi=self.pass_max_hi,
@@ -223,7 +223,14 @@ class DeviceState:
         mats = np.ascontiguousarray(np.concatenate([np.asarray(b.matrix, dtype=np.complex128).reshape(-1) for b in blocks]))
         hi = np.asarray(list(tile_hi) if len(tile_hi) else [0], dtype=np.int32)
         info = np.zeros(8, dtype=np.float64)
-        rc = self._gate_pass_call(len(blocks), ks, bits, mats, len(tile_hi), hi, info)
+        if any(b.batched for b in blocks):
+            for b in blocks:
+                if b.batched and b.matrix.shape[0] != self.batch:
+                    raise ValueError("batched block of size %d on a state of batch %d" % (b.matrix.shape[0], self.batch))
+            flags = np.asarray([1 if b.batched else 0 for b in blocks], dtype=np.int32)
+            rc = self._gate_pass_call_batched(len(blocks), ks, bits, mats, flags, len(tile_hi), hi, info)
+        else:
+            rc = self._gate_pass_call(len(blocks), ks, bits, mats, len(tile_hi), hi, info)
         if rc == _lib.ERR_CAPACITY and len(blocks) > 1:
             h = len(blocks) // 2
             return self.apply_gate_pass(blocks[:h], tile_hi) + self.apply_gate_pass(blocks[h:], tile_hi)
@@ -239,6 +246,15 @@ class DeviceState:
     def _gate_pass_call(self, nops: int, ks: np.ndarray, bits: np.ndarray, mats: np.ndarray, n_hi: int, hi: np.ndarray, info: np.ndarray) -> int:
         return lib.tcb200_apply_gate_pass(_ptr(self.buf), self.nbits, self.dt, nops, _lib.iptr(ks), _lib.iptr(bits), _lib.dptr(mats.view(np.float64)),
                                           n_hi, _lib.iptr(hi), self.batch, _lib.dptr(info), _stream())
+
+    def _gate_pass_call_batched(self, nops: int, ks: np.ndarray, bits: np.ndarray, mats: np.ndarray, flags: np.ndarray, n_hi: int,
+                                hi: np.ndarray, info: np.ndarray) -> int:
+        need = int(lib.tcb200_gate_pass_batched_workspace_bytes(self.dt, self.batch))
+        if getattr(self, "_gp_ws", None) is None or self._gp_ws.numel() < need:
+            self._gp_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return lib.tcb200_apply_gate_pass_batched(_ptr(self.buf), self.nbits, self.dt, nops, _lib.iptr(ks), _lib.iptr(bits), _lib.dptr(mats.view(np.float64)),
+                                                  _lib.iptr(flags), n_hi, _lib.iptr(hi), self.batch, _ptr(self._gp_ws), self._gp_ws.numel(),
+                                                  _lib.dptr(info), _stream())
 
     # Register tiles (several gates per shared-memory round trip) pay off when many gates pile up
     # on the same <= 4 qubits inside a pass (nearest-neighbour ladders); on the random-matching

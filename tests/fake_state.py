@@ -87,6 +87,14 @@ class FakeState:
         del st
         return 0
 
+    def _gate_pass_call_batched(self, nops, ks, bits, mats, flags, n_hi, hi, info):
+        rc = self._lib.emu_apply_gate_pass_batched(self.np.ctypes.data_as(ctypes.c_void_p), self.nbits, self.dt, nops, _ip(ks), _ip(bits),
+                                                   mats.view(np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _ip(flags), n_hi, _ip(hi),
+                                                   self.batch, info.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        if rc and rc != -4:
+            raise engine._lib.EngineError("emu gate pass: %s" % self._lib.emu_last_error().decode())
+        return rc
+
     regtile_max_gates = 2  # pair mode, as the engine; tests override it to cover the generic path
 
     def apply_planned(self, blocks):
@@ -96,7 +104,7 @@ class FakeState:
         if not blocks:
             return 0
         T = self._lib.emu_pass_tile_bits(self.dt)
-        if self.use_gate_pass and self.nbits >= 4 and not any(b.batched for b in blocks):
+        if self.use_gate_pass and self.nbits >= 4:
             # the engine's own planning code, with the launch replaced by the emulated kernel
             return self._apply_gate_planned(blocks, T)
         passes = plan_passes([b.bits for b in blocks], self.nbits, T, max_hi=self.pass_max_hi, max_ops=16,

@@ -219,3 +219,44 @@ def test_capacity_error_is_reported(emu):
     mats = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.complex128).reshape(-1) for _, m in gates]))
     rc = emu.emu_apply_gate_pass(st.ctypes.data_as(ctypes.c_void_p), n, 0, len(gates), _ip(ks), _ip(bits), _dp(mats.view(np.float64)), 0, _ip([0]), None)
     assert rc == -4 and b"gate pass" in emu.emu_last_error()
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+@pytest.mark.parametrize("n", [7, 14])
+def test_batched_gate_pass_vs_oracle(emu, dtype, n):
+    """vmap: per-element matrices for rx / rzz (dense and diagonal classes), shared cnot / h; one
+    schedule for the whole batch, every element checked against the oracle"""
+    rng = np.random.default_rng(20 + n)
+    B = 3
+    T = emu.emu_pass_tile_bits(0 if dtype == np.complex64 else 1)
+    inside = list(range(n)) if n <= T else list(range(T - 2)) + [n - 2, n - 1]
+    tile_hi = [] if n <= T else [n - 2, n - 1]
+    gates = []  # (bits, [B matrices] or single matrix)
+    for _ in range(20):
+        c = int(rng.integers(0, 5))
+        if c == 0:
+            gates.append(([int(rng.choice(inside))], [orc.m_rx(t) for t in rng.uniform(0, 6.28, size=B)]))
+        elif c == 1:
+            gates.append((sorted(rng.choice(inside, size=2, replace=False).tolist()), [orc.gate_matrix("rzz", theta=t) for t in rng.uniform(0, 6.28, size=B)]))
+        elif c == 2:
+            gates.append((sorted(rng.choice(inside, size=2, replace=False).tolist()), _bit_matrix("cnot")))
+        elif c == 3:
+            gates.append(([int(rng.choice(inside))], _bit_matrix("h")))
+        else:
+            gates.append((sorted(rng.choice(inside, size=2, replace=False).tolist()), [_rand_u(rng, 2) for _ in range(B)]))
+    st = np.stack([_rand_state(rng, n, dtype) for _ in range(B)])
+    refs = []
+    for b in range(B):
+        per = [(bits, m[b] if isinstance(m, list) else m) for bits, m in gates]
+        refs.append(_oracle(st[b], n, per))
+    ks = [len(b) for b, _ in gates]
+    bits = [x for b, _ in gates for x in b]
+    flags = [1 if isinstance(m, list) else 0 for _, m in gates]
+    mats = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.complex128).reshape(-1) for _, m in gates]))
+    info = np.zeros(8)
+    rc = emu.emu_apply_gate_pass_batched(st.ctypes.data_as(ctypes.c_void_p), n, 0 if dtype == np.complex64 else 1, len(gates), _ip(ks), _ip(bits),
+                                         _dp(mats.view(np.float64)), _ip(flags), len(tile_hi), _ip(tile_hi if tile_hi else [0]), B, _dp(info))
+    assert rc == 0, emu.emu_last_error()
+    assert info[1] >= 1  # the shared cnots were absorbed into the index map
+    for b in range(B):
+        assert np.max(np.abs(st[b] - refs[b])) < TOL[dtype] * 6, b
