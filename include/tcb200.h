@@ -280,6 +280,22 @@ int tcb200_run_circuit_host(void* state, int nbits, int dtype, int init_zero, in
                             int64_t shots, const double* uniforms_host, int64_t* out_idx_host,
                             void* workspace, size_t ws_bytes, void* stream);
 
+/* Single-flip Pauli strings -- exactly one X or Y, any number of Z's: the transverse-field /
+ * kinetic half of TFIM- and Heisenberg-type Hamiltonians (quantum.py:1461-1482 with a one-bit flip
+ * mask).  Up to tcb200_expect_single_flip_max_terms() = 24 strings per read of the state (<= 12
+ * distinct flip bits, <= 2 strings per flip bit), all flip bits inside the tile {low bits} U
+ * {tile_hi} (<= 9 gathered bits): the pair sums are formed in registers, 16 amplitudes per
+ * shared-memory access, instead of one partner load per amplitude and string.
+ *   flip_bit[t]  amplitude-index bit of the X / Y;  sign[t]: bits carrying Z or Y;  ny[t]: 0 or 1
+ *   out_dev      DEVICE double [batch][nterms][2], as tcb200_expect_pauli
+ * The state must be larger than one 64 KiB tile (14 bits complex64 / 13 bits complex128); smaller
+ * states go through tcb200_expect_pauli.  Float64 accumulation across tiles, fixed order. */
+int tcb200_expect_single_flip_max_terms(void);
+size_t tcb200_expect_single_flip_workspace_bytes(int nbits, int64_t batch);
+int tcb200_expect_single_flip(const void* state, int nbits, int dtype, int nterms, const int* flip_bit,
+                              const uint64_t* sign, const int* ny, int n_hi, const int* tile_hi,
+                              double* out_dev, int64_t batch, void* workspace, size_t ws_bytes, void* stream);
+
 /* Diagonal Pauli strings (only I and Z): expectation_ps(z=[...]) / the cost function of an Ising
  * or QAOA Hamiltonian, quantum.py:1461-1482 with an empty flip mask.  Up to
  * tcb200_expect_z_max_terms(dtype) strings (32 complex64 / 16 complex128) are evaluated in ONE

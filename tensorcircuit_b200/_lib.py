@@ -75,6 +75,9 @@ def _load() -> ctypes.CDLL:
         "tcb200_expect_z_workspace_bytes": (c_size_t, [c_int, c_int64]),
         "tcb200_expect_z": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_uint64), c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
         "tcb200_expect_tile_bits": (c_int, [c_int]),
+        "tcb200_expect_single_flip_max_terms": (c_int, []),
+        "tcb200_expect_single_flip_workspace_bytes": (c_size_t, [c_int, c_int64]),
+        "tcb200_expect_single_flip": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_uint64), POINTER(c_int), c_int, POINTER(c_int), c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
         "tcb200_sample": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_double, c_double, c_void_p, c_size_t, c_void_p]),
         "tcb200_sample_workspace_bytes": (c_size_t, [c_int]),
         "tcb200_run_circuit_host": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_double), c_int64, POINTER(c_double), POINTER(c_int64), c_void_p, c_size_t, c_void_p]),
@@ -93,7 +96,7 @@ EXPORTS = [
     "tcb200_apply_dense", "tcb200_apply_dense_batched", "tcb200_apply_diag", "tcb200_apply_pass", "tcb200_apply_pass_host", "tcb200_apply_rpass_host", "tcb200_apply_gate_pass", "tcb200_gate_pass_info", "tcb200_gate_pass_batched_workspace_bytes", "tcb200_apply_gate_pass_batched",
     "tcb200_pass_tile_bits", "tcb200_norm2", "tcb200_reduce_workspace_bytes", "tcb200_masked_norm2_workspace_bytes", "tcb200_masked_norm2", "tcb200_probability_state", "tcb200_probability",
     "tcb200_expect_pauli", "tcb200_expect_workspace_bytes", "tcb200_expect_tile_bits",
-    "tcb200_expect_z_max_terms", "tcb200_expect_z_min_bits", "tcb200_expect_z_workspace_bytes", "tcb200_expect_z", "tcb200_sample",
+    "tcb200_expect_single_flip_max_terms", "tcb200_expect_single_flip_workspace_bytes", "tcb200_expect_single_flip", "tcb200_expect_z_max_terms", "tcb200_expect_z_min_bits", "tcb200_expect_z_workspace_bytes", "tcb200_expect_z", "tcb200_sample",
     "tcb200_sample_workspace_bytes", "tcb200_run_circuit_host",
 ]
 

@@ -193,7 +193,7 @@ class Circuit:
                 self._applied = 0
             elif self._batch != m.batch:
                 raise ValueError("inconsistent vmap batch sizes")
-        self._ops.append(GateOp(index, m, name))
+        self._ops.append(GateOp(index, m, name, getattr(gate, "kind", None) if is_batched(m) else None))
         self.state_tensor = None
 
     apply = apply_general_gate

@@ -70,7 +70,50 @@ def plan_expect_groups(flips: Sequence[int], nbits: int, tile_bits: int, max_hi:
     return groups
 
 
+def plan_single_flip_groups(flip_bits: Sequence[int], nbits: int, tile_bits: int, max_hi: int = 9, max_bits: int = 12,
+                            per_bit: int = 2) -> List[Tuple[List[int], List[int]]]:
+    """Launch plan of the single-flip kernel: each launch covers <= max_bits distinct flip bits that
+    fit one tile ({low bits} U <= max_hi gathered bits), <= per_bit strings each.  High bits go
+    first (they need a gathered slot; the low bits are inside every tile).  Returns
+    [(term ids, gathered bits)]."""
+    by_bit: dict = {}
+    for i, b in enumerate(flip_bits):
+        by_bit.setdefault(int(b), []).append(i)
+    groups: List[Tuple[List[int], List[int]]] = []
+    while by_bit:
+        bits = sorted(by_bit, reverse=True)
+        best: Optional[Tuple[int, int, List[int], List[int]]] = None
+        for h in range(0, max_hi + 1):
+            lrow = tile_bits - h
+            if nbits <= tile_bits and h:
+                break
+            high = [b for b in bits if b >= lrow][:h]
+            if len(high) < h:
+                continue
+            low = [b for b in bits if b < lrow]
+            covered = high + low  # gathered bits first: the low bits are inside every tile
+            score = (min(max_bits, len(covered)), h)
+            if best is None or score > best[:2]:
+                best = (score[0], h, sorted(high), covered[:max_bits])
+        assert best is not None
+        hi, chosen = best[2], best[3]
+        # bits between lrow and the lowest gathered bit cannot be reached unless gathered
+        ids: List[int] = []
+        for b in chosen:
+            take = by_bit[b][:per_bit]
+            ids += take
+            by_bit[b] = by_bit[b][per_bit:]
+            if not by_bit[b]:
+                del by_bit[b]
+        if not ids:
+            raise _lib.EngineError("single-flip planner made no progress")
+        groups.append((ids, hi))
+    return groups
+
+
 class DeviceState:
+    use_single_flip = os.environ.get("TCB200_SINGLE_FLIP", "1") != "0"
+
     def __init__(self, nbits: int, dtype: str = "complex64", batch: int = 1, device: Any = None,
                  buffer: Optional[torch.Tensor] = None):
         require_cuda()
@@ -378,6 +421,26 @@ class DeviceState:
                                           _ptr(wsz), wsz.numel(), _stream()))
                 STATS["expect_launches"] += 1
                 outs.append((ids, out))
+        # single-flip strings (one X or Y, any Z's): up to 24 per read through the register-pair kernel
+        Tp = lib.tcb200_pass_tile_bits(self.dt)
+        if self.use_single_flip and self.nbits > Tp and Tp - (1 if self.amp_bytes == 8 else 0) == 12:
+            sf = [t for t in rest if bin(int(flips[t])).count("1") == 1 and int(nys[t]) <= 1]
+            if sf:
+                rest = [t for t in rest if t not in set(sf)]
+                wsx = self._workspace(max(lib.tcb200_expect_single_flip_workspace_bytes(self.nbits, self.batch),
+                                          lib.tcb200_expect_workspace_bytes(self.nbits, self.batch),
+                                          lib.tcb200_expect_z_workspace_bytes(self.nbits, self.batch) if self.nbits >= lib.tcb200_expect_z_min_bits(self.dt) else 0))
+                for ids, hi in plan_single_flip_groups([int(flips[t]).bit_length() - 1 for t in sf], self.nbits, Tp):
+                    tid = [sf[i] for i in ids]
+                    fb = np.asarray([int(flips[t]).bit_length() - 1 for t in tid], dtype=np.int32)
+                    s = np.asarray([int(signs[t]) for t in tid], dtype=np.uint64)
+                    ny = np.asarray([int(nys[t]) for t in tid], dtype=np.int32)
+                    hia = np.asarray(hi if hi else [0], dtype=np.int32)
+                    out = torch.empty((self.batch, len(tid), 2), dtype=torch.float64, device=self.device)
+                    check(lib.tcb200_expect_single_flip(_ptr(self.buf), self.nbits, self.dt, len(tid), _lib.iptr(fb), _lib.u64ptr(s), _lib.iptr(ny),
+                                                        len(hi), _lib.iptr(hia), _ptr(out), self.batch, _ptr(wsx), wsx.numel(), _stream()))
+                    STATS["expect_launches"] += 1
+                    outs.append((tid, out))
         sub = plan_expect_groups([flips[t] for t in rest], self.nbits, T)
         groups = [([rest[i] for i in ids], union) for ids, union in sub]
         ws = self._workspace(lib.tcb200_expect_workspace_bytes(self.nbits, self.batch))

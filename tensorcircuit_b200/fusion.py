@@ -34,6 +34,7 @@ class GateOp:
     qubits: Tuple[int, ...]
     matrix: Any  # np.ndarray [D, D] complex128, or BatchArray with shape [D, D]
     name: str = ""
+    kind: Optional[str] = None  # zero-pattern class when the gate constructor knows it (vmap fast path)
 
     @property
     def batched(self) -> bool:
@@ -210,16 +211,20 @@ SNAP_EPS = 1e-15
 def matrix_kind(m: Any) -> str:
     """Class of a gate matrix by its zero pattern (batched: the union over the batch)."""
     a = _raw(m)
-    nz = np.abs(a) > SNAP_EPS
+    mag = np.abs(a)
     if a.ndim == 3:
-        nz = nz.any(axis=0)
+        mag = mag.max(axis=0)
+    nz = mag > SNAP_EPS
     D = nz.shape[-1]
-    if not nz[~np.eye(D, dtype=bool)].any():
+    if not nz[_OFFDIAG[D]].any():
         return KIND_DIAG
     if D <= 4 and (nz.sum(axis=0) == 1).all() and (nz.sum(axis=1) == 1).all():
         vals = a[..., nz]
         return KIND_PERM if np.all(np.abs(vals - 1) <= SNAP_EPS) else KIND_MONO
     return KIND_DENSE
+
+
+_OFFDIAG = {1 << k: ~np.eye(1 << k, dtype=bool) for k in range(0, 6)}
 
 
 def _kind_cost(kind: str, k: int) -> int:
@@ -241,18 +246,23 @@ def _combine_kinds(kinds: Sequence[str]) -> str:
     return KIND_MONO
 
 
-def plan_structure_kinds(gate_qubits: Sequence[Tuple[int, ...]], gate_kinds: Sequence[str], kmax: int) -> FusionPlan:
+def plan_structure_kinds(gate_qubits: Sequence[Tuple[int, ...]], gate_kinds: Sequence[str], kmax: int,
+                          gate_batched: Optional[Sequence[bool]] = None) -> FusionPlan:
     """Cost-aware greedy fusion.  A gate merges with the blocks that are currently the latest on
     its qubits when (i) each of them is still the latest block on ALL of its own qubits (so it
     commutes forward to the merge point), (ii) the union stays within ``kmax`` qubits (2 for
     monomial / diagonal results) and (iii) the merged block costs no more than the parts."""
-    key = ("kinds", tuple(gate_qubits), tuple(gate_kinds), kmax)
+    # vmap: a merge that involves per-element matrices costs a batched matrix product on the host
+    # for every call; it is only taken when it saves device work by a clear margin
+    gb = tuple(bool(x) for x in gate_batched) if gate_batched is not None else (False,) * len(gate_qubits)
+    key = ("kinds", tuple(gate_qubits), tuple(gate_kinds), kmax, gb if any(gb) else None)
     hit = _PLAN_CACHE.get(key)
     if hit is not None:
         return hit
     groups: List[List[int]] = []
     bq: List[set] = []
     bkind: List[str] = []
+    bbat: List[bool] = []
     last: Dict[int, int] = {}
     # next gate on each qubit after gate gi (lookahead credit of the inner merge below)
     ng = len(gate_qubits)
@@ -273,6 +283,7 @@ def plan_structure_kinds(gate_qubits: Sequence[Tuple[int, ...]], gate_kinds: Seq
         groups[target] = sorted(groups[target])
         bq[target] = union
         bkind[target] = kind_m
+        bbat[target] = bbat[target] or any(bbat[b] for b in others)
 
     for gi, (qs, kg) in enumerate(zip(gate_qubits, gate_kinds)):
         if len(qs) > MAX_BLOCK_K:
@@ -289,7 +300,8 @@ def plan_structure_kinds(gate_qubits: Sequence[Tuple[int, ...]], gate_kinds: Seq
             kind_m = _combine_kinds([bkind[b] for b in tops] + [kg])
             limit = kmax if kind_m == KIND_DENSE else 2
             parts = sum(_kind_cost(bkind[b], len(bq[b])) for b in tops) + _kind_cost(kg, len(qs))
-            if len(union) <= max(limit, len(qs)) and len(union) <= MAX_BLOCK_K and _kind_cost(kind_m, len(union)) <= parts:
+            margin = 3 if (gb[gi] or any(bbat[b] for b in tops)) and kind_m == KIND_DENSE and len(union) > 1 else 0
+            if len(union) <= max(limit, len(qs)) and len(union) <= MAX_BLOCK_K and _kind_cost(kind_m, len(union)) + margin <= parts:
                 target = tops[-1]
                 merge_into(target, tops[:-1], union, kind_m)
         if target < 0 and len(qs) == 2 and len(qs) <= kmax:
@@ -306,20 +318,24 @@ def plan_structure_kinds(gate_qubits: Sequence[Tuple[int, ...]], gate_kinds: Seq
                     j = nxt_on[gi].get(q)
                     if j is not None and len(gate_qubits[j]) == 1 and gate_kinds[j] == KIND_DENSE:
                         credit += _kind_cost(KIND_DENSE, 1)
-                if _kind_cost(kind_m, len(sq)) <= parts + credit:
+                margin = 3 if (gb[gi] or any(bbat[b] for b in inner)) else 0
+                if _kind_cost(kind_m, len(sq)) + margin <= parts + credit:
                     # the merged block holds the gate, which must follow the latest blocks that
                     # are NOT merged: it becomes a new block at the end, the inner ones move into it
                     groups.append([])
                     bq.append(set())
                     bkind.append(kind_m)
+                    bbat.append(False)
                     target = len(groups) - 1
                     merge_into(target, inner, set(sq), kind_m)
         if target < 0:
             groups.append([])
             bq.append(set(sq))
             bkind.append(kg)
+            bbat.append(False)
             target = len(groups) - 1
         groups[target].append(gi)
+        bbat[target] = bbat[target] or gb[gi]
         for q in bq[target]:
             last[q] = target
     keep = [i for i in range(len(groups)) if groups[i]]
@@ -335,15 +351,16 @@ def fuse_structured(ops: Sequence[GateOp], nqubits: int, kmax: int = 2) -> List[
     ('dense' / 'diag' / 'perm' / 'mono') computed from the fused matrix."""
     if not ops:
         return []
-    kinds = [matrix_kind(op.matrix) for op in ops]
-    plan = plan_structure_kinds([op.qubits for op in ops], kinds, kmax)
+    kinds = [op.kind if op.kind is not None else matrix_kind(op.matrix) for op in ops]
+    plan = plan_structure_kinds([op.qubits for op in ops], kinds, kmax, [is_batched(op.matrix) for op in ops])
     blocks: List[Block] = []
     for grp, qs in zip(plan.groups, plan.block_qubits):
         k = len(qs)
         D = 1 << k
         qlist = list(qs)
-        if len(grp) == 1 and tuple(ops[grp[0]].qubits) == tuple(qs) and not is_batched(ops[grp[0]].matrix):
-            m = np.asarray(ops[grp[0]].matrix, dtype=np.complex128)
+        single = len(grp) == 1 and tuple(ops[grp[0]].qubits) == tuple(qs)
+        if single:
+            m = np.asarray(_raw(ops[grp[0]].matrix), dtype=np.complex128)
         else:
             m = np.eye(D, dtype=np.complex128)
             for gi in grp:
@@ -351,7 +368,7 @@ def fuse_structured(ops: Sequence[GateOp], nqubits: int, kmax: int = 2) -> List[
                 m = embed_apply(m, qlist, _raw(op.matrix), list(op.qubits))
         batched = m.ndim == 3
         bits = tuple(sorted(nqubits - 1 - q for q in qs))
-        kind = matrix_kind(m)
+        kind = kinds[grp[0]] if single else matrix_kind(m)
         if kind != KIND_DENSE and not batched:
             # hand the library exact zeros / ones: it classifies by exact comparison
             m = np.where(np.abs(m) > SNAP_EPS, m, 0)
