@@ -62,6 +62,7 @@ def run_dist(args, tc, rank, world, local):
     for _ in range(args.warmup):
         step()
     sync()
+    ds.finalize_stats()
     for k in ds.stats:
         ds.stats[k] = 0
     clocks = ClockSampler(local) if rank == 0 else None
@@ -78,7 +79,7 @@ def run_dist(args, tc, rank, world, local):
     total_ms = float(ms.item())
     launches = _lib.launch_count() - l0
     norm2 = ds.norm2()
-    stats = dict(ds.stats)
+    stats = dict(ds.finalize_stats())
     clk = clocks.stop() if clocks else None
 
     # end-to-end through the public API (SPMD: every rank records the circuit, state sharded)
@@ -156,7 +157,8 @@ def run_dist(args, tc, rank, world, local):
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": None},
             "remap": {"per_step": stats["remaps"] / args.steps, "bytes_per_rank_per_remap": (stats["remap_bytes"] / stats["remaps"]) if stats["remaps"] else 0,
                       "ms_per_remap": (stats["remap_ms"] / stats["remaps"]) if stats["remaps"] else 0, "nvlink_gbs_per_direction": remap_gbs,
-                      "nvlink_peak_gbs": 770.0, "nvlink_frac": (remap_gbs / 770.0) if remap_gbs else None,
+                      "nvlink_peak_gbs": 900.0, "nvlink_peak_source": "nominal NVLink 5 per direction per GPU (B200_PROFILING.md; measured peer-copy reference on this pool: 770)",
+                      "nvlink_frac": (remap_gbs / 900.0) if remap_gbs else None,
                       "local_passes_per_step": stats["local_passes"] / args.steps, "swap_passes_per_step": stats["swap_passes"] / args.steps,
                       "remap_share_of_step": stats["remap_ms"] / total_ms},
             "e2e": {"value": e2e_steps * ngates * float(2**n) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(shots * 8), "d2h_bytes_per_step": int(shots * 8),

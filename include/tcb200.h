@@ -282,8 +282,8 @@ int tcb200_run_circuit_host(void* state, int nbits, int dtype, int init_zero, in
 
 /* Single-flip Pauli strings -- exactly one X or Y, any number of Z's: the transverse-field /
  * kinetic half of TFIM- and Heisenberg-type Hamiltonians (quantum.py:1461-1482 with a one-bit flip
- * mask).  Up to tcb200_expect_single_flip_max_terms() = 24 strings per read of the state (<= 12
- * distinct flip bits, <= 2 strings per flip bit), all flip bits inside the tile {low bits} U
+ * mask).  Up to tcb200_expect_single_flip_max_terms() = 12 strings per read of the state (12
+ * distinct flip bits, one string per flip bit and launch), all flip bits inside the tile {low bits} U
  * {tile_hi} (<= 9 gathered bits): the pair sums are formed in registers, 16 amplitudes per
  * shared-memory access, instead of one partner load per amplitude and string.
  *   flip_bit[t]  amplitude-index bit of the X / Y;  sign[t]: bits carrying Z or Y;  ny[t]: 0 or 1

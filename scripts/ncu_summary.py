@@ -1,44 +1,20 @@
-"""Summarise an .ncu-rep (captured on the GPU box with --set full) into a small CSV for profiles/.
-
-    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep profiles/name.csv
-"""
-
+"""Reduce an ncu report (gpurun_out/*.ncu-rep) to the handful of metrics the docs cite, as CSV."""
 import csv
 import subprocess
 import sys
 
-METRICS = [
-    "gpu__time_duration.sum",
-    "dram__bytes_read.sum",
-    "dram__bytes_write.sum",
-    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-    "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
-    "smsp__inst_executed.sum",
-    "smsp__issue_active.avg.pct_of_peak_sustained_active",
-    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
-    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
-    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
-    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
-    "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
-    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
-    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
-    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-    "sm__warps_active.avg.pct_of_peak_sustained_active",
-    "launch__registers_per_thread",
-    "launch__occupancy_limit_registers",
-    "launch__occupancy_limit_shared_mem",
-    "launch__shared_mem_per_block_dynamic",
-    "launch__grid_size",
-    "launch__block_size",
-    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
-    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
-    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
-    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
-    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
-    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
-    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
-]
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__inst_executed.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg.per_second",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
 
 
 def main():
@@ -46,17 +22,14 @@ def main():
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
-    idx = {h: i for i, h in enumerate(hdr)}
+    name_col = hdr.index("Kernel Name")
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
-        w.writerow(["launch", "kernel", "metric", "value", "unit"])
-        for li, r in enumerate(rows[2:]):
-            name = r[idx["Kernel Name"]].split("(")[0]
-            for m in METRICS:
-                if m in idx:
-                    w.writerow([li, name, m, r[idx[m]], units[idx[m]]])
-    print("wrote", out)
+        w.writerow(["metric", "unit"] + ["launch%d:%s" % (i, r[name_col][:48]) for i, r in enumerate(rows[2:])])
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                w.writerow([k, units[i]] + [r[i] for r in rows[2:]])
 
 
-if __name__ == "__main__":
-    main()
+main()

@@ -1,5 +1,5 @@
 // Single-flip Pauli strings -- X_j or Y_j with any Z dressing: the off-diagonal half of every
-// transverse-field / Heisenberg-type Hamiltonian -- evaluated up to 24 per read of the state.
+// transverse-field / Heisenberg-type Hamiltonian -- evaluated 12 per read of the state.
 //
 // Replaces expectation_before + contraction (tensorcircuit/basecircuit.py:267-319,
 // circuit.py:914-990) for these strings, like tcb200_expect_pauli, but with the register-tile
@@ -8,7 +8,7 @@
 // up to three rounds a thread loads 16 amplitudes -- 4 tile bits -- once and forms, for each of
 // those 4 bits j, the pair sums
 //     sum_{e: e_j = 0} s(e) * Re / Im( conj(psi_e) psi_{e | 1<<j} )         (quantum.py:1461-1482)
-// entirely in registers (2 FMA per pair).  12 flip bits x 2 strings per launch.  Signs of the Z
+// entirely in registers (2 FMA per pair).  12 flip bits, one string each, per launch.  Signs of the Z
 // dressing split into a per-register mask, a per-thread parity and a per-tile parity.  Per-thread
 // partial sums are kept in the state's real type for 16 tiles at a time and then folded into
 // float64 (warp shuffle -> shared memory), so the result does not depend on the size of the state.
@@ -22,7 +22,7 @@
 namespace tcb {
 
 constexpr int XE_ROUNDS = 3;
-constexpr int XE_SLOTS = 2;                                // strings per flip bit
+constexpr int XE_SLOTS = 1;                                // strings per flip bit and launch
 constexpr int XE_TERMS = XE_ROUNDS * LP_RB * XE_SLOTS;     // 24
 constexpr int XE_FLUSH = 16;                               // tiles between float -> double folds
 
@@ -74,7 +74,7 @@ __device__ __forceinline__ Real xe_pairs(const C* v, const XESlot& s) {
 }
 
 template <typename Real>
-__global__ void __launch_bounds__(256, 2) xexpect_kernel(const __grid_constant__ XEParams p) {
+__global__ void __launch_bounds__(256, sizeof(Real) == 4 ? 3 : 2) xexpect_kernel(const __grid_constant__ XEParams p) {
     using C = typename CT<Real>::type;
     constexpr int NIT = sizeof(C) == 8 ? 2 : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) xexpect_final_kernel(const __grid_constan
 
 static unsigned xe_grid_x(int nbits, int T, int64_t batch) {
     const uint64_t ntiles = nbits > T ? (1ull << (nbits - T)) : 1ull;
-    uint64_t cap = (148ull * 2) / (uint64_t)(batch < 1 ? 1 : batch);
+    uint64_t cap = (148ull * 3) / (uint64_t)(batch < 1 ? 1 : batch);
     if (cap < 4) cap = 4;
     return (unsigned)(ntiles < cap ? ntiles : cap);
 }

@@ -104,6 +104,7 @@ class DistState:
         # logical bit -> physical bit (physical bits >= nloc are the rank bits)
         self.phys: List[int] = list(range(self.n))
         self.stats = {"remaps": 0, "remap_bytes": 0, "local_passes": 0, "swap_passes": 0, "remap_ms": 0.0}
+        self._remap_events: List[Any] = []
 
     # -- bookkeeping -------------------------------------------------------------------------
     def logical_at(self, p: int) -> int:
@@ -188,6 +189,16 @@ class DistState:
         self.phys[la], self.phys[lb] = pb, pa
         self.stats["swap_passes"] += 1
 
+    def finalize_stats(self) -> Dict[str, Any]:
+        """Fold the CUDA-event times of the remaps issued so far into stats['remap_ms'] (synchronises
+        the device once; the data path itself never waits for the host)."""
+        if self._remap_events:
+            torch.cuda.synchronize()
+            for t0, t1 in self._remap_events:
+                self.stats["remap_ms"] += t0.elapsed_time(t1)
+            self._remap_events = []
+        return self.stats
+
     # -- the exchange ---------------------------------------------------------------------------------
     def remap(self) -> None:
         """Swap the g global bits with the top g local bits (all-to-all over contiguous chunks)."""
@@ -207,8 +218,7 @@ class DistState:
             self._remap_chunked(src)
         if t0 is not None:
             t1.record()
-            t1.synchronize()
-            self.stats["remap_ms"] += t0.elapsed_time(t1)
+            self._remap_events.append((t0, t1))  # read in finalize_stats(): no host sync on the data path
         for j in range(self.g):
             a, b = self.logical_at(self.nloc - self.g + j), self.logical_at(self.nloc + j)
             self.phys[a], self.phys[b] = self.nloc + j, self.nloc - self.g + j

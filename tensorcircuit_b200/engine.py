@@ -71,9 +71,9 @@ def plan_expect_groups(flips: Sequence[int], nbits: int, tile_bits: int, max_hi:
 
 
 def plan_single_flip_groups(flip_bits: Sequence[int], nbits: int, tile_bits: int, max_hi: int = 9, max_bits: int = 12,
-                            per_bit: int = 2) -> List[Tuple[List[int], List[int]]]:
+                            per_bit: int = 1) -> List[Tuple[List[int], List[int]]]:
     """Launch plan of the single-flip kernel: each launch covers <= max_bits distinct flip bits that
-    fit one tile ({low bits} U <= max_hi gathered bits), <= per_bit strings each.  High bits go
+    fit one tile ({low bits} U <= max_hi gathered bits), per_bit strings each.  High bits go
     first (they need a gathered slot; the low bits are inside every tile).  Returns
     [(term ids, gathered bits)]."""
     by_bit: dict = {}
@@ -421,7 +421,7 @@ class DeviceState:
                                           _ptr(wsz), wsz.numel(), _stream()))
                 STATS["expect_launches"] += 1
                 outs.append((ids, out))
-        # single-flip strings (one X or Y, any Z's): up to 24 per read through the register-pair kernel
+        # single-flip strings (one X or Y, any Z's): 12 per read through the register-pair kernel
         Tp = lib.tcb200_pass_tile_bits(self.dt)
         if self.use_single_flip and self.nbits > Tp and Tp - (1 if self.amp_bytes == 8 else 0) == 12:
             sf = [t for t in rest if bin(int(flips[t])).count("1") == 1 and int(nys[t]) <= 1]

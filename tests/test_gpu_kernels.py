@@ -587,3 +587,54 @@ def test_masked_norm2(dtype, n):
         assert abs(got - want) < 4 * TOL[dtype], (mask, value, got, want)
     with pytest.raises(_lib.EngineError):
         st.masked_norm2(1, 2)  # value outside the mask
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n", [14, 17, 21])
+def test_expect_single_flip_vs_oracle(dtype, n):
+    """tcb200_expect_single_flip (X_j / Y_j with Z dressing, register-pair kernel) through
+    DeviceState.expectation_terms: vs the oracle's closed form and vs tcb200_expect_pauli"""
+    rng = np.random.default_rng(n)
+    psi = _rand_state(rng, n)
+    st = DeviceState(n, dtype)
+    st.load(psi)
+    terms = []
+    for j in range(n):  # every flip bit, both types, random Z dressing
+        q = n - 1 - j
+        others = [k for k in range(n) if k != q]
+        terms.append(([q], [], sorted(rng.choice(others, size=int(rng.integers(0, 4)), replace=False).tolist())))
+        terms.append(([], [q], sorted(rng.choice(others, size=int(rng.integers(0, 3)), replace=False).tolist())))
+    fl, sg, ny = [], [], []
+    for x, y, z in terms:
+        f, s, k = orc.pauli_masks(n, x, y, z)
+        fl.append(f)
+        sg.append(s)
+        ny.append(k)
+    before = engine.STATS["expect_launches"]
+    got = st.expectation_terms(fl, sg, ny)[0]
+    launches = engine.STATS["expect_launches"] - before
+    assert launches <= (2 * n + 11) // 12 + 3  # 12 strings per launch, not 8
+    want = np.array([orc.pauli_expectation(psi, n, x, y, z) for x, y, z in terms])
+    tol = 2e-6 if dtype == "complex64" else 1e-12
+    assert np.max(np.abs(got - want)) < tol, np.max(np.abs(got - want))
+    old = DeviceState.use_single_flip
+    try:
+        DeviceState.use_single_flip = False
+        ref = st.expectation_terms(fl, sg, ny)[0]
+    finally:
+        DeviceState.use_single_flip = old
+    assert np.max(np.abs(got - ref)) < tol
+
+
+def test_expect_single_flip_batched_rows():
+    n, B = 15, 3
+    rng = np.random.default_rng(4)
+    rows = [_rand_state(rng, n) for _ in range(B)]
+    st = DeviceState(n, "complex64", batch=B)
+    st.buf.copy_(torch.from_numpy(np.stack(rows)).to(st.device, dtype=torch.complex64))
+    terms = [([n - 1 - j], [], [(n - j) % n] if (n - j) % n != n - 1 - j else []) for j in range(n)]
+    fl, sg, ny = zip(*[orc.pauli_masks(n, x, y, z) for x, y, z in terms])
+    got = st.expectation_terms(list(fl), list(sg), list(ny))
+    for b in range(B):
+        want = np.array([orc.pauli_expectation(rows[b], n, x, y, z) for x, y, z in terms])
+        assert np.max(np.abs(got[b] - want)) < 2e-6
