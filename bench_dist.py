@@ -65,6 +65,7 @@ def run_dist(args, tc, rank, world, local):
     ds.finalize_stats()
     for k in ds.stats:
         ds.stats[k] = 0
+    engine.reset_stats()
     clocks = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -80,6 +81,8 @@ def run_dist(args, tc, rank, world, local):
     launches = _lib.launch_count() - l0
     norm2 = ds.norm2()
     stats = dict(ds.finalize_stats())
+    gp_stats = {"rounds_per_step": engine.STATS["gate_pass_rounds"] / max(1, args.steps), "fma_per_amplitude_per_step": engine.STATS["gate_pass_fma_per_amp"] / max(1, args.steps),
+                "gates_absorbed_into_index_map_per_step": engine.STATS["gate_pass_free_gates"] / max(1, args.steps)}
     clk = clocks.stop() if clocks else None
 
     # end-to-end through the public API (SPMD: every rank records the circuit, state sharded)
@@ -160,6 +163,7 @@ def run_dist(args, tc, rank, world, local):
                       "nvlink_peak_gbs": 900.0, "nvlink_peak_source": "nominal NVLink 5 per direction per GPU (B200_PROFILING.md; measured peer-copy reference on this pool: 770)",
                       "nvlink_frac": (remap_gbs / 900.0) if remap_gbs else None,
                       "local_passes_per_step": stats["local_passes"] / args.steps, "swap_passes_per_step": stats["swap_passes"] / args.steps,
+                      "swap_blocks_folded_into_passes_per_step": stats.get("swap_blocks", 0) / args.steps,
                       "remap_share_of_step": stats["remap_ms"] / total_ms},
             "e2e": {"value": e2e_steps * ngates * float(2**n) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(shots * 8), "d2h_bytes_per_step": int(shots * 8),
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "samples_match_device_leg": same},
@@ -169,7 +173,7 @@ def run_dist(args, tc, rank, world, local):
             "clocks": clk,
             "checks": {"norm2": norm2, "sample_min": int(s.min()), "sample_max": int(s.max()),
                        "dist_parity_relerr": dist_parity, "dist_parity_what": "config-5 recipe at n=22 depth 6 on the sharded state (remaps included) vs the oracle, relative l2 error; tolerance 1e-5"},
-            "gate_pass": {"rounds_per_step": engine.STATS["gate_pass_rounds"] / max(1, args.steps + args.warmup + 1), "fma_per_amplitude_per_step": engine.STATS["gate_pass_fma_per_amp"] / max(1, args.steps + args.warmup + 1)},
+            "gate_pass": gp_stats,
         }
         if cfg3 is not None:
             line["configs"] = [cfg3]

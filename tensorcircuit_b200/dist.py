@@ -294,6 +294,7 @@ class DistState:
         indeg = [len(p) for p in preds]
         ready = sorted(i for i in range(nb) if indeg[i] == 0)
         done = 0
+        done_flag = [False] * nb
         stuck_rounds = 0
         while done < nb:
             progressed = False
@@ -308,12 +309,18 @@ class DistState:
                     batch.append(lb)
                     ready.remove(i)
                     done += 1
+                    done_flag[i] = True
                     progressed = again = True
                     for s in succs[i]:
                         indeg[s] -= 1
                         if indeg[s] == 0:
                             ready.append(s)
                     ready.sort()
+            if done < nb and self.G > 1:
+                # choose the qubits that become global and move them into the swap window with
+                # SWAP blocks that ride at the end of this batch (permutations cost nothing inside
+                # a gate pass) instead of one extra pass per moved bit
+                batch += self._plan_evictions(blocks, done_flag)
             self._run_local_batch(batch)
             if done == nb:
                 break
@@ -323,8 +330,53 @@ class DistState:
                     raise RuntimeError("distributed scheduler made no progress")
             else:
                 stuck_rounds = 0
-            self._prepare_remap([blocks[i] for i in ready])
             self.remap()
+
+    @staticmethod
+    def _nonlocal_bits(blk: Block) -> Tuple[int, ...]:
+        """bits of the block on which its matrix is NOT block diagonal: the ones that must be local"""
+        cached = getattr(blk, "_nl", None)
+        if cached is not None:
+            return cached
+        k = len(blk.bits)
+        m = np.asarray(blk.matrix)
+        out = []
+        for j in range(k):
+            if restrict_global(m, [x == j for x in range(k)], [0]) is None:
+                out.append(blk.bits[j])
+        blk._nl = tuple(out)  # type: ignore[attr-defined]
+        return blk._nl  # type: ignore[attr-defined]
+
+    def _plan_evictions(self, blocks: Sequence[Block], done_flag: Sequence[bool]) -> List[Block]:
+        """Before a remap: the g local qubits whose next non-diagonal use lies farthest ahead go into
+        the swap window (they become global).  Returns the SWAP blocks (physical bits) that put them
+        there and updates the logical -> physical map accordingly."""
+        top0 = self.nloc - self.g
+        INF = 1 << 60
+        nxt = {q: INF for q in range(self.n)}
+        for i, b in enumerate(blocks):
+            if done_flag[i]:
+                continue
+            for q in self._nonlocal_bits(b):
+                if nxt[q] == INF:
+                    nxt[q] = i
+        local_q = [q for q in range(self.n) if self.phys[q] < self.nloc]
+        # farthest next use first; ties: qubits already in the window (no swap needed)
+        local_q.sort(key=lambda q: (-nxt[q], 0 if self.phys[q] >= top0 else 1))
+        evict = local_q[: self.g]
+        window_free = [p for p in range(top0, self.nloc) if self.logical_at(p) not in evict]
+        swaps: List[Block] = []
+        for q in evict:
+            pq = self.phys[q]
+            if pq >= top0:
+                continue
+            pw = window_free.pop(0)
+            lo, hi = sorted((pq, pw))
+            swaps.append(Block(qubits=(self.nloc - 1 - hi, self.nloc - 1 - lo), bits=(lo, hi), matrix=_SWAP, batched=False, ngates=0, kind="perm"))
+            other = self.logical_at(pw)
+            self.phys[q], self.phys[other] = pw, pq
+            self.stats["swap_blocks"] = self.stats.get("swap_blocks", 0) + 1
+        return swaps
 
     def _prepare_remap(self, blocked: Sequence[Block]) -> None:
         """A blocked block that also uses a top-local bit would stay blocked after the swap
