@@ -64,6 +64,11 @@ def embed_apply(block_m: np.ndarray, block_qubits: Sequence[int], g: np.ndarray,
     D = 1 << k
     pos = [block_qubits.index(q) for q in gq]
     batched = block_m.ndim == 3 or g.ndim == 3
+    if not batched and k <= 3:
+        # small blocks: embed the gate by fancy indexing and multiply (a few microseconds; the
+        # general tensordot path below costs ~60)
+        og, same_rest = _embed_index(k, tuple(pos))
+        return np.matmul(g[og[:, None], og[None, :]] * same_rest, block_m)
     if not batched:
         t = block_m.reshape([2] * k + [D])
         gt = g.reshape([2] * (2 * kg))
@@ -211,6 +216,8 @@ SNAP_EPS = 1e-15
 def matrix_kind(m: Any) -> str:
     """Class of a gate matrix by its zero pattern (batched: the union over the batch)."""
     a = _raw(m)
+    if a.ndim == 2 and a.shape[0] <= 4:
+        return _small_matrix_kind(a.tolist())
     mag = np.abs(a)
     if a.ndim == 3:
         mag = mag.max(axis=0)
@@ -221,6 +228,34 @@ def matrix_kind(m: Any) -> str:
     if D <= 4 and (nz.sum(axis=0) == 1).all() and (nz.sum(axis=1) == 1).all():
         vals = a[..., nz]
         return KIND_PERM if np.all(np.abs(vals - 1) <= SNAP_EPS) else KIND_MONO
+    return KIND_DENSE
+
+
+def _small_matrix_kind(rows: List[List[complex]]) -> str:
+    """matrix_kind for a 2x2 / 4x4 matrix given as nested lists (no numpy call overhead)"""
+    D = len(rows)
+    diag = True
+    colcount = [0] * D
+    mono = True
+    ones = True
+    for i in range(D):
+        cnt = 0
+        ri = rows[i]
+        for j in range(D):
+            v = ri[j]
+            if abs(v) > SNAP_EPS:
+                cnt += 1
+                colcount[j] += 1
+                if i != j:
+                    diag = False
+                if abs(v - 1) > SNAP_EPS:
+                    ones = False
+        if cnt != 1:
+            mono = False
+    if diag:
+        return KIND_DIAG
+    if mono and all(c == 1 for c in colcount):
+        return KIND_PERM if ones else KIND_MONO
     return KIND_DENSE
 
 
