@@ -153,6 +153,8 @@ struct LPassParams {
     int fast;    // production shape: 256 threads, 16 staging units per thread (LStage valid)
     const ME<Real>* bmats;  // vmap: DEVICE [batch][bstride] matrix elements (nullptr: shared matrices in m[])
     int bstride;
+    int vtl;                // pipelined kernel: log2(tiles per state vector)
+    uint64_t ntiles;        // pipelined kernel: tiles over all vectors of the batch
     LOut out;
     LStage stage;
     LRound r[LP_MAX_ROUNDS];
@@ -579,6 +581,273 @@ __global__ void __launch_bounds__(256, (sizeof(Real) == 4 && !BATCHED) ? 3 : 2) 
     lstage_out_fast<C>(p.stage, p.out, vec, smem_raw, tid);
 }
 
+// ------------------------------------------------------------------------------------------------
+// pipelined production shape (complex64): one persistent CTA per SM, three 64 KiB tile buffers
+// ------------------------------------------------------------------------------------------------
+// lpass_fast_kernel runs load -> rounds -> write-back serially inside a CTA and relies on the three
+// CTAs of an SM to overlap each other's phases; measured, a pass costs about 0.66 x (HBM time) more
+// than max(HBM, FP32).  Here the phases are split by warp role instead:
+//
+//   4 producer warps                           2 compute groups of 8 warps (tiles j = g, g + 2, ...)
+//   ----------------------------------         -------------------------------------------------
+//   wait empty[j % 3]                          wait full[j % 3]
+//   LDGSTS tile j -> buf[j % 3]                rounds on buf[j % 3]   (bar.sync 1 + g between rounds)
+//   cp.async.mbarrier.arrive full[j % 3]       write-back through the final index map
+//                                              arrive empty[j % 3]
+//
+// so while the two groups work on two buffers the third one is always being filled, and the two
+// groups are in different phases of their tiles (one in its FMA rounds while the other writes back).
+// Same staging swizzle, same rounds, same write-back as lpass_fast_kernel: the parameter block is
+// the same one.
+constexpr int PL_STAGES = 3;
+constexpr int PL_GROUP = 256;
+constexpr int PL_NGROUPS = 2;
+constexpr int PL_PRODUCERS = 128;
+constexpr int PL_THREADS = PL_GROUP * PL_NGROUPS + PL_PRODUCERS;
+constexpr uint32_t PL_TILE_BYTES = 64 * 1024;
+
+__device__ __forceinline__ uint32_t pl_smem(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void pl_mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(pl_smem(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pl_mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(pl_smem(b)) : "memory");
+}
+// arrive once every cp.async this thread has issued so far has landed (counted in the init count)
+__device__ __forceinline__ void pl_cp_async_arrive(uint64_t* b) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(pl_smem(b)) : "memory");
+}
+__device__ __forceinline__ void pl_mbar_wait(uint64_t* b, uint32_t parity) {
+    const uint32_t a = pl_smem(b);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void pl_bar_group(uint32_t id) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "n"(PL_GROUP) : "memory"); }
+
+template <typename Real>
+__global__ void __launch_bounds__(PL_THREADS, 1) lpass_pipe_kernel(const __grid_constant__ LPassParams<Real> p) {
+    using C = typename CT<Real>::type;
+    constexpr int APU = 16 / (int)sizeof(C);
+    constexpr int NIT = sizeof(C) == 8 ? 2 : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[PL_STAGES];
+    __shared__ __align__(8) uint64_t empty[PL_STAGES];
+
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < PL_STAGES; ++s) {
+            pl_mbar_init(&full[s], PL_PRODUCERS);
+            pl_mbar_init(&empty[s], PL_GROUP);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint64_t first = blockIdx.x, stride = gridDim.x;
+    const uint32_t nmine = p.ntiles > first ? (uint32_t)((p.ntiles - first + stride - 1) / stride) : 0u;
+    const uint64_t vmask = (1ull << p.vtl) - 1ull;
+    auto tile_ptr = [&](uint32_t j) -> C* {
+        const uint64_t t = first + (uint64_t)j * stride;
+        return p.state + ((t >> p.vtl) << p.g.n) + tile_base(p.g, t & vmask);
+    };
+
+    // warp-uniform role (the shuffle tells the compiler so: without it everything below counts as
+    // divergent code and the matrices leave the uniform registers -- LDC + MOV instead of LDCU / UR operands)
+    const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    if (warp >= PL_GROUP * PL_NGROUPS / 32) {
+        // ---- producers: thread pt stages the units of the virtual staging threads pt and pt + 128 ----
+        const uint32_t pt = tid - PL_GROUP * PL_NGROUPS;
+        const uint64_t go0 = lstage_thread_goff<APU>(p.stage, pt), go1 = lstage_thread_goff<APU>(p.stage, pt + PL_PRODUCERS);
+        const uint32_t s0 = swz_unit(pt) << 4, s1 = swz_unit(pt + PL_PRODUCERS) << 4;
+        uint32_t s = 0, ph = 1;  // ph: parity of the previous completion of empty[s] (none yet for the first lap)
+        for (uint32_t j = 0; j < nmine; ++j) {
+            if (j >= PL_STAGES) pl_mbar_wait(&empty[s], ph);
+            unsigned char* buf = smem_raw + s * PL_TILE_BYTES;
+            const C* v = tile_ptr(j);
+            const C* v0 = v + go0;
+            const C* v1 = v + go1;
+#pragma unroll
+            for (int i = 0; i < LP_FAST_ITERS; ++i) cp_async16(buf + (s0 ^ p.stage.sin[i]), v0 + p.stage.goff[i]);
+#pragma unroll
+            for (int i = 0; i < LP_FAST_ITERS; ++i) cp_async16(buf + (s1 ^ p.stage.sin[i]), v1 + p.stage.goff[i]);
+            pl_cp_async_arrive(&full[s]);
+            if (++s == PL_STAGES) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+        cp_async_wait_all();
+        return;
+    }
+
+    // ---- compute groups ----
+    const uint32_t grp = warp >> 3, lt = tid & (PL_GROUP - 1);
+    uint32_t s = grp, ph = 0;  // tile j lives in buffer j % 3; ph = (j / 3) & 1
+    for (uint32_t j = grp; j < nmine; j += PL_NGROUPS) {
+        unsigned char* buf = smem_raw + s * PL_TILE_BYTES;
+        pl_mbar_wait(&full[s], ph);
+        for (int r = 0; r < p.nrounds; ++r) {
+            lround_thread_fast<C, Real, NIT>(buf, p.r[r], p.m, lt);
+            pl_bar_group(1 + grp);
+        }
+        lstage_out_fast<C>(p.stage, p.out, tile_ptr(j), buf, lt);
+        pl_mbar_arrive(&empty[s]);
+        s += PL_NGROUPS;
+        if (s >= PL_STAGES) {
+            s -= PL_STAGES;
+            ph ^= 1u;
+        }
+    }
+}
+
+// Variant B of the pipeline: two compute groups of 512 threads (one 16-amplitude group per thread and
+// round), no producer warps -- the group that has written a tile back refills the buffer itself (for
+// the tile the OTHER group will work on three tiles later).  32 warps at 64 registers.
+constexpr int PB_GROUP = 512;
+__device__ __forceinline__ void pb_bar_group(uint32_t id) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "n"(PB_GROUP) : "memory"); }
+
+template <typename C, typename Real>
+__device__ __forceinline__ void lround_thread_512(unsigned char* tile, const LRound& R, const ME<Real>* mats, uint32_t tid) {
+    uint32_t b = R.d;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) b ^= (0u - ((tid >> i) & 1u)) & R.gcol[i];
+    const bool vec = sizeof(C) == 8 && ((R.ncodes >> 8) & 1u);
+    lround_group<C, Real>(tile, b, R, mats, vec);
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(2 * PB_GROUP, 1) lpass_pipe2_kernel(const __grid_constant__ LPassParams<Real> p) {
+    using C = typename CT<Real>::type;
+    constexpr int APU = 16 / (int)sizeof(C);
+    constexpr int SH = APU == 2 ? 1 : 0;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[PL_STAGES];
+
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < PL_STAGES; ++s) pl_mbar_init(&full[s], PB_GROUP);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint64_t first = blockIdx.x, stride = gridDim.x;
+    const uint32_t nmine = p.ntiles > first ? (uint32_t)((p.ntiles - first + stride - 1) / stride) : 0u;
+    const uint64_t vmask = (1ull << p.vtl) - 1ull;
+    auto tile_ptr = [&](uint32_t j) -> C* {
+        const uint64_t t = first + (uint64_t)j * stride;
+        return p.state + ((t >> p.vtl) << p.g.n) + tile_base(p.g, t & vmask);
+    };
+    const uint32_t grp = __shfl_sync(0xffffffffu, tid >> 9, 0), lt = tid & (PB_GROUP - 1);  // warp-uniform
+    // staging: thread lt owns the units (lt & 255) + 256 i for i in [8 * (lt >> 8), 8 * (lt >> 8) + 8)
+    const uint32_t vt = lt & 255u, half = lt >> 8;
+    const uint64_t tg = lstage_thread_goff<APU>(p.stage, vt);
+    const uint32_t sin0 = swz_unit(vt) << 4;
+    uint32_t aout = p.out.d;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) aout ^= (0u - ((vt >> i) & 1u)) & p.out.col[i + SH];
+    const bool ovec = APU == 1 || p.out.vec;
+    const uint32_t oc0 = p.out.col[0];
+
+    auto issue_load = [&](uint32_t j, uint32_t s) {
+        unsigned char* buf = smem_raw + s * PL_TILE_BYTES;
+        const C* v = tile_ptr(j) + tg;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int ii = (int)half * 8 + i;
+            cp_async16(buf + (sin0 ^ p.stage.sin[ii]), v + p.stage.goff[ii]);
+        }
+        pl_cp_async_arrive(&full[s]);
+    };
+    // prologue: group 0 fills buffers 0 and 2 (its first two tiles), group 1 buffer 1
+    if (grp < nmine) issue_load(grp, grp);
+    if (grp == 0 && 2 < nmine) issue_load(2, 2);
+
+    uint32_t s = grp, ph = 0;
+    for (uint32_t j = grp; j < nmine; j += 2) {
+        unsigned char* buf = smem_raw + s * PL_TILE_BYTES;
+        pl_mbar_wait(&full[s], ph);
+        for (int r = 0; r < p.nrounds; ++r) {
+            lround_thread_512<C, Real>(buf, p.r[r], p.m, lt);
+            pb_bar_group(1 + grp);
+        }
+        {
+            C* g = tile_ptr(j) + tg;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int ii = (int)half * 8 + i;
+                const uint32_t ai = aout ^ p.stage.sout[ii];
+                Unit16 q;
+                if (ovec) {
+                    q = *reinterpret_cast<const Unit16*>(buf + ai);
+                } else {
+                    C* qc = reinterpret_cast<C*>(&q);
+                    qc[0] = *reinterpret_cast<const C*>(buf + ai);
+                    qc[1 % APU] = *reinterpret_cast<const C*>(buf + (ai ^ oc0));
+                }
+                *reinterpret_cast<Unit16*>(g + p.stage.goff[ii]) = q;
+            }
+        }
+        if (j + PL_STAGES < nmine) {
+            pb_bar_group(1 + grp);  // every thread of the group has read its part of the buffer
+            issue_load(j + PL_STAGES, s);
+        }
+        s += 2;
+        if (s >= PL_STAGES) {
+            s -= PL_STAGES;
+            ph ^= 1u;
+        }
+    }
+    cp_async_wait_all();
+}
+
+static void launch_pipe(const LPassParams<float>& q, unsigned grid, cudaStream_t st) {
+    const char* e = getenv("TCB200_PIPE");
+    if (e && e[0] == '2') lpass_pipe2_kernel<float><<<grid, 2 * PB_GROUP, PL_STAGES * PL_TILE_BYTES, st>>>(q);
+    else lpass_pipe_kernel<float><<<grid, PL_THREADS, PL_STAGES * PL_TILE_BYTES, st>>>(q);
+}
+static void launch_pipe(const LPassParams<double>&, unsigned, cudaStream_t) {}
+
+// Opt-in (TCB200_PIPE=1: producer warps + two groups of 8 warps; =2: two self-loading groups of 16
+// warps at 64 registers).  Both are bit-identical to lpass_fast_kernel and both are SLOWER on the
+// measured circuits (config-4 recipe at n = 30: 127 ms fast, 143 ms / 185 ms pipelined;
+// profiles/README.md "Pipelined gate pass"): the rounds are issue-bound, and 16 always-computing warps
+// issue less than the 24 warps of three independent CTAs even though those stall on their own staging.
+// (read at every launch: the tests and the A/B scripts flip it inside one process)
+static bool pipe_enabled() {
+    const char* e = getenv("TCB200_PIPE");
+    return e && (e[0] == '1' || e[0] == '2');
+}
+// test knobs: TCB200_PIPE_MIN_TILES (tiles from which the pipeline is used; default 4 per SM),
+// TCB200_PIPE_GRID (persistent CTAs; default one per SM)
+static long pipe_knob(const char* name, long dflt) {
+    const char* e = getenv(name);
+    if (!e || !e[0]) return dflt;
+    const long v = atol(e);
+    return v > 0 ? v : dflt;
+}
+
+static int lp_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+            (void)cudaGetLastError();
+            sms = 0;
+        }
+    }
+    return sms;
+}
+
 // pinned staging + events for the per-element matrix blobs of batched passes (two buffers, so that
 // the host can fill the blob of pass i + 1 while the copy of pass i is still in flight)
 struct BlobStage {
@@ -655,7 +924,21 @@ static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, cons
         if (q.fast) lpass_fast_kernel<Real, true><<<grid, block, smem, st>>>(q);
         else lpass_kernel<Real, true><<<grid, block, smem, st>>>(q);
     } else {
-        if (q.fast) lpass_fast_kernel<Real, false><<<grid, block, smem, st>>>(q);
+        const uint64_t total = ntiles * (uint64_t)batch;
+        const int sms = lp_sm_count();
+        // the pipeline pays off once every SM walks a few tiles
+        if (q.fast && sizeof(Real) == 4 && sms > 0 && pipe_enabled() && total >= (uint64_t)pipe_knob("TCB200_PIPE_MIN_TILES", 4l * sms)) {
+            static bool pattr = false;
+            if (!pattr) {
+                TCB_CUDA(cudaFuncSetAttribute(lpass_pipe_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PL_STAGES * PL_TILE_BYTES)));
+                TCB_CUDA(cudaFuncSetAttribute(lpass_pipe2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PL_STAGES * PL_TILE_BYTES)));
+                pattr = true;
+            }
+            q.vtl = nbits - q.g.T;
+            q.ntiles = total;
+            const uint64_t ctas = (uint64_t)pipe_knob("TCB200_PIPE_GRID", sms);
+            launch_pipe(q, (unsigned)(total < ctas ? total : ctas), st);
+        } else if (q.fast) lpass_fast_kernel<Real, false><<<grid, block, smem, st>>>(q);
         else lpass_kernel<Real, false><<<grid, block, smem, st>>>(q);
     }
     TCB_LAUNCH_CHECK("lpass_kernel");

@@ -186,6 +186,33 @@ def test_gate_pass_matches_dense_pass_at_n26():
     assert abs(float(s1.norm2()[0]) - 1.0) < 1e-5
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_pipelined_gate_pass_is_bit_identical(mode, monkeypatch):
+    """the opt-in persistent pipelines (lpass_pipe_kernel / lpass_pipe2_kernel: three tile buffers per
+    SM, mbarrier hand-over) run the same rounds as lpass_fast_kernel: identical bits, vs the oracle too"""
+    n, depth = 20, 6
+    rc = recipes.random_circuit(n, depth, 7)
+    ops = [GateOp(q, np.asarray(orc.gate_matrix(name, **p)), name) for name, q, p in rc]
+    blocks = fusion.fuse_structured(ops, n, 2)
+
+    def run():
+        st = DeviceState(n, "complex64")
+        st.init_zero()
+        st.apply_planned(blocks)
+        return st.buf.clone()
+
+    monkeypatch.delenv("TCB200_PIPE", raising=False)
+    base = run()
+    for grid in ("3", "77", "1000"):  # many tiles per CTA, uneven split, more CTAs than tiles
+        monkeypatch.setenv("TCB200_PIPE", mode)
+        monkeypatch.setenv("TCB200_PIPE_MIN_TILES", "1")
+        monkeypatch.setenv("TCB200_PIPE_GRID", grid)
+        got = run()
+        assert torch.equal(got, base), (mode, grid)
+    ref = orc.run_gatelist(n, rc).state()
+    assert _relerr(base[0].cpu().numpy(), ref) < TOL["complex64"]
+
+
 @pytest.mark.parametrize("dtype", ["complex64", "complex128"])
 @pytest.mark.parametrize("n", [6, 15])
 def test_batched_gate_pass_vmap_vs_oracle(dtype, n):
