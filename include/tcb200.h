@@ -328,14 +328,47 @@ int tcb200_masked_norm2(const void* state, int nbits, int dtype, uint64_t mask, 
  * in and out may be the same buffer. */
 int tcb200_probability_state(const void* in, void* out, int nbits, int dtype, int mode, void* stream);
 
+/* <psi| H |psi> for a sparse operator kept on the DEVICE in COO form (rows / cols: int64 amplitude
+ * indices in the reference's basis order, vals: complex128), one value per batch element.
+ * Replaces templates/measurements.py:173-188 (sparse_expectation: backend.sparse_dense_matmul +
+ * adjoint(state) @ tmp) and the dense branch of operator_expectation (measurements.py:156-170).
+ * Pauli-sum Hamiltonians do not take this route: quantum.PauliStringSum2COO keeps the strings and
+ * they go through tcb200_expect_*.  out_dev: DEVICE double [batch][2] (re, im).  Indices must be
+ * below 2^nbits (checked by the caller when the operator is uploaded).  Float64 accumulation,
+ * fixed-order reduction. */
+size_t tcb200_coo_expectation_workspace_bytes(int64_t nnz, int64_t batch);
+int tcb200_coo_expectation(const void* state, int nbits, int dtype, int64_t nnz, const int64_t* rows_dev, const int64_t* cols_dev,
+                           const void* vals_dev, double* out_dev, int64_t batch, void* workspace, size_t ws_bytes, void* stream);
+
+/* dst = sum_t coef_t P_t src for Pauli strings P_t given as (flip, sign) masks, coef_t = w_t (-i)^{ny_t}
+ * (HOST arrays; coef: [nterms][2] doubles): row r of quantum.py:1461-1482,
+ *     dst_r = sum_t coef_t (-1)^{popc(r & sign_t)} src_{r ^ flip_t}.
+ * This is lambda = H psi, the seed of the adjoint-state gradient sweep that stands in for the
+ * backend autodiff of backends/jax_backend.py:668-776.  src and dst are distinct device buffers of
+ * `batch` states. */
+size_t tcb200_apply_pauli_sum_workspace_bytes(int nterms);
+int tcb200_apply_pauli_sum(const void* src, void* dst, int nbits, int dtype, int nterms, const uint64_t* flip, const uint64_t* sign,
+                           const double* coef, int64_t batch, void* workspace, size_t ws_bytes, void* stream);
+
+/* <bra| G_j |ket> for up to tcb200_transition_local_max_ops() local operators G_j (1 or 2 bits each;
+ * ops_bits ascending amplitude-index bits, ops_mats row-major complex128 with matrix index bit i <->
+ * bit i of the operator, HOST arrays) between two device states, all in one launch.  In the adjoint
+ * sweep G_j = dM_j/dtheta M_j^+, bra = lambda_j, ket = psi_j, and 2 Re of the result is the
+ * derivative of the energy through gate j (jax_backend.py:668-776).  out_dev: DEVICE double [nops][2]. */
+int tcb200_transition_local_max_ops(void);
+size_t tcb200_transition_local_workspace_bytes(int nops);
+int tcb200_transition_local(const void* bra, const void* ket, int nbits, int dtype, int nops, const int* ops_k, const int* ops_bits,
+                            const double* ops_mats, double* out_dev, void* workspace, size_t ws_bytes, void* stream);
+
 /* Number of kernel launches issued by this process through the library so far. */
 int64_t tcb200_launch_count(void);
 
 /* How many of those were the persistent TMA pipeline (tpass_kernel) rather than the LDGSTS-staged
- * cpass_kernel: tcb200_apply_pass_host picks the pipeline whenever the pass uses the production
- * 64 KiB tile, the state is larger than one tile and the driver exports cuTensorMapEncodeTiled
- * (TCB200_TMA=0 forces the staged kernel; TCB200_TMA_STRICT=1 turns a failed tensor-map encode
- * into an error instead of a fallback). */
+ * cpass_kernel.  The pipeline is OPT-IN (TCB200_TMA=1: it measured slower than the staged kernels,
+ * profiles/README.md); with it enabled tcb200_apply_pass_host uses it whenever the pass has the
+ * production 64 KiB tile, the state is larger than one tile and the driver exports
+ * cuTensorMapEncodeTiled (TCB200_TMA_STRICT=1 turns a failed tensor-map encode into an error
+ * instead of a fallback). */
 int64_t tcb200_tma_pass_count(void);
 
 #ifdef __cplusplus

@@ -30,7 +30,12 @@ def energy(p):
 
 p = np.random.default_rng(0).uniform(0, 2, size=(2 * layers, n))
 vg = tc.backend.value_and_grad(energy)
-for rep in range(2):
+from tensorcircuit_b200 import autodiff  # noqa: E402
+
+if len(sys.argv) > 3 and sys.argv[3] == "shift":
+    autodiff._ADJOINT = False
+print("adjoint sweep" if autodiff._ADJOINT else "shift rule", flush=True)
+for rep in range(3):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     v, g = vg(p)
@@ -41,4 +46,5 @@ h = 1e-3
 e = np.zeros_like(p)
 e[1, 2] = h
 fd = (float(energy(p + e)) - float(energy(p - e))) / (2 * h)
-print("d/dp[1,2]: shift rule %.6f  central difference %.6f" % (g[1, 2], fd))
+print(autodiff.ADJOINT_STATS)
+print("d/dp[1,2]: gradient %.6f  central difference %.6f" % (g[1, 2], fd))

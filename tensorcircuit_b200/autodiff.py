@@ -11,8 +11,12 @@ rule that holds for ANY gate (no generator assumption, no truncation error), nee
 simulations with non-unitary matrices, and therefore runs on the existing kernels: all shifted
 circuits of a query are evaluated as ONE vmap-style batch (batched matrices for the shifted
 gates only).  Cost: two batch elements per (parameter, dependent gate) pair, like a
-parameter-shift gradient; the adjoint-state sweep (O(1) simulations) is the next step
-(DESIGN.md 7).
+parameter-shift gradient.  That path is the FALLBACK.  The default is the adjoint-state sweep
+(``_adjoint_contrib``, O(1) simulations): with lambda = H psi and both states swept backwards
+through the circuit, the derivative through gate j is 2 Re <lambda_j| dM_j M_j^+ |psi_j> -- one
+forward simulation, one backward sweep over a two-row state, one reduction launch per group of
+commuting taps (csrc/sparse.cu).  It needs unitary gates and derivative-carrying gates on <= 2 qubits;
+anything else goes through the shift rule.
 
 What is differentiated is the function itself, not a restricted form of it:
   * dM_j/d theta_k comes from re-running the *recording* of ``f`` (no device work) at
@@ -190,6 +194,106 @@ def _shift_batch(q: _Query, base: _Query, shifts: List[Tuple[int, np.ndarray]], 
     return out
 
 
+_ADJOINT = True      # False: always use the shift rule (tests compare the two)
+ADJOINT_STATS = {"sweeps": 0, "flushes": 0, "tap_launches": 0, "fallbacks": 0}
+
+
+def _embed(m: np.ndarray, qubits: Sequence[int], union: Sequence[int]) -> np.ndarray:
+    """operator ``m`` on ``qubits`` (caller's order, big-endian) as a matrix on the ascending qubit list ``union``"""
+    from .fusion import embed_apply
+
+    return embed_apply(np.eye(1 << len(union), dtype=np.complex128), list(union), np.asarray(m, dtype=np.complex128), list(qubits))
+
+
+def _commute(a: np.ndarray, qa: Sequence[int], b: np.ndarray, qb: Sequence[int]) -> bool:
+    if not set(qa) & set(qb):
+        return True
+    da = np.count_nonzero(a - np.diag(np.diagonal(a))) == 0
+    db = np.count_nonzero(b - np.diag(np.diagonal(b))) == 0
+    if da and db:
+        return True
+    u = sorted(set(qa) | set(qb))
+    A, B = _embed(a, qa, u), _embed(b, qb, u)
+    return bool(np.abs(A @ B - B @ A).max() < 1e-10)
+
+
+def _sorted_local(m: np.ndarray, qubits: Sequence[int], n: int) -> Tuple[List[int], np.ndarray]:
+    """(ascending amplitude-index bits, matrix with index bit i <-> bits[i]) of an operator given on
+    ``qubits`` in the caller's order"""
+    qs = sorted(qubits)
+    return [n - 1 - q for q in reversed(qs)], _embed(m, qubits, qs)
+
+
+def _adjoint_contrib(q: _Query, weights: np.ndarray, lst: List[Tuple[int, int, np.ndarray]], dtype: str) -> Optional[np.ndarray]:
+    """d(sum_t weights_t Re E_t)/d theta through gate j with dM_j = D, for every (k, j, D) of ``lst``, by
+    one backward sweep.  None when the circuit is outside the sweep's scope (caller falls back)."""
+    n = q.nqubits
+    if n > 31:
+        return None
+    Mdag: List[np.ndarray] = []
+    for qubits, M in q.ops:
+        if M.ndim != 2 or np.abs(M @ M.conj().T - np.eye(M.shape[0])).max() > 1e-9:
+            return None  # non-unitary gate (Kraus branch, projector): cannot be undone by its adjoint
+        Mdag.append(M.conj().T)
+    taps: Dict[int, List[int]] = {}
+    for idx, (_, j, D) in enumerate(lst):
+        if len(q.ops[j][0]) > 2:
+            return None
+        taps.setdefault(j, []).append(idx)
+    st2 = _engine.DeviceState(n, dtype, 2)
+    circ = q.circ
+    src = getattr(circ, "_state", None)
+    if src is None or getattr(circ, "_applied", -1) != len(q.ops) or len(circ._ops) != len(q.ops) or getattr(src, "batch", 0) != 1:
+        c = _circuit.Circuit(n)  # the recorded circuit has moved on: one more forward simulation
+        for qubits, M in q.ops:
+            c.any(*qubits, unitary=M)
+        src = c._ensure_state()
+    st2.copy_row_from(0, src, 0)
+    coef = [w * (-1j) ** (int(y) & 3) for w, y in zip(weights, q.ny)]
+    keep = [t for t in range(len(coef)) if coef[t] != 0]
+    if not keep:
+        return np.zeros(len(lst))
+    st2.apply_pauli_sum_rows(0, 1, [q.fl[t] for t in keep], [q.sg[t] for t in keep], [coef[t] for t in keep])
+    out = np.zeros(len(lst))
+    pending_undo: List[Tuple[Tuple[int, ...], np.ndarray]] = []
+    pending_taps: List[Tuple[int, List[int], np.ndarray]] = []
+    fuser = _circuit.Circuit(n)
+
+    def flush() -> None:
+        if pending_taps:
+            vals = st2.transition_local(1, 0, [(bits, G) for _, bits, G in pending_taps])
+            for (idx, _, _), v in zip(pending_taps, vals):
+                out[idx] = 2.0 * float(np.real(v))
+            ADJOINT_STATS["tap_launches"] += 1
+            pending_taps.clear()
+        if pending_undo:
+            from .fusion import GateOp
+
+            blocks = fuser._fuse([GateOp(tuple(qs), m) for qs, m in pending_undo], n)
+            if hasattr(st2, "apply_planned") and fuser.use_passes:
+                st2.apply_planned(blocks)
+            else:
+                st2.apply_blocks(blocks)
+            ADJOINT_STATS["flushes"] += 1
+            pending_undo.clear()
+
+    jmin = min(taps)
+    for j in range(len(q.ops) - 1, jmin - 1, -1):
+        qubits, M = q.ops[j]
+        for idx in taps.get(j, []):
+            G = lst[idx][2] @ Mdag[j]
+            if any(not _commute(G, qubits, m, qs) for qs, m in pending_undo):
+                flush()  # taps registered so far see the current states; then the states move on
+            bits, Gs = _sorted_local(G, qubits, n)
+            pending_taps.append((idx, bits, Gs))
+        if j > jmin:
+            pending_undo.append((tuple(qubits), Mdag[j]))
+    pending_undo.clear()  # nobody needs the states below the lowest tap
+    flush()
+    ADJOINT_STATS["sweeps"] += 1
+    return out
+
+
 def value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0, has_aux: bool = False) -> Callable[..., Any]:
     single = isinstance(argnums, int)
     nums: Tuple[int, ...] = (argnums,) if single else tuple(argnums)  # type: ignore[assignment]
@@ -330,9 +434,14 @@ def value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0
                 merged.fl = [x for m in members for x in base.queries[m].fl]
                 merged.sg = [x for m in members for x in base.queries[m].sg]
                 merged.ny = [x for m in members for x in base.queries[m].ny]
-                diff = _shift_batch(merged, merged, [(j, D) for _, j, D in lst], dtype)  # [nshift, nterms]
-                de = 0.5 * np.real(diff)  # d E_t / d theta through that gate
-                contrib = de @ np.concatenate([dl_de[m] for m in members])
+                wts = np.concatenate([dl_de[m] for m in members])
+                merged.circ, merged.ny = base.queries[qi].circ, list(merged.ny)
+                contrib = _adjoint_contrib(merged, wts, lst, dtype) if _ADJOINT else None
+                if contrib is None:
+                    ADJOINT_STATS["fallbacks"] += 1
+                    diff = _shift_batch(merged, merged, [(j, D) for _, j, D in lst], dtype)  # [nshift, nterms]
+                    de = 0.5 * np.real(diff)  # d E_t / d theta through that gate
+                    contrib = de @ wts
                 for (k, _, _), c in zip(lst, contrib):
                     g[k] += c
             grads.append(g.reshape(theta.shape))

@@ -150,6 +150,40 @@ class B200Backend:
     def transpose(self, a: Any, perm: Optional[Sequence[int]] = None) -> Any:
         return np.transpose(_np(a), perm)
 
+    # -- sparse operators (abstract_backend.py: coo_sparse_matrix / sparse_dense_matmul / to_dense / is_sparse) --
+    def coo_sparse_matrix(self, indices: Any, values: Any, shape: Any) -> Any:
+        """numpy_backend.py:303-309 returns a scipy COO matrix; so does this (host object -- it is uploaded
+        once, on first use by ``operator_expectation`` / ``sparse_expectation``)."""
+        import scipy.sparse as sp
+
+        idx = np.asarray(indices)
+        return sp.coo_matrix((np.asarray(values), (idx[:, 0], idx[:, 1])), shape=tuple(shape))
+
+    def coo_sparse_matrix_from_numpy(self, a: Any) -> Any:
+        return a
+
+    def is_sparse(self, a: Any) -> bool:
+        from .engine import DeviceCOO
+        from .quantum import PauliSum
+
+        return isinstance(a, (PauliSum, DeviceCOO)) or hasattr(a, "tocoo")
+
+    def to_dense(self, sp_a: Any) -> Any:
+        from .quantum import PauliSum
+
+        if isinstance(sp_a, PauliSum):
+            return sp_a.todense()
+        return np.asarray(sp_a.todense())
+
+    def sparse_dense_matmul(self, sp_a: Any, b: Any) -> Any:
+        """host-side (scipy) product for small operands; the engine's own use of a sparse Hamiltonian is
+        ``templates.measurements.sparse_expectation``, which never forms H|psi> on the host"""
+        from .quantum import PauliSum
+
+        if isinstance(sp_a, PauliSum):
+            sp_a = sp_a.tocoo()
+        return sp_a @ self.numpy(b)
+
     def adjoint(self, a: Any) -> Any:
         return np.conj(np.transpose(_np(a)))
 

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libtcb200.so")
-SOURCES = ["abi.cu", "apply.cu", "lpass.cu", "tpass.cu", "reduce.cu", "expect.cu", "xexpect.cu", "host.cu"]
+SOURCES = ["abi.cu", "apply.cu", "lpass.cu", "tpass.cu", "reduce.cu", "expect.cu", "xexpect.cu", "sparse.cu", "host.cu"]
 
 
 def _nvcc() -> str:

@@ -1,0 +1,355 @@
+// Sparse-operator expectation  <psi| H |psi>  for an operator kept on the device in COO form.
+//
+// Replaces tensorcircuit/templates/measurements.py:173-188 (sparse_expectation: backend
+// sparse_dense_matmul of the COO Hamiltonian with the ket, then <psi|tmp>) and the dense branch of
+// operator_expectation (measurements.py:156-170) for operators that are NOT Pauli sums; Pauli sums
+// built by quantum.PauliStringSum2COO never become a matrix here -- they stay strings and go
+// through the Pauli kernels (expect.cu / xexpect.cu).
+//
+// One thread per stored element k:  acc += conj(psi[row_k]) * val_k * psi[col_k], float64
+// accumulation, grid-stride loop over a fixed grid, fixed-order block and grid reductions (the
+// result does not depend on timing).  The kernel is bound by the 32 bytes of (row, col, value) per
+// element plus two gathered amplitudes; the operator is uploaded once and stays resident over the
+// iterations of a VQE loop.
+//
+// The same file holds the two kernels of the adjoint-state gradient (autodiff.py; replaces the
+// backend autodiff of tensorcircuit/backends/jax_backend.py:668-776 for losses built from
+// expectation values):
+//   * pauli_sum_kernel:  dst = sum_t w_t P_t src        (lambda = H psi, the seed of the backward sweep;
+//                        closed form of the rows of quantum.py:1461-1482)
+//   * transition_kernel: <bra| G_j |ket> for a list of local (<= 2-bit) operators G_j = dM_j/dtheta M_j^+,
+//                        every operator of a launch evaluated on the same pair of states.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tcb {
+
+__device__ __forceinline__ double sp_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+constexpr int COO_THREADS = 256;
+constexpr int COO_MAX_CTAS = 148 * 8;
+
+template <typename C>
+__global__ void __launch_bounds__(COO_THREADS) coo_expect_kernel(const C* __restrict__ state, int nbits, long long nnz,
+                                                                 const long long* __restrict__ rows, const long long* __restrict__ cols,
+                                                                 const double2* __restrict__ vals, double* __restrict__ partials) {
+    __shared__ double red[COO_THREADS / 32][2];
+    const C* psi = state + ((uint64_t)blockIdx.y << nbits);
+    double re = 0.0, im = 0.0;
+    for (long long k = (long long)blockIdx.x * COO_THREADS + threadIdx.x; k < nnz; k += (long long)gridDim.x * COO_THREADS) {
+        const C a = psi[rows[k]];
+        const C b = psi[cols[k]];
+        const double2 v = vals[k];
+        const double tr = v.x * (double)b.x - v.y * (double)b.y;  // val * psi[col]
+        const double ti = v.x * (double)b.y + v.y * (double)b.x;
+        re += (double)a.x * tr + (double)a.y * ti;  // conj(psi[row]) * t
+        im += (double)a.x * ti - (double)a.y * tr;
+    }
+    re = sp_warp_sum(re);
+    im = sp_warp_sum(im);
+    const int tid = threadIdx.x;
+    if ((tid & 31) == 0) {
+        red[tid >> 5][0] = re;
+        red[tid >> 5][1] = im;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        re = im = 0.0;
+        for (int w = 0; w < COO_THREADS / 32; ++w) {
+            re += red[w][0];
+            im += red[w][1];
+        }
+        double* o = partials + ((uint64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
+        o[0] = re;
+        o[1] = im;
+    }
+}
+
+__global__ void __launch_bounds__(COO_THREADS) coo_final_kernel(const double* __restrict__ partials, int nctas, double* __restrict__ out) {
+    __shared__ double red[COO_THREADS / 32][2];
+    const double* src = partials + (uint64_t)blockIdx.x * nctas * 2;
+    const int tid = threadIdx.x;
+    double re = 0.0, im = 0.0;
+    for (int c = tid; c < nctas; c += COO_THREADS) {
+        re += src[2 * c];
+        im += src[2 * c + 1];
+    }
+    re = sp_warp_sum(re);
+    im = sp_warp_sum(im);
+    if ((tid & 31) == 0) {
+        red[tid >> 5][0] = re;
+        red[tid >> 5][1] = im;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        re = im = 0.0;
+        for (int w = 0; w < COO_THREADS / 32; ++w) {
+            re += red[w][0];
+            im += red[w][1];
+        }
+        out[2 * blockIdx.x] = re;
+        out[2 * blockIdx.x + 1] = im;
+    }
+}
+
+static unsigned coo_grid(int64_t nnz) {
+    int64_t g = (nnz + COO_THREADS - 1) / COO_THREADS;
+    if (g < 1) g = 1;
+    if (g > COO_MAX_CTAS) g = COO_MAX_CTAS;
+    return (unsigned)g;
+}
+
+
+// ---- dst = sum_t coef_t (-1)^{parity(r & sign_t)} src[r ^ flip_t] -------------------------------------
+// Terms arrive sorted by flip mask (host), so that strings with the same flip share one partner load;
+// they are staged through shared memory in chunks.
+constexpr int PS_CHUNK = 256;
+
+struct PauliTerm {
+    uint64_t flip, sign;
+    double cr, ci;
+};
+
+template <typename C>
+__global__ void __launch_bounds__(256) pauli_sum_kernel(const C* __restrict__ src, C* __restrict__ dst, int nbits, int nterms,
+                                                        const PauliTerm* __restrict__ terms) {
+    __shared__ PauliTerm sh[PS_CHUNK];
+    const uint64_t r = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool live = r < (1ull << nbits);
+    const C* s = src + ((uint64_t)blockIdx.y << nbits);
+    double ar = 0.0, ai = 0.0;
+    for (int t0 = 0; t0 < nterms; t0 += PS_CHUNK) {
+        const int nc = nterms - t0 < PS_CHUNK ? nterms - t0 : PS_CHUNK;
+        __syncthreads();
+        if ((int)threadIdx.x < nc) sh[threadIdx.x] = terms[t0 + threadIdx.x];
+        __syncthreads();
+        if (!live) continue;
+        int t = 0;
+        while (t < nc) {
+            const uint64_t f = sh[t].flip;
+            const C b = s[r ^ f];
+            double cr = 0.0, ci = 0.0;
+            do {
+                const double sg = (__popcll(r & sh[t].sign) & 1) ? -1.0 : 1.0;
+                cr += sg * sh[t].cr;
+                ci += sg * sh[t].ci;
+                ++t;
+            } while (t < nc && sh[t].flip == f);
+            ar += cr * (double)b.x - ci * (double)b.y;
+            ai += cr * (double)b.y + ci * (double)b.x;
+        }
+    }
+    if (live) {
+        C o;
+        o.x = (decltype(o.x))ar;
+        o.y = (decltype(o.y))ai;
+        dst[((uint64_t)blockIdx.y << nbits) + r] = o;
+    }
+}
+
+// ---- <bra| G_j |ket> for local operators ---------------------------------------------------------------
+constexpr int TR_MAX_OPS = 64;   // operators per launch (kernel-parameter bank)
+constexpr int TR_CTAS = 148;     // CTAs per operator
+
+struct TransOp {
+    int k;          // 1 or 2 bits
+    int b0, b1;     // ascending amplitude-index bit positions
+    int pad;
+    double2 m[16];  // row-major 2^k x 2^k, matrix index bit i <-> bit b_i
+};
+struct TransParams {
+    int nbits, nops;
+    TransOp op[TR_MAX_OPS];
+};
+
+template <typename C>
+__global__ void __launch_bounds__(256) transition_kernel(const C* __restrict__ bra, const C* __restrict__ ket,
+                                                         const __grid_constant__ TransParams p, double* __restrict__ partials) {
+    __shared__ double red[8][2];
+    const TransOp& op = p.op[blockIdx.y];
+    const int k = op.k, D = 1 << k;
+    const uint64_t ngroups = 1ull << (p.nbits - k);
+    double re = 0.0, im = 0.0;
+    for (uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x; g < ngroups; g += (uint64_t)gridDim.x * 256) {
+        // insert a zero at b0 (and b1)
+        uint64_t base = ((g >> op.b0) << (op.b0 + 1)) | (g & ((1ull << op.b0) - 1ull));
+        if (k == 2) base = ((base >> op.b1) << (op.b1 + 1)) | (base & ((1ull << op.b1) - 1ull));
+        double kr[4], ki[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (b < D) {
+                const uint64_t idx = base | ((uint64_t)(b & 1) << op.b0) | (k == 2 ? ((uint64_t)(b >> 1) << op.b1) : 0ull);
+                const C v = ket[idx];
+                kr[b] = (double)v.x;
+                ki[b] = (double)v.y;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            if (a < D) {
+                double tr = 0.0, ti = 0.0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (b < D) {
+                        const double2 m = op.m[a * D + b];
+                        tr += m.x * kr[b] - m.y * ki[b];
+                        ti += m.x * ki[b] + m.y * kr[b];
+                    }
+                }
+                const uint64_t idx = base | ((uint64_t)(a & 1) << op.b0) | (k == 2 ? ((uint64_t)(a >> 1) << op.b1) : 0ull);
+                const C u = bra[idx];
+                re += (double)u.x * tr + (double)u.y * ti;
+                im += (double)u.x * ti - (double)u.y * tr;
+            }
+        }
+    }
+    re = sp_warp_sum(re);
+    im = sp_warp_sum(im);
+    const int tid = threadIdx.x;
+    if ((tid & 31) == 0) {
+        red[tid >> 5][0] = re;
+        red[tid >> 5][1] = im;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        re = im = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            re += red[w][0];
+            im += red[w][1];
+        }
+        double* o = partials + ((uint64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
+        o[0] = re;
+        o[1] = im;
+    }
+}
+
+}  // namespace tcb
+
+using namespace tcb;
+
+extern "C" {
+
+size_t tcb200_coo_expectation_workspace_bytes(int64_t nnz, int64_t batch) {
+    return (size_t)(batch < 1 ? 1 : batch) * coo_grid(nnz) * 2 * sizeof(double);
+}
+
+int tcb200_coo_expectation(const void* state, int nbits, int dtype, int64_t nnz, const int64_t* rows_dev, const int64_t* cols_dev,
+                           const void* vals_dev, double* out_dev, int64_t batch, void* workspace, size_t ws_bytes, void* stream) {
+    if (!state || !out_dev) return fail(TCB200_ERR_ARG, "NULL argument");
+    if (dtype != TCB200_C64 && dtype != TCB200_C128) return fail(TCB200_ERR_ARG, "bad dtype %d", dtype);
+    if (nbits < 1 || nbits > 40) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
+    if (nnz < 0) return fail(TCB200_ERR_ARG, "nnz=%lld out of range", (long long)nnz);
+    if (nnz > 0 && (!rows_dev || !cols_dev || !vals_dev)) return fail(TCB200_ERR_ARG, "NULL operator array");
+    if (batch < 1 || batch > 65535) return fail(TCB200_ERR_ARG, "batch=%lld out of range", (long long)batch);
+    if (!workspace || ws_bytes < tcb200_coo_expectation_workspace_bytes(nnz, batch))
+        return fail(TCB200_ERR_WORKSPACE, "sparse expectation needs %zu bytes of workspace", tcb200_coo_expectation_workspace_bytes(nnz, batch));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned g = coo_grid(nnz);
+    double* partials = static_cast<double*>(workspace);
+    const dim3 grid(g, (unsigned)batch);
+    if (dtype == TCB200_C64)
+        coo_expect_kernel<float2><<<grid, COO_THREADS, 0, st>>>(static_cast<const float2*>(state), nbits, (long long)nnz,
+                                                               reinterpret_cast<const long long*>(rows_dev),
+                                                               reinterpret_cast<const long long*>(cols_dev),
+                                                               static_cast<const double2*>(vals_dev), partials);
+    else
+        coo_expect_kernel<double2><<<grid, COO_THREADS, 0, st>>>(static_cast<const double2*>(state), nbits, (long long)nnz,
+                                                                reinterpret_cast<const long long*>(rows_dev),
+                                                                reinterpret_cast<const long long*>(cols_dev),
+                                                                static_cast<const double2*>(vals_dev), partials);
+    TCB_LAUNCH_CHECK("coo_expect_kernel");
+    coo_final_kernel<<<(unsigned)batch, COO_THREADS, 0, st>>>(partials, (int)g, out_dev);
+    TCB_LAUNCH_CHECK("coo_final_kernel");
+    return 0;
+}
+
+size_t tcb200_apply_pauli_sum_workspace_bytes(int nterms) { return (size_t)(nterms < 1 ? 1 : nterms) * sizeof(PauliTerm); }
+
+int tcb200_apply_pauli_sum(const void* src, void* dst, int nbits, int dtype, int nterms, const uint64_t* flip, const uint64_t* sign,
+                           const double* coef, int64_t batch, void* workspace, size_t ws_bytes, void* stream) {
+    if (!src || !dst || src == dst) return fail(TCB200_ERR_ARG, "src / dst must be two distinct buffers");
+    if (dtype != TCB200_C64 && dtype != TCB200_C128) return fail(TCB200_ERR_ARG, "bad dtype %d", dtype);
+    if (nbits < 1 || nbits > 40) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
+    if (nterms < 1 || !flip || !sign || !coef) return fail(TCB200_ERR_ARG, "nterms=%d / NULL term arrays", nterms);
+    if (batch < 1 || batch > 65535) return fail(TCB200_ERR_ARG, "batch=%lld out of range", (long long)batch);
+    if (!workspace || ws_bytes < tcb200_apply_pauli_sum_workspace_bytes(nterms))
+        return fail(TCB200_ERR_WORKSPACE, "apply_pauli_sum needs %zu bytes of workspace", tcb200_apply_pauli_sum_workspace_bytes(nterms));
+    std::vector<PauliTerm> t((size_t)nterms);
+    for (int i = 0; i < nterms; ++i) {
+        if (flip[i] >> nbits || sign[i] >> nbits) return fail(TCB200_ERR_ARG, "term %d touches a bit outside the state", i);
+        t[i].flip = flip[i];
+        t[i].sign = sign[i];
+        t[i].cr = coef[2 * i];
+        t[i].ci = coef[2 * i + 1];
+    }
+    std::stable_sort(t.begin(), t.end(), [](const PauliTerm& a, const PauliTerm& b) { return a.flip < b.flip; });
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TCB_CUDA(cudaMemcpyAsync(workspace, t.data(), (size_t)nterms * sizeof(PauliTerm), cudaMemcpyHostToDevice, st));
+    TCB_CUDA(cudaStreamSynchronize(st));  // `t` is pageable host memory and goes out of scope
+    const uint64_t ctas = ((1ull << nbits) + 255) / 256;
+    if (ctas > 0x7fffffffull) return fail(TCB200_ERR_UNSUPPORTED, "state too large for one grid");
+    const dim3 grid((unsigned)ctas, (unsigned)batch);
+    if (dtype == TCB200_C64)
+        pauli_sum_kernel<float2><<<grid, 256, 0, st>>>(static_cast<const float2*>(src), static_cast<float2*>(dst), nbits, nterms,
+                                                      static_cast<const PauliTerm*>(workspace));
+    else
+        pauli_sum_kernel<double2><<<grid, 256, 0, st>>>(static_cast<const double2*>(src), static_cast<double2*>(dst), nbits, nterms,
+                                                       static_cast<const PauliTerm*>(workspace));
+    TCB_LAUNCH_CHECK("pauli_sum_kernel");
+    return 0;
+}
+
+int tcb200_transition_local_max_ops(void) { return TR_MAX_OPS; }
+size_t tcb200_transition_local_workspace_bytes(int nops) { return (size_t)(nops < 1 ? 1 : nops) * TR_CTAS * 2 * sizeof(double); }
+
+int tcb200_transition_local(const void* bra, const void* ket, int nbits, int dtype, int nops, const int* ops_k, const int* ops_bits,
+                            const double* ops_mats, double* out_dev, void* workspace, size_t ws_bytes, void* stream) {
+    if (!bra || !ket || !out_dev || !ops_k || !ops_bits || !ops_mats) return fail(TCB200_ERR_ARG, "NULL argument");
+    if (dtype != TCB200_C64 && dtype != TCB200_C128) return fail(TCB200_ERR_ARG, "bad dtype %d", dtype);
+    if (nbits < 1 || nbits > 40) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
+    if (nops < 1 || nops > TR_MAX_OPS) return fail(TCB200_ERR_ARG, "nops=%d out of range (max %d per call)", nops, TR_MAX_OPS);
+    if (!workspace || ws_bytes < tcb200_transition_local_workspace_bytes(nops))
+        return fail(TCB200_ERR_WORKSPACE, "transition_local needs %zu bytes of workspace", tcb200_transition_local_workspace_bytes(nops));
+    static thread_local TransParams* tp = nullptr;
+    if (!tp) tp = new TransParams();
+    TransParams& p = *tp;
+    p.nbits = nbits;
+    p.nops = nops;
+    const int* b = ops_bits;
+    const double* m = ops_mats;
+    for (int o = 0; o < nops; ++o) {
+        const int k = ops_k[o];
+        if (k < 1 || k > 2) return fail(TCB200_ERR_UNSUPPORTED, "local operator of %d bits (max 2)", k);
+        if (k > nbits) return fail(TCB200_ERR_ARG, "operator wider than the state");
+        for (int i = 0; i < k; ++i) {
+            if (b[i] < 0 || b[i] >= nbits) return fail(TCB200_ERR_ARG, "bit %d out of range", b[i]);
+            if (i > 0 && b[i] <= b[i - 1]) return fail(TCB200_ERR_ARG, "bits must be strictly ascending");
+        }
+        p.op[o].k = k;
+        p.op[o].b0 = b[0];
+        p.op[o].b1 = k == 2 ? b[1] : 0;
+        const int D = 1 << k;
+        for (int i = 0; i < D * D; ++i) p.op[o].m[i] = make_double2(m[2 * i], m[2 * i + 1]);
+        b += k;
+        m += 2 * D * D;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* partials = static_cast<double*>(workspace);
+    const dim3 grid(TR_CTAS, (unsigned)nops);
+    if (dtype == TCB200_C64)
+        transition_kernel<float2><<<grid, 256, 0, st>>>(static_cast<const float2*>(bra), static_cast<const float2*>(ket), p, partials);
+    else
+        transition_kernel<double2><<<grid, 256, 0, st>>>(static_cast<const double2*>(bra), static_cast<const double2*>(ket), p, partials);
+    TCB_LAUNCH_CHECK("transition_kernel");
+    coo_final_kernel<<<(unsigned)nops, COO_THREADS, 0, st>>>(partials, TR_CTAS, out_dev);
+    TCB_LAUNCH_CHECK("coo_final_kernel");
+    return 0;
+}
+
+}  // extern "C"

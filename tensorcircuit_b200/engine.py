@@ -111,6 +111,34 @@ def plan_single_flip_groups(flip_bits: Sequence[int], nbits: int, tile_bits: int
     return groups
 
 
+class DeviceCOO:
+    """A sparse operator resident on the device: int64 row / column amplitude indices (reference basis
+    order) and complex128 values.  Built once (``backend.coo_sparse_matrix_from_numpy``,
+    ``quantum.PauliStringSum2COO`` for a generic matrix) and reused over the iterations of a loop."""
+
+    def __init__(self, rows: Any, cols: Any, vals: Any, dim: int, device: Any = None):
+        require_cuda()
+        r = np.ascontiguousarray(np.asarray(rows, dtype=np.int64).reshape(-1))
+        c = np.ascontiguousarray(np.asarray(cols, dtype=np.int64).reshape(-1))
+        v = np.ascontiguousarray(np.asarray(vals, dtype=np.complex128).reshape(-1))
+        if not (r.size == c.size == v.size):
+            raise ValueError("rows, cols and values must have the same length")
+        if r.size and (min(r.min(), c.min()) < 0 or max(r.max(), c.max()) >= dim):
+            raise ValueError("sparse operator index outside [0, %d)" % dim)
+        dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.dim, self.nnz, self.shape = int(dim), int(r.size), (int(dim), int(dim))
+        self.rows = torch.from_numpy(r).to(dev)
+        self.cols = torch.from_numpy(c).to(dev)
+        self.vals = torch.from_numpy(v).to(dev)
+
+    @classmethod
+    def from_scipy(cls, m: Any, device: Any = None) -> "DeviceCOO":
+        m = m.tocoo()
+        if m.shape[0] != m.shape[1]:
+            raise ValueError("operator must be square")
+        return cls(m.row, m.col, m.data, m.shape[0], device)
+
+
 class DeviceState:
     use_single_flip = os.environ.get("TCB200_SINGLE_FLIP", "1") != "0"
 
@@ -459,6 +487,56 @@ class DeviceState:
             o = out.cpu().numpy()
             out_all[:, ids] = o[..., 0] + 1j * o[..., 1]
         return out_all
+
+    # -- sparse operators and the adjoint-sweep primitives (csrc/sparse.cu) -------------------------
+    def coo_expectation(self, op: "DeviceCOO") -> np.ndarray:
+        """<psi| H |psi> per batch element for a device-resident COO operator: complex [batch]."""
+        if op.dim != 1 << self.nbits:
+            raise ValueError("operator of dimension %d on a state of %d qubits" % (op.dim, self.nbits))
+        ws = self._workspace(lib.tcb200_coo_expectation_workspace_bytes(op.nnz, self.batch))
+        out = torch.empty((self.batch, 2), dtype=torch.float64, device=self.device)
+        check(lib.tcb200_coo_expectation(_ptr(self.buf), self.nbits, self.dt, op.nnz, _ptr(op.rows), _ptr(op.cols), _ptr(op.vals), _ptr(out),
+                                         self.batch, _ptr(ws), ws.numel(), _stream()))
+        STATS["expect_launches"] += 1
+        o = out.cpu().numpy()
+        return o[:, 0] + 1j * o[:, 1]
+
+    def copy_row_from(self, row: int, src: "DeviceState", src_row: int = 0) -> None:
+        """self[row] <- src[src_row] (device-to-device, same size and dtype)."""
+        assert src.nbits == self.nbits and src.dtype == self.dtype
+        nb = self.amp_bytes << self.nbits
+        check(lib.tcb200_copy_rows(_ptr(self.buf[row]), nb, _ptr(src.buf[src_row]), nb, nb, 1, _stream()))
+
+    def apply_pauli_sum_rows(self, src_row: int, dst_row: int, flips: Sequence[int], signs: Sequence[int], coef: Sequence[complex]) -> None:
+        """self[dst_row] <- sum_t coef_t P_t self[src_row]  (coef_t already holds (-i)^ny_t)."""
+        assert src_row != dst_row
+        nt = len(flips)
+        f = np.asarray([int(x) for x in flips], dtype=np.uint64)
+        g = np.asarray([int(x) for x in signs], dtype=np.uint64)
+        c = np.ascontiguousarray(np.asarray(coef, dtype=np.complex128))
+        ws = self._workspace(lib.tcb200_apply_pauli_sum_workspace_bytes(nt))
+        check(lib.tcb200_apply_pauli_sum(_ptr(self.buf[src_row]), _ptr(self.buf[dst_row]), self.nbits, self.dt, nt, _lib.u64ptr(f), _lib.u64ptr(g),
+                                         _lib.dptr(c.view(np.float64)), 1, _ptr(ws), ws.numel(), _stream()))
+        STATS["apply_launches"] += 1
+
+    def transition_local(self, bra_row: int, ket_row: int, ops: Sequence[Tuple[Sequence[int], np.ndarray]]) -> np.ndarray:
+        """<self[bra_row]| G_j |self[ket_row]> for local operators (bits ascending, matrix index bit i <->
+        bits[i]): complex [nops]; tcb200_transition_local_max_ops() operators per launch."""
+        res = np.zeros(len(ops), dtype=np.complex128)
+        per = lib.tcb200_transition_local_max_ops()
+        for c0 in range(0, len(ops), per):
+            chunk = ops[c0 : c0 + per]
+            ks = np.asarray([len(b) for b, _ in chunk], dtype=np.int32)
+            bits = np.asarray([x for b, _ in chunk for x in b], dtype=np.int32)
+            mats = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.complex128).reshape(-1) for _, m in chunk]))
+            ws = self._workspace(lib.tcb200_transition_local_workspace_bytes(len(chunk)))
+            out = torch.empty((len(chunk), 2), dtype=torch.float64, device=self.device)
+            check(lib.tcb200_transition_local(_ptr(self.buf[bra_row]), _ptr(self.buf[ket_row]), self.nbits, self.dt, len(chunk), _lib.iptr(ks),
+                                              _lib.iptr(bits), _lib.dptr(mats.view(np.float64)), _ptr(out), _ptr(ws), ws.numel(), _stream()))
+            STATS["expect_launches"] += 1
+            o = out.cpu().numpy()
+            res[c0 : c0 + len(chunk)] = o[:, 0] + 1j * o[:, 1]
+        return res
 
     # -- sampler ------------------------------------------------------------------------------
     def sample(self, uniforms: Any, cdf_offset: float = 0.0, cdf_total: float = -1.0, return_total: bool = False) -> Any:

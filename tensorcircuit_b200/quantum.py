@@ -7,6 +7,8 @@ from __future__ import annotations
 
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
+from functools import partial
+
 import numpy as np
 
 Tensor = Any
@@ -182,3 +184,121 @@ def correlation_from_counts(index: Sequence[int], results: Tensor) -> Tensor:
     for i in index:
         results = results * spin_by_basis(n, i)
     return np.sum(results)
+
+
+# ---- Pauli-sum Hamiltonians (quantum.py:1163-1482) ----------------------------------------------
+class PauliSum:
+    """A Hamiltonian  sum_t w_t P_t  kept as its Pauli strings.
+
+    The reference turns such a sum into a COO matrix with nterms * 2^n stored elements
+    (``PauliStringSum2COO``, quantum.py:1304-1376) and multiplies it with the state
+    (``sparse_expectation``).  Here the object returned by ``PauliStringSum2COO`` keeps the strings:
+    ``operator_expectation`` / ``sparse_expectation`` evaluate them with the multi-term Pauli kernels
+    (a few reads of the state, no matrix), and the matrix is only materialised on request
+    (``tocoo`` / ``todense``, host, scipy -- same element values as the reference's)."""
+
+    def __init__(self, ls: Sequence[Sequence[int]], weight: Optional[Sequence[float]] = None):
+        self.ls = np.asarray(ls, dtype=np.int64).reshape(len(ls), -1)
+        if self.ls.size and (self.ls.min() < 0 or self.ls.max() > 3):
+            raise ValueError("Pauli strings are sequences of 0 (I), 1 (X), 2 (Y), 3 (Z)")
+        self.weight = np.ones(len(self.ls)) if weight is None else np.asarray(weight).reshape(-1)
+        if len(self.weight) != len(self.ls):
+            raise ValueError("one weight per Pauli string")
+        self.nqubits = int(self.ls.shape[1])
+        self.shape = (1 << self.nqubits, 1 << self.nqubits)
+
+    def __len__(self) -> int:
+        return len(self.ls)
+
+    def tocoo(self) -> Any:
+        return PauliStringSum2COO(self.ls, self.weight, numpy=True)
+
+    def todense(self) -> Any:
+        return np.asarray(self.tocoo().todense())
+
+
+def ps2coo_core(idx_x: int, idx_y: int, idx_z: int, weight: Any, nqubits: int) -> Any:
+    """quantum.py:1461-1482: element (r, r ^ x ^ y) = (1 - 2 parity(r & (y | z))) (-i)^{ny} w."""
+    import scipy.sparse as sp
+
+    s = 1 << nqubits
+    idx1 = np.arange(s, dtype=np.int64)
+    idx2 = idx1 ^ np.int64(idx_x) ^ np.int64(idx_y)
+    tmp = idx1 & np.int64(idx_y | idx_z)
+    e = np.zeros(s, dtype=np.int64)
+    for i in range(nqubits):
+        e ^= (tmp >> i) & 1
+    ny = bin(int(idx_y)).count("1") % 4
+    values = (1 - 2 * e) * ((-1.0j) ** ny) * weight
+    return sp.coo_matrix((values.astype(dtypestr_()), (idx1, idx2)), shape=(s, s))
+
+
+def dtypestr_() -> str:
+    from . import cons
+
+    return cons.dtypestr
+
+
+def PauliString2COO(l: Sequence[int], weight: Optional[float] = None) -> Any:
+    """quantum.py:1415-1458 (host, scipy)."""
+    n = len(l)
+    ix = iy = iz = 0
+    for j, p in enumerate(l):
+        b = 1 << (n - j - 1)
+        if p == 1:
+            ix |= b
+        elif p == 2:
+            iy |= b
+        elif p == 3:
+            iz |= b
+    return ps2coo_core(ix, iy, iz, 1.0 if weight is None else weight, n)
+
+
+def PauliStringSum2COO(ls: Sequence[Sequence[int]], weight: Optional[Sequence[float]] = None, numpy: bool = False) -> Any:
+    """quantum.py:1304-1360.  ``numpy=True``: the scipy COO matrix, element for element the
+    reference's.  Otherwise the backend-side operator, which here is a :class:`PauliSum` -- the
+    strings themselves; ``operator_expectation`` / ``sparse_expectation`` / ``backend.is_sparse`` /
+    ``backend.to_dense`` / ``backend.sparse_dense_matmul`` accept it wherever the reference takes its
+    sparse tensor."""
+    if not numpy:
+        return PauliSum(ls, weight)
+    ls = np.asarray(ls, dtype=np.int64)
+    w = np.ones(len(ls)) if weight is None else np.asarray(weight)
+    acc = None
+    for i in range(len(ls)):
+        m = PauliString2COO(ls[i], w[i]).tocsr()
+        acc = m if acc is None else acc + m
+    return acc.tocoo()
+
+
+PauliStringSum2COO_numpy = partial(PauliStringSum2COO, numpy=True)
+PauliStringSum2COO_tf = PauliStringSum2COO
+
+
+def PauliStringSum2Dense(ls: Sequence[Sequence[int]], weight: Optional[Sequence[float]] = None, numpy: bool = False) -> Any:
+    """quantum.py:1257-1284."""
+    return np.asarray(PauliStringSum2COO(ls, weight, numpy=True).todense())
+
+
+def heisenberg_hamiltonian(g: Any, hzz: float = 1.0, hxx: float = 1.0, hyy: float = 1.0, hz: float = 0.0, hx: float = 0.0,
+                           hy: float = 0.0, sparse: bool = True, numpy: bool = False) -> Any:
+    """quantum.py:1163-1254: same string order as the reference (per edge zz, xx, yy; per node z, x, y)."""
+    n = len(g.nodes)
+    ls, weight = [], []
+    for e in g.edges:
+        for p, h in ((3, hzz), (1, hxx), (2, hyy)):
+            if h != 0:
+                r = [0] * n
+                r[e[0]] = r[e[1]] = p
+                ls.append(r)
+                weight.append(h)
+    for node in g.nodes:
+        for p, h in ((3, hz), (1, hx), (2, hy)):
+            if h != 0:
+                r = [0] * n
+                r[node] = p
+                ls.append(r)
+                weight.append(h)
+    if sparse:
+        return PauliStringSum2COO(ls, weight, numpy=numpy)
+    return PauliStringSum2Dense(ls, weight)

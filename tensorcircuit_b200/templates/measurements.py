@@ -1,5 +1,6 @@
 """Measurement shortcuts (tensorcircuit/templates/measurements.py:18-208, 290-335) mapped onto the
-multi-term Pauli expectation kernel."""
+multi-term Pauli expectation kernels and, for generic sparse / dense operators, onto the COO
+expectation kernel (csrc/sparse.cu)."""
 
 from __future__ import annotations
 
@@ -105,3 +106,60 @@ def heisenberg_measurements(c: Circuit, g: Any, hzz: float = 1.0, hxx: float = 1
                 pss.append(ps)
                 ws.append(h)
     return pauli_sum_expectation(c, pss, ws)
+
+
+def _operator_on_device(hamiltonian: Any) -> Any:
+    """scipy sparse / dense ndarray -> engine.DeviceCOO, cached on scipy objects (a VQE loop passes the
+    same Hamiltonian every iteration: it is uploaded once)."""
+    from ..engine import DeviceCOO
+
+    if isinstance(hamiltonian, DeviceCOO):
+        return hamiltonian
+    cached = getattr(hamiltonian, "_tcb200_device", None)
+    if cached is not None:
+        return cached
+    if hasattr(hamiltonian, "tocoo"):
+        op = DeviceCOO.from_scipy(hamiltonian)
+        try:
+            hamiltonian._tcb200_device = op
+        except AttributeError:
+            pass
+        return op
+    a = np.asarray(hamiltonian)
+    if a.ndim != 2 or a.shape[0] != a.shape[1]:
+        raise ValueError("operator_expectation needs a square matrix")
+    r, c = np.nonzero(a)
+    return DeviceCOO(r, c, a[r, c], a.shape[0])
+
+
+def sparse_expectation(c: Circuit, hamiltonian: Tensor) -> Tensor:
+    """measurements.py:173-188.  A :class:`quantum.PauliSum` (what ``PauliStringSum2COO`` returns) goes
+    through the Pauli kernels string by string -- no matrix; a scipy sparse matrix / ``DeviceCOO`` /
+    dense array goes through the COO expectation kernel with the operator resident on the device."""
+    from ..quantum import PauliSum
+
+    if isinstance(hamiltonian, PauliSum):
+        if hamiltonian.nqubits != c._nqubits:
+            raise ValueError("Hamiltonian on %d qubits, circuit on %d" % (hamiltonian.nqubits, c._nqubits))
+        return pauli_sum_expectation(c, hamiltonian.ls.tolist(), hamiltonian.weight)
+    op = _operator_on_device(hamiltonian)
+    st = c._ensure_state()
+    r = np.real(st.coo_expectation(op))
+    rd = np.float32 if c._dtype == "complex64" else np.float64
+    if c._batch is None:
+        return rd(r[0])
+    return BatchArray(r.astype(rd))
+
+
+def mpo_expectation(c: Circuit, mpo: Any) -> Tensor:
+    """measurements.py:191-208 contracts a tensornetwork ``QuOperator`` with the circuit's node graph;
+    both live in the tensor-network layer that this engine replaces (no node graph exists here)."""
+    raise NotImplementedError("mpo_expectation needs the tensornetwork QuOperator layer, which is outside the statevector hot path; "
+                              "pass the Hamiltonian as Pauli strings (quantum.PauliStringSum2COO) or as a sparse matrix")
+
+
+def operator_expectation(c: Circuit, hamiltonian: Any) -> Tensor:
+    """measurements.py:156-170: dense matrix, sparse matrix or Pauli sum (MPO: see mpo_expectation)."""
+    if type(hamiltonian).__name__ == "QuOperator":
+        return mpo_expectation(c, hamiltonian)
+    return sparse_expectation(c, hamiltonian)

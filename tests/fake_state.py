@@ -193,3 +193,56 @@ class FakeState:
             own = (t > 0) & (t <= cdf[-1])
             r = np.where(own, np.minimum(np.searchsorted(cdf, t, side="left"), p.size - 1), -1).astype(np.int64)
         return (r, float(p.sum())) if return_total else r
+
+    # ---- sparse operators / adjoint-sweep primitives: numpy restatements of csrc/sparse.cu ----
+    def coo_expectation(self, op):
+        out = np.zeros(self.batch, dtype=np.complex128)
+        for b in range(self.batch):
+            psi = self.np[b].astype(np.complex128)
+            out[b] = np.sum(np.conj(psi[op.rows]) * op.vals * psi[op.cols])
+        return out
+
+    def copy_row_from(self, row, src, src_row=0):
+        self.np[row] = src.np[src_row]
+
+    def apply_pauli_sum_rows(self, src_row, dst_row, flips, signs, coef):
+        r = np.arange(1 << self.nbits, dtype=np.uint64)
+        src = self.np[src_row].astype(np.complex128)
+        acc = np.zeros_like(src)
+        for f, g, c in zip(flips, signs, coef):
+            par = np.zeros(r.size, dtype=np.int64)
+            m = r & np.uint64(int(g))
+            for i in range(self.nbits):
+                par ^= ((m >> np.uint64(i)) & np.uint64(1)).astype(np.int64)
+            acc += c * (1 - 2 * par) * src[r ^ np.uint64(int(f))]
+        self.np[dst_row] = acc.astype(self.np.dtype)
+
+    def transition_local(self, bra_row, ket_row, ops):
+        n = self.nbits
+        bra = self.np[bra_row].astype(np.complex128)
+        ket = self.np[ket_row].astype(np.complex128)
+        out = np.zeros(len(ops), dtype=np.complex128)
+        for j, (bits, m) in enumerate(ops):
+            k = len(bits)
+            axes = [n - 1 - b for b in bits][::-1]  # matrix index big-endian = (bits[k-1], ..., bits[0])
+            t = np.tensordot(np.asarray(m, dtype=np.complex128).reshape([2] * (2 * k)), ket.reshape([2] * n), axes=(list(range(k, 2 * k)), axes))
+            t = np.moveaxis(t, list(range(k)), axes)
+            out[j] = np.vdot(bra, t.reshape(-1))
+        return out
+
+
+class FakeCOO:
+    """host stand-in for engine.DeviceCOO (same checks, numpy arrays)"""
+
+    def __init__(self, rows, cols, vals, dim, device=None):
+        self.rows = np.asarray(rows, dtype=np.int64).reshape(-1)
+        self.cols = np.asarray(cols, dtype=np.int64).reshape(-1)
+        self.vals = np.asarray(vals, dtype=np.complex128).reshape(-1)
+        if self.rows.size and (min(self.rows.min(), self.cols.min()) < 0 or max(self.rows.max(), self.cols.max()) >= dim):
+            raise ValueError("sparse operator index outside [0, %d)" % dim)
+        self.dim, self.nnz, self.shape = int(dim), int(self.rows.size), (int(dim), int(dim))
+
+    @classmethod
+    def from_scipy(cls, m, device=None):
+        m = m.tocoo()
+        return cls(m.row, m.col, m.data, m.shape[0])

@@ -16,9 +16,10 @@ from oracle.tc_oracle import OracleCircuit
 @pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
 def eng(request, monkeypatch):
     if request.param == "emu":
-        from .fake_state import FakeState
+        from .fake_state import FakeCOO, FakeState
 
         monkeypatch.setattr(tc.engine, "DeviceState", FakeState)
+        monkeypatch.setattr(tc.engine, "DeviceCOO", FakeCOO)
     tc.set_dtype("complex64")
     yield request.param
     tc.set_dtype("complex64")
