@@ -15,10 +15,13 @@ import tensorcircuit_b200 as tc  # noqa: E402
 from tensorcircuit_b200 import engine, recipes  # noqa: E402
 
 
+ENV = {0: {}, 1: {"TCB200_PIPE": "1"}, 2: {"TCB200_PIPE": "2"}, 3: {"TCB200_GATE_TMA": "1"}}  # 3: TMA-staged tiles
+
+
 def run(n, depth, pipe, knobs=None, reps=1, seed=3):
-    os.environ["TCB200_PIPE"] = str(int(pipe))
-    for k in ("TCB200_PIPE_MIN_TILES", "TCB200_PIPE_GRID"):
+    for k in ("TCB200_PIPE", "TCB200_GATE_TMA", "TCB200_PIPE_MIN_TILES", "TCB200_PIPE_GRID"):
         os.environ.pop(k, None)
+    os.environ.update(ENV[int(pipe)])
     for k, v in (knobs or {}).items():
         os.environ[k] = str(v)
     c = recipes.build(tc.Circuit(n), recipes.random_circuit(n, depth, seed))
@@ -38,7 +41,7 @@ def run(n, depth, pipe, knobs=None, reps=1, seed=3):
     return st, best
 
 
-MODES = (1, 2)
+MODES = tuple(int(x) for x in os.environ.get("PIPE_CHECK_MODES", "1,2,3").split(","))
 
 
 def main():
@@ -69,7 +72,8 @@ def main():
         _, ms = run(n_time, depth, pipe, reps=3)
         out["timing"].setdefault("mode%d" % pipe, []).append(ms)
         print("n=%d depth=%d pipe=%s: %.2f ms" % (n_time, depth, pipe, ms), flush=True)
-    os.environ.pop("TCB200_PIPE", None)
+    for k in ("TCB200_PIPE", "TCB200_GATE_TMA"):
+        os.environ.pop(k, None)
     print(json.dumps(out))
 
 

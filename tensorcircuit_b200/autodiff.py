@@ -256,6 +256,7 @@ def _adjoint_contrib(q: _Query, weights: np.ndarray, lst: List[Tuple[int, int, n
     st2.apply_pauli_sum_rows(0, 1, [q.fl[t] for t in keep], [q.sg[t] for t in keep], [coef[t] for t in keep])
     out = np.zeros(len(lst))
     pending_undo: List[Tuple[Tuple[int, ...], np.ndarray]] = []
+    on_qubit: Dict[int, List[int]] = {}  # qubit -> indices into pending_undo (only those can fail to commute with a tap)
     pending_taps: List[Tuple[int, List[int], np.ndarray]] = []
     fuser = _circuit.Circuit(n)
 
@@ -276,17 +277,21 @@ def _adjoint_contrib(q: _Query, weights: np.ndarray, lst: List[Tuple[int, int, n
                 st2.apply_blocks(blocks)
             ADJOINT_STATS["flushes"] += 1
             pending_undo.clear()
+            on_qubit.clear()
 
     jmin = min(taps)
     for j in range(len(q.ops) - 1, jmin - 1, -1):
         qubits, M = q.ops[j]
         for idx in taps.get(j, []):
             G = lst[idx][2] @ Mdag[j]
-            if any(not _commute(G, qubits, m, qs) for qs, m in pending_undo):
+            near = sorted({i for qb in qubits for i in on_qubit.get(qb, ())})
+            if any(not _commute(G, qubits, pending_undo[i][1], pending_undo[i][0]) for i in near):
                 flush()  # taps registered so far see the current states; then the states move on
             bits, Gs = _sorted_local(G, qubits, n)
             pending_taps.append((idx, bits, Gs))
         if j > jmin:
+            for qb in qubits:
+                on_qubit.setdefault(qb, []).append(len(pending_undo))
             pending_undo.append((tuple(qubits), Mdag[j]))
     pending_undo.clear()  # nobody needs the states below the lowest tap
     flush()

@@ -400,7 +400,8 @@ class B200Backend:
         if 2**n != pv.numel():
             raise ValueError("probability_sample on the B200 backend needs a power-of-two length")
         st = DeviceState(n, "complex128", 1)
-        st.load(torch.sqrt(pv.to(st.device, dtype=torch.float64)))
+        st.load(pv)                 # (p, 0) as a state-shaped buffer ...
+        st.sqrt_real_inplace()      # ... -> (sqrt(p), 0) by tcb200_probability_state: no torch op on 2^n data
         return st.sample(np.asarray(status, dtype=np.float64))
 
     # -- program transforms ------------------------------------------------------------------

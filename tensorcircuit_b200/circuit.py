@@ -596,7 +596,13 @@ class Circuit:
         if format_ is not None:
             format = format_
         if self._batch is not None:
-            raise NotImplementedError("sample() inside vmap")
+            # vmap over ``status`` and / or circuit parameters (docs/source/advance.rst:95-170): one sampler
+            # run per batch row, on a view of that row of the batched state
+            if format not in ("sample_int", "sample_bin"):
+                raise NotImplementedError("sample() inside vmap returns arrays: use format='sample_int' or 'sample_bin'")
+            outs = [rc.sample(batch=batch, allow_state=allow_state, readout_error=readout_error, format=format, random_generator=random_generator,
+                              status=sb) for rc, sb in self._row_circuits(status)]
+            return BatchArray(np.stack([np.asarray(o) for o in outs]))
         nbatch = 1 if batch is None else int(batch)
         if status is None:
             u = cons.backend.stateful_randu(random_generator, shape=[nbatch]) if random_generator is not None else cons.backend.implicit_randu(shape=[nbatch])
@@ -623,6 +629,24 @@ class Circuit:
             r = list(zip(confg, prob))
             return r[0] if batch is None else r
         return sample2all(sample=ch, n=self._nqubits, format=format, jittable=True)
+
+    def _row_circuits(self, status: Any = None) -> List[Tuple["Circuit", Any]]:
+        """Unbatched views of a vmapped circuit: (circuit whose state IS row b of the batched state, row b of
+        ``status`` when that is batched too)."""
+        st = self._ensure_state()
+        if not hasattr(st, "row_state"):
+            raise NotImplementedError("per-row queries on this kind of state")
+        rows = []
+        for b in range(st.batch):
+            rc = type(self)(self._nqubits)
+            rc._ntot = self._ntot
+            rc._state = st.row_state(b)
+            rc._applied = 0
+            sb = status
+            if is_batched(status):
+                sb = np.asarray(status.a)[b]
+            rows.append((rc, sb))
+        return rows
 
     def _readout_state(self, readout_error: Sequence[Any]) -> Any:
         """A state-shaped device buffer whose |amplitude|^2 is the distribution after readout error
@@ -735,7 +759,8 @@ class Circuit:
         and the running probability is updated as ``p * (pu * (-1)**outcome + outcome)``.
         Returns (outcomes as a real vector, probability of the record or -1.0)."""
         if self._batch is not None:
-            raise NotImplementedError("measure() inside vmap")
+            outs = [rc.measure(*index, with_prob=with_prob, status=sb) for rc, sb in self._row_circuits(status)]
+            return BatchArray(np.stack([o[0] for o in outs])), BatchArray(np.asarray([o[1] for o in outs]))
         st = self._ensure_state()
         if self._ntot != self._nqubits:
             raise NotImplementedError("measure with unitary-form inputs")
@@ -933,13 +958,33 @@ Circuit._meta_apply_channels()
 
 
 def expectation(*ops: Tuple[Any, List[int]], ket: Tensor, bra: Optional[Tensor] = None, conj: bool = True, normalization: bool = False) -> Tensor:
-    """tensorcircuit/circuit.py:997-1129 for the ``bra is None`` case: <ket| ops |ket>."""
-    if bra is not None:
-        raise NotImplementedError("expectation with a separate bra")
-    size = int(np.prod(np.shape(ket)))
+    """tensorcircuit/circuit.py:997-1129: <bra| ops |ket>.  With a separate ``bra`` the operators are
+    applied to a copy of ``ket`` as (generally non-unitary) gates and the inner product with ``bra`` is
+    one launch of the transition-element kernel; ``conj=False`` gives the bilinear form sum_r bra_r (ops ket)_r."""
+    size = int(np.prod(np.shape(ket))) if not hasattr(ket, "numel") else int(ket.numel())
     n = int(round(np.log2(size)))
     c = Circuit(n, inputs=ket)
-    r = c.expectation(*ops)
+    if bra is None and conj:
+        r = c.expectation(*ops)
+        if normalization:
+            r = r / c._ensure_state().norm2()[0]
+        return r
+    nk = float(c._ensure_state().norm2()[0]) if normalization else 1.0
+    occupied: set = set()
+    for op, index in ops:
+        index = [index] if isinstance(index, int) else list(index)
+        for e in index:
+            if e in occupied:
+                raise ValueError("Cannot measure two operators in one index")
+            occupied.add(e)
+        c.any(*index, unitary=op)
+    if bra is None:
+        bra = ket
+    if not conj:
+        bra = bra.t.conj().resolve_conj() if isinstance(bra, DeviceArray) else np.conj(np.asarray(bra))
+    cb = Circuit(n, inputs=bra)
+    sb = cb._ensure_state()
+    v = c._ensure_state().inner(sb)
     if normalization:
-        r = r / c._ensure_state().norm2()[0]
-    return r
+        v = v / np.sqrt(nk * float(sb.norm2()[0]))
+    return _np_scalar(v, c._dtype)

@@ -898,6 +898,8 @@ int make_group_map(const TileGeom& g, int apu, int k, const int* bits, GroupMap*
 // caller falls back to cpass_kernel; < 0: error.
 int launch_tpass(int dtype, void* state, int nbits, int nops, const int* ops_k, const int* ops_bits,
                  const double* mats, int n_hi, const int* tile_hi, int64_t batch, cudaStream_t st);
+// tensor map (CUtensorMap, 128 bytes, 64-byte aligned) + box plan for tiles of geometry g; 0: ready, > 0: not eligible
+int tma_encode_state_map(void* state, int nbits, int is_c64, const TileGeom& g, int64_t batch, TmaPlan* tp, void* map_out);
 // complex64 register-tile pass (<= 4-bit tiles of 1-/2-bit gates) through the same pipeline
 int launch_trpass(void* state, int nbits, int nrt, const int* rt_k, const int* rt_bits, const int* rt_nsub,
                   const int* sub_k, const int* sub_bits, const double* sub_mats, int n_hi, const int* tile_hi,

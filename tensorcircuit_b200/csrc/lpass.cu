@@ -5,6 +5,7 @@
 // tensordot of tensorcircuit/cons.py:605-623 and, for the structured gates of
 // tensorcircuit/gates.py:46-127, 826-865 (cnot / swap / x / cz / rzz / rz ...), the dense
 // multiplication by a table multiply (diagonal) or by nothing at all (affine permutations).
+#include <cuda.h>  // CUtensorMap (kernel parameter of the TMA-staged variant)
 #include <stdlib.h>
 #include <string.h>
 
@@ -153,6 +154,7 @@ struct LPassParams {
     int fast;    // production shape: 256 threads, 16 staging units per thread (LStage valid)
     const ME<Real>* bmats;  // vmap: DEVICE [batch][bstride] matrix elements (nullptr: shared matrices in m[])
     int bstride;
+    TmaPlan tp;             // TMA-staged kernel: boxes of one tile
     int vtl;                // pipelined kernel: log2(tiles per state vector)
     uint64_t ntiles;        // pipelined kernel: tiles over all vectors of the batch
     LOut out;
@@ -199,10 +201,12 @@ struct Scheduler {
         else put_elem<Real>(q->m[idx], z);
     }
 
+    int swz_mode = SWZ_SW;  // SWZ_HW128: the layout a TMA tensor-map load with SWIZZLE_128B leaves behind
+
     void init_layout() {
         for (int t = 0; t < T; ++t) {
             const uint32_t e = 1u << t;
-            col[t] = (C64 ? swz_amp<2>(e) : swz_amp<1>(e)) * (uint32_t)AMP;
+            col[t] = (C64 ? swz_amp<2>(e, swz_mode) : swz_amp<1>(e, swz_mode)) * (uint32_t)AMP;
         }
         d = 0;
     }
@@ -459,7 +463,7 @@ struct Scheduler {
 template <typename Real>
 int fill_lpass(LPassParams<Real>& q, LPassInfo& info, void* state, int nbits, int nops, const int* ops_k, const int* ops_bits,
                const double* mats, int n_hi, const int* tile_hi, const int* ops_batched = nullptr, int batch = 1,
-               ME<Real>* blob = nullptr) {
+               ME<Real>* blob = nullptr, int swz_mode = SWZ_SW) {
     using C = typename CT<Real>::type;
     q.state = static_cast<C*>(state);
     q.bmats = nullptr;
@@ -476,6 +480,11 @@ int fill_lpass(LPassParams<Real>& q, LPassInfo& info, void* state, int nbits, in
     s.T = q.g.T;
     s.q = &q;
     memset(&s.info, 0, sizeof(s.info));
+    s.swz_mode = swz_mode;
+    {
+        const char* e = getenv("TCB200_LAYOUT_HW128");  // planning statistics (dry runs only)
+        if (e && e[0] == '1' && !state) s.swz_mode = SWZ_HW128;
+    }
     s.init_layout();
     s.batch = batch;
     s.blob = blob;
@@ -710,6 +719,60 @@ __global__ void __launch_bounds__(PL_THREADS, 1) lpass_pipe_kernel(const __grid_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA-staged production shape: the tile arrives as cp.async.bulk.tensor boxes issued by ONE thread
+// ------------------------------------------------------------------------------------------------
+// Same rounds and write-back as lpass_fast_kernel; the 16 LDGSTS + address arithmetic per thread of
+// the stage-in (10 % of the issued instructions of a pass, and its share of the MIO queue) are
+// replaced by <= 64 bulk tensor copies (one per thread of the first two warps) that complete on an mbarrier.  The tile then
+// sits in the hardware SWIZZLE_128B layout, which is one more affine index map for the scheduler
+// (Scheduler::swz_mode = SWZ_HW128).
+__device__ __forceinline__ void pl_mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(pl_smem(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pl_tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n"
+        ::"r"(pl_smem(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(pl_smem(bar)), "r"(0), "r"(c1), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256, 3) lpass_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ LPassParams<Real> p) {
+    using C = typename CT<Real>::type;
+    constexpr int NIT = sizeof(C) == 8 ? 2 : 1;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full;
+    // SWIZZLE_128B atoms are 1024 bytes: align the tile by hand (the launch reserves the slack)
+    unsigned char* tile = smem_raw + ((1024u - (pl_smem(smem_raw) & 1023u)) & 1023u);
+    const uint32_t tid = threadIdx.x;
+    const uint64_t base = ((uint64_t)blockIdx.y << p.g.n) + tile_base(p.g, blockIdx.x);
+    if (tid == 0) {
+        pl_mbar_init(&full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        pl_mbar_expect_tx(&full, PL_TILE_BYTES);
+    }
+    __syncthreads();  // the barrier is armed before any copy can complete on it and before anyone polls it
+    // one box per thread: a single issuing thread needs ~4 us for the 64 boxes of a 9-gathered-bit tile
+    if (tid < (1u << p.tp.nextra)) {
+        const uint32_t box_bytes = (uint32_t)sizeof(C) << p.tp.box_amps_log2;
+        pl_tma_load_5d(tile + tid * box_bytes, &tmap, &full, (int)((base + tma_box_offset(p.tp, tid)) >> p.tp.line_bits));
+    }
+    pl_mbar_wait(&full, 0);
+    for (int r = 0; r < p.nrounds; ++r) {
+        lround_thread_fast<C, Real, NIT>(tile, p.r[r], p.m, tid);
+        __syncthreads();
+    }
+    lstage_out_fast<C>(p.stage, p.out, p.state + base, tile, tid);
+}
+
+// TCB200_GATE_TMA=1: stage the tiles of the production shape by TMA (complex64, shared matrices)
+static bool gate_tma_enabled() {
+    const char* e = getenv("TCB200_GATE_TMA");
+    return e && e[0] == '1';
+}
+
 // Variant B of the pipeline: two compute groups of 512 threads (one 16-amplitude group per thread and
 // round), no producer warps -- the group that has written a tile back refills the buffer itself (for
 // the tile the OTHER group will work on three tiles later).  32 warps at 64 registers.
@@ -810,6 +873,16 @@ __global__ void __launch_bounds__(2 * PB_GROUP, 1) lpass_pipe2_kernel(const __gr
     cp_async_wait_all();
 }
 
+static void launch_tma(const CUtensorMap& tmap, const LPassParams<float>& q, dim3 grid, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(lpass_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PL_TILE_BYTES + 1024));
+        attr = true;
+    }
+    lpass_tma_kernel<float><<<grid, 256, PL_TILE_BYTES + 1024, st>>>(tmap, q);
+}
+static void launch_tma(const CUtensorMap&, const LPassParams<double>&, dim3, cudaStream_t) {}
+
 static void launch_pipe(const LPassParams<float>& q, unsigned grid, cudaStream_t st) {
     const char* e = getenv("TCB200_PIPE");
     if (e && e[0] == '2') lpass_pipe2_kernel<float><<<grid, 2 * PB_GROUP, PL_STAGES * PL_TILE_BYTES, st>>>(q);
@@ -892,8 +965,16 @@ static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, cons
         dry.resize((size_t)batch * LP_MAT_ELEMS);
         blob = dry.data();
     }
-    int rc = fill_lpass<Real>(q, info, state, nbits, nops, ops_k, ops_bits, mats, n_hi, tile_hi, ops_batched, (int)batch, blob);
+    alignas(64) CUtensorMap tmap;
+    bool use_tma = state && !batched && sizeof(Real) == 4 && gate_tma_enabled();
+    int rc = fill_lpass<Real>(q, info, state, nbits, nops, ops_k, ops_bits, mats, n_hi, tile_hi, ops_batched, (int)batch, blob,
+                              use_tma ? SWZ_HW128 : SWZ_SW);
     if (rc) return rc;
+    if (use_tma && (!q.fast || tma_encode_state_map(state, nbits, 1, q.g, batch, &q.tp, &tmap) != 0)) {
+        use_tma = false;  // not eligible (small state, alignment, coordinate range): plan again for the LDGSTS layout
+        rc = fill_lpass<Real>(q, info, state, nbits, nops, ops_k, ops_bits, mats, n_hi, tile_hi, ops_batched, (int)batch, blob);
+        if (rc) return rc;
+    }
     if (info_out) *info_out = info;
     if (!state) return 0;  // dry run (tcb200_gate_pass_info)
     const uint64_t ntiles = 1ull << (nbits - q.g.T);
@@ -926,6 +1007,11 @@ static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, cons
     } else {
         const uint64_t total = ntiles * (uint64_t)batch;
         const int sms = lp_sm_count();
+        if (use_tma) {
+            launch_tma(tmap, q, grid, st);
+            TCB_LAUNCH_CHECK("lpass_tma_kernel");
+            return 0;
+        }
         // the pipeline pays off once every SM walks a few tiles
         if (q.fast && sizeof(Real) == 4 && sms > 0 && pipe_enabled() && total >= (uint64_t)pipe_knob("TCB200_PIPE_MIN_TILES", 4l * sms)) {
             static bool pattr = false;

@@ -335,6 +335,33 @@ static int sm_count() {
     return sms;
 }
 
+// Tensor map + box plan for tiles of geometry `g` over `batch` state vectors (shared with the gate
+// pass, lpass.cu).  > 0: not eligible (alignment, coordinate range, no driver entry point), 0: ready.
+int tma_encode_state_map(void* state, int nbits, int is_c64, const TileGeom& g, int64_t batch, TmaPlan* tp, void* map_out) {
+    const int apu = is_c64 ? 2 : 1;
+    const size_t amp = is_c64 ? 8 : 16;
+    if (batch < 1 || (reinterpret_cast<uintptr_t>(state) & 127u)) return 1;
+    if (make_tma_plan(g, apu, tp)) return 1;
+    const uint64_t total_lines = ((uint64_t)batch << nbits) >> tp->line_bits;
+    if (total_lines > 0x7fffffffull) return 1;  // TMA coordinates are int32
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return 1;
+    const cuuint32_t line_scalars = is_c64 ? 32 : 16;
+    cuuint64_t gdim[5] = {line_scalars, total_lines, 1, 1, 1};
+    cuuint64_t gstr[4] = {128, 128, 128, 128};
+    cuuint32_t box[5] = {line_scalars, (cuuint32_t)1 << (tp->lrow2 - tp->line_bits), 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < tp->nbox_bits; ++i) {
+        gdim[2 + i] = 2;
+        box[2 + i] = 2;
+        gstr[1 + i] = (cuuint64_t)amp << tp->box_bit[i];
+    }
+    const CUresult cr = enc(static_cast<CUtensorMap*>(map_out), is_c64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5,
+                            state, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return cr == CUDA_SUCCESS ? 0 : 1;
+}
+
 // Eligibility, tile geometry, box plan and tensor map shared by both kernels.
 // >0: not eligible (caller uses the LDGSTS-staged kernels), 0: ready, <0: error
 template <typename Real>

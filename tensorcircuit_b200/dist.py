@@ -559,4 +559,7 @@ class DistEngineState:
         return torch.from_numpy(full.astype(self.dtype))[None, :]
 
     def probability(self) -> torch.Tensor:
-        return (self.buf.abs() ** 2).to(torch.float32 if self.dtype == "complex64" else torch.float64)
+        # the gathered state is a HOST array (n <= 28, debugging / small-state convenience only)
+        full = self.ds.gather_state()
+        p = (full.real.astype(np.float64) ** 2 + full.imag.astype(np.float64) ** 2)
+        return torch.from_numpy(p.astype(np.float32 if self.dtype == "complex64" else np.float64))[None, :]

@@ -501,6 +501,24 @@ class DeviceState:
         o = out.cpu().numpy()
         return o[:, 0] + 1j * o[:, 1]
 
+    def row_state(self, b: int) -> "DeviceState":
+        """row ``b`` of a batched state as an unbatched state on the same memory (no copy)"""
+        return type(self)(self.nbits, self.dtype, 1, self.device, buffer=self.buf[b])
+
+    def inner(self, bra: "DeviceState", row: int = 0, bra_row: int = 0) -> complex:
+        """<bra|self> through the transition-element kernel with the identity on bit 0"""
+        assert bra.nbits == self.nbits and bra.dtype == self.dtype
+        ks = np.asarray([1], dtype=np.int32)
+        bits = np.asarray([0], dtype=np.int32)
+        mats = np.ascontiguousarray(np.eye(2, dtype=np.complex128).reshape(-1))
+        ws = self._workspace(lib.tcb200_transition_local_workspace_bytes(1))
+        out = torch.empty((1, 2), dtype=torch.float64, device=self.device)
+        check(lib.tcb200_transition_local(_ptr(bra.buf[bra_row]), _ptr(self.buf[row]), self.nbits, self.dt, 1, _lib.iptr(ks), _lib.iptr(bits),
+                                          _lib.dptr(mats.view(np.float64)), _ptr(out), _ptr(ws), ws.numel(), _stream()))
+        STATS["expect_launches"] += 1
+        o = out.cpu().numpy()
+        return complex(o[0, 0], o[0, 1])
+
     def copy_row_from(self, row: int, src: "DeviceState", src_row: int = 0) -> None:
         """self[row] <- src[src_row] (device-to-device, same size and dtype)."""
         assert src.nbits == self.nbits and src.dtype == self.dtype

@@ -31,7 +31,7 @@ class FakeState:
             FakeState._lib.emu_last_error.restype = ctypes.c_char_p
         self.nbits, self.dtype, self.batch = int(nbits), dtype, int(batch)
         self.dt = 0 if dtype == "complex64" else 1
-        self.np = np.zeros((self.batch, 1 << self.nbits), dtype=dtype)
+        self.np = np.zeros((self.batch, 1 << self.nbits), dtype=dtype) if buffer is None else buffer.reshape(self.batch, -1)
         self.buf = torch.from_numpy(self.np)  # shares memory
         self.device = torch.device("cpu")
 
@@ -201,6 +201,12 @@ class FakeState:
             psi = self.np[b].astype(np.complex128)
             out[b] = np.sum(np.conj(psi[op.rows]) * op.vals * psi[op.cols])
         return out
+
+    def row_state(self, b):
+        return type(self)(self.nbits, self.dtype, 1, buffer=self.np[b])
+
+    def inner(self, bra, row=0, bra_row=0):
+        return complex(np.vdot(bra.np[bra_row].astype(np.complex128), self.np[row].astype(np.complex128)))
 
     def copy_row_from(self, row, src, src_row=0):
         self.np[row] = src.np[src_row]

@@ -186,10 +186,11 @@ def test_gate_pass_matches_dense_pass_at_n26():
     assert abs(float(s1.norm2()[0]) - 1.0) < 1e-5
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["1", "2", "tma"])
 def test_pipelined_gate_pass_is_bit_identical(mode, monkeypatch):
-    """the opt-in persistent pipelines (lpass_pipe_kernel / lpass_pipe2_kernel: three tile buffers per
-    SM, mbarrier hand-over) run the same rounds as lpass_fast_kernel: identical bits, vs the oracle too"""
+    """the opt-in staging variants -- persistent pipelines (lpass_pipe_kernel / lpass_pipe2_kernel: three tile
+    buffers per SM, mbarrier hand-over) and TMA-staged tiles (lpass_tma_kernel: SWIZZLE_128B layout as the
+    start of the index map) -- run the same arithmetic as lpass_fast_kernel: identical bits, vs the oracle too"""
     n, depth = 20, 6
     rc = recipes.random_circuit(n, depth, 7)
     ops = [GateOp(q, np.asarray(orc.gate_matrix(name, **p)), name) for name, q, p in rc]
@@ -202,9 +203,13 @@ def test_pipelined_gate_pass_is_bit_identical(mode, monkeypatch):
         return st.buf.clone()
 
     monkeypatch.delenv("TCB200_PIPE", raising=False)
+    monkeypatch.delenv("TCB200_GATE_TMA", raising=False)
     base = run()
     for grid in ("3", "77", "1000"):  # many tiles per CTA, uneven split, more CTAs than tiles
-        monkeypatch.setenv("TCB200_PIPE", mode)
+        if mode == "tma":
+            monkeypatch.setenv("TCB200_GATE_TMA", "1")
+        else:
+            monkeypatch.setenv("TCB200_PIPE", mode)
         monkeypatch.setenv("TCB200_PIPE_MIN_TILES", "1")
         monkeypatch.setenv("TCB200_PIPE_GRID", grid)
         got = run()
