@@ -34,6 +34,8 @@ struct GOp {
     std::vector<cd> m;  // per held matrix -- dense: D*D row-major; diag: D
     int linv[4];        // lin: L^{-1} e_i as k-bit masks (the inverse map is y -> L^{-1} y ^ cinv)
     int cinv;
+    int half = 0;       // dense 1-bit gate whose elements are each real or imaginary: 1 = real diagonal +
+                        // imaginary off-diagonal (rx-like), 2 = real matrix (h, ry): LOP_RA / LOP_RB
 };
 
 // split one input gate into classified ops (appended to `out`); < 0 on error.  `mat` holds bm
@@ -122,6 +124,16 @@ int classify(int k, const int* lb, const double* mat, int bm, std::vector<GOp>& 
     for (int b = 0; b < bm; ++b)
         for (int i = 0; i < D; ++i)
             for (int j = 0; j < D; ++j) g.m[((size_t)b * D + i) * D + j] = M(b, i, j);
+    if (k == 1) {  // exact zeros of the real / imaginary parts (gate matrices are built analytically on the host)
+        bool real_diag = true, imag_off = true, real_off = true;
+        for (int b = 0; b < bm; ++b) {
+            real_diag = real_diag && M(b, 0, 0).imag() == 0.0 && M(b, 1, 1).imag() == 0.0;
+            imag_off = imag_off && M(b, 0, 1).real() == 0.0 && M(b, 1, 0).real() == 0.0;
+            real_off = real_off && M(b, 0, 1).imag() == 0.0 && M(b, 1, 0).imag() == 0.0;
+        }
+        if (real_diag && real_off) g.half = 2;
+        else if (real_diag && imag_off) g.half = 1;
+    }
     out.push_back(g);
     return 0;
 }
@@ -382,7 +394,8 @@ struct Scheduler {
             }
             uint32_t opc = 0;
             const int p0 = pos[srt[0]], p1 = k > 1 ? pos[srt[1]] : 0, p2 = k > 2 ? pos[srt[2]] : 0;
-            if (k == 1) opc = LOP_G1 + (uint32_t)p0;
+            if (k == 1 && g.half) opc = (g.half == 1 ? LOP_RA : LOP_RB) + (uint32_t)p0;
+            else if (k == 1) opc = LOP_G1 + (uint32_t)p0;
             else if (k == 2) {
                 static const int pair_index[4][4] = {{-1, 0, 1, 2}, {-1, -1, 3, 4}, {-1, -1, -1, 5}, {-1, -1, -1, -1}};
                 opc = LOP_G2 + (uint32_t)pair_index[p0][p1];
@@ -392,7 +405,7 @@ struct Scheduler {
             }
             r.code[nc++] = opc | ((uint32_t)nmat << 8);
             nmat += D * D;
-            info.fma_per_amp += 4.0 * D;
+            info.fma_per_amp += (k == 1 && g.half) ? 4.0 : 4.0 * D;
         }
         r.ncodes = (uint32_t)nc | (vec ? 0x100u : 0u);
         info.rounds++;

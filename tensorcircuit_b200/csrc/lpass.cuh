@@ -38,7 +38,9 @@ constexpr uint32_t LOP_G1 = 0;    // +p          general 2x2 on register positio
 constexpr uint32_t LOP_G2 = 4;    // +pair index general 4x4 on positions (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
 constexpr uint32_t LOP_G3 = 10;   // +e          general 8x8 on the three positions other than e
 constexpr uint32_t LOP_DG = 14;   //             16-entry diagonal table over the register index
-constexpr uint32_t LOP_COUNT = 15;
+constexpr uint32_t LOP_RA = 15;   // +p          2x2 with real diagonal and imaginary off-diagonal (rx, ...): half the FMAs
+constexpr uint32_t LOP_RB = 19;   // +p          real 2x2 (h, ry, ...): half the FMAs
+constexpr uint32_t LOP_COUNT = 23;
 
 // one matrix element in the parameter bank
 template <typename Real>
@@ -105,6 +107,50 @@ __device__ __forceinline__ void me_fma<float2, float>(float2& acc, const ME<floa
 }
 #endif
 
+// products with a purely real / purely imaginary element: one packed FMA instead of two
+template <typename C, typename Real>
+TCB_HD C me_mul_re(const ME<Real>& m, const C v) {
+    C r;
+    r.x = m.re * v.x;
+    r.y = m.re * v.y;
+    return r;
+}
+template <typename C, typename Real>
+TCB_HD void me_fma_re(C& acc, const ME<Real>& m, const C v) {
+    acc.x = fma(m.re, v.x, acc.x);
+    acc.y = fma(m.re, v.y, acc.y);
+}
+template <typename C, typename Real>
+TCB_HD C me_mul_im(const ME<Real>& m, const C v) {  // (i im) * v
+    C r;
+    r.x = -m.im0 * v.y;
+    r.y = m.im0 * v.x;
+    return r;
+}
+template <typename C, typename Real>
+TCB_HD void me_fma_im(C& acc, const ME<Real>& m, const C v) {
+    acc.x = fma(-m.im0, v.y, acc.x);
+    acc.y = fma(m.im0, v.x, acc.y);
+}
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+template <>
+__device__ __forceinline__ float2 me_mul_re<float2, float>(const ME<float>& m, const float2 v) {
+    return __fmul2_rn(make_float2(m.re, m.re), v);
+}
+template <>
+__device__ __forceinline__ void me_fma_re<float2, float>(float2& acc, const ME<float>& m, const float2 v) {
+    acc = __ffma2_rn(make_float2(m.re, m.re), v, acc);
+}
+template <>
+__device__ __forceinline__ float2 me_mul_im<float2, float>(const ME<float>& m, const float2 v) {
+    return __fmul2_rn(make_float2(-m.im0, m.im1), make_float2(v.y, v.x));
+}
+template <>
+__device__ __forceinline__ void me_fma_im<float2, float>(float2& acc, const ME<float>& m, const float2 v) {
+    acc = __ffma2_rn(make_float2(-m.im0, m.im1), make_float2(v.y, v.x), acc);
+}
+#endif
+
 // ---- micro-ops on the 16 amplitudes of a group -------------------------------------------------
 template <typename C, typename Real, int P0>
 TCB_HD void lp_g1(C* v, const ME<Real>* m) {
@@ -117,6 +163,31 @@ TCB_HD void lp_g1(C* v, const ME<Real>* m) {
         me_fma<C, Real>(o0, m[1], a1);
         C o1 = me_mul<C, Real>(m[2], a0);
         me_fma<C, Real>(o1, m[3], a1);
+        v[i0] = o0;
+        v[i1] = o1;
+    }
+}
+
+// 2x2 whose elements are each purely real or purely imaginary.  IMOFF: the off-diagonal pair is
+// imaginary (rx-like: cos I - i sin X); otherwise the whole matrix is real (h, ry).  4 real FMA per
+// amplitude instead of 8.
+template <typename C, typename Real, int P0, bool IMOFF>
+TCB_HD void lp_r1(C* v, const ME<Real>* m) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int lo = r & ((1 << P0) - 1);
+        const int i0 = ((r >> P0) << (P0 + 1)) | lo, i1 = i0 | (1 << P0);
+        const C a0 = v[i0], a1 = v[i1];
+        C o0 = me_mul_re<C, Real>(m[0], a0);
+        C o1;
+        if (IMOFF) {
+            me_fma_im<C, Real>(o0, m[1], a1);
+            o1 = me_mul_im<C, Real>(m[2], a0);
+        } else {
+            me_fma_re<C, Real>(o0, m[1], a1);
+            o1 = me_mul_re<C, Real>(m[2], a0);
+        }
+        me_fma_re<C, Real>(o1, m[3], a1);
         v[i0] = o0;
         v[i1] = o1;
     }
@@ -197,6 +268,14 @@ TCB_HD void lp_dispatch(C* v, uint32_t code, const ME<Real>* mats) {
         case 11: lp_g3<C, Real, 1>(v, m); break;
         case 12: lp_g3<C, Real, 2>(v, m); break;
         case 13: lp_g3<C, Real, 3>(v, m); break;
+        case 15: lp_r1<C, Real, 0, true>(v, m); break;
+        case 16: lp_r1<C, Real, 1, true>(v, m); break;
+        case 17: lp_r1<C, Real, 2, true>(v, m); break;
+        case 18: lp_r1<C, Real, 3, true>(v, m); break;
+        case 19: lp_r1<C, Real, 0, false>(v, m); break;
+        case 20: lp_r1<C, Real, 1, false>(v, m); break;
+        case 21: lp_r1<C, Real, 2, false>(v, m); break;
+        case 22: lp_r1<C, Real, 3, false>(v, m); break;
         default: lp_dg<C, Real>(v, m); break;
     }
 }

@@ -206,6 +206,10 @@ def fuse(ops: Sequence[GateOp], nqubits: int, kmax: int = 4) -> List[Block]:
 # :826-865 (rzz/rxx/ryy via exponential_gate_unity).
 
 KIND_DENSE, KIND_DIAG, KIND_PERM, KIND_MONO = "dense", "diag", "perm", "mono"
+# planner-only class: a dense 1-qubit gate whose elements are each purely real or purely imaginary (rx, ry,
+# h ...): the gate pass applies it with half the FMAs (LOP_RA / LOP_RB).  Blocks carry KIND_DENSE -- the
+# library recognises the pattern from the matrix itself.
+KIND_HALF = "half"
 
 
 # entries below this magnitude are rounding residue of the gate formulas (cos(pi/2) = 6e-17 in
@@ -218,6 +222,13 @@ def matrix_kind(m: Any) -> str:
     a = _raw(m)
     if a.ndim == 2 and a.shape[0] <= 4:
         return _small_matrix_kind(a.tolist())
+    if a.ndim == 3 and a.shape[-1] == 2:
+        off = np.abs(a[:, 0, 1]).max() > SNAP_EPS or np.abs(a[:, 1, 0]).max() > SNAP_EPS
+        if off and not (a[:, 0, 0].imag.any() or a[:, 1, 1].imag.any()):
+            if not (a[:, 0, 1].imag.any() or a[:, 1, 0].imag.any()) or not (a[:, 0, 1].real.any() or a[:, 1, 0].real.any()):
+                dg = np.abs(a[:, 0, 0]).max() > SNAP_EPS or np.abs(a[:, 1, 1]).max() > SNAP_EPS
+                if dg:
+                    return KIND_HALF
     mag = np.abs(a)
     if a.ndim == 3:
         mag = mag.max(axis=0)
@@ -256,6 +267,10 @@ def _small_matrix_kind(rows: List[List[complex]]) -> str:
         return KIND_DIAG
     if mono and all(c == 1 for c in colcount):
         return KIND_PERM if ones else KIND_MONO
+    if D == 2:
+        (a, b), (c, d) = rows
+        if a.imag == 0 and d.imag == 0 and ((b.imag == 0 and c.imag == 0) or (b.real == 0 and c.real == 0)):
+            return KIND_HALF
     return KIND_DENSE
 
 
@@ -268,12 +283,12 @@ def _kind_cost(kind: str, k: int) -> int:
         return 2 << k
     if kind == KIND_PERM:
         return 0
-    return 2  # one table multiply
+    return 2  # one table multiply / a half-cost 1-qubit gate
 
 
 def _combine_kinds(kinds: Sequence[str]) -> str:
-    if KIND_DENSE in kinds:
-        return KIND_DENSE
+    if KIND_DENSE in kinds or KIND_HALF in kinds:
+        return KIND_DENSE  # (a product of half-cost gates may be half-cost again: fuse_structured looks at the matrix)
     if all(k == KIND_DIAG for k in kinds):
         return KIND_DIAG
     if all(k == KIND_PERM for k in kinds):
@@ -345,14 +360,14 @@ def plan_structure_kinds(gate_qubits: Sequence[Tuple[int, ...]], gate_kinds: Seq
             # upgraded to a dense 2-qubit block that the following 1-qubit gates then join for
             # free (lookahead: 4 packed FMA of credit per qubit whose next gate is such a gate).
             inner = [b for b in ontop if bq[b] <= sq]
-            if inner and any(bkind[b] == KIND_DENSE for b in inner):
+            if inner and any(bkind[b] in (KIND_DENSE, KIND_HALF) for b in inner):
                 kind_m = _combine_kinds([bkind[b] for b in inner] + [kg])
                 parts = sum(_kind_cost(bkind[b], len(bq[b])) for b in inner) + _kind_cost(kg, len(qs))
                 credit = 0
                 for q in qs:
                     j = nxt_on[gi].get(q)
-                    if j is not None and len(gate_qubits[j]) == 1 and gate_kinds[j] == KIND_DENSE:
-                        credit += _kind_cost(KIND_DENSE, 1)
+                    if j is not None and len(gate_qubits[j]) == 1 and gate_kinds[j] in (KIND_DENSE, KIND_HALF):
+                        credit += _kind_cost(gate_kinds[j], 1)
                 margin = 3 if (gb[gi] or any(bbat[b] for b in inner)) else 0
                 if _kind_cost(kind_m, len(sq)) + margin <= parts + credit:
                     # the merged block holds the gate, which must follow the latest blocks that
@@ -404,6 +419,8 @@ def fuse_structured(ops: Sequence[GateOp], nqubits: int, kmax: int = 2) -> List[
         batched = m.ndim == 3
         bits = tuple(sorted(nqubits - 1 - q for q in qs))
         kind = kinds[grp[0]] if single else matrix_kind(m)
+        if kind == KIND_HALF:
+            kind = KIND_DENSE  # planner-only class; the exact zeros of analytic matrices survive as they are
         if kind != KIND_DENSE and not batched:
             # hand the library exact zeros / ones: it classifies by exact comparison
             m = np.where(np.abs(m) > SNAP_EPS, m, 0)

@@ -309,6 +309,9 @@ def _rot(p: np.ndarray, theta: Any) -> Gate:
     theta = _s(theta)
     if is_batched(theta):
         g = Gate(_cos_sin_batched(theta / 2.0, _i_matrix, p))
+        # (not the planner's half-cost class: with per-element matrices a merged block saves more -- one
+        # matrix fetch and one dispatch per amplitude group -- than the halved FMAs of an unmerged rx / ry;
+        # config 3: 131 ms merged, 151 ms unmerged)
         g.kind = "diag" if not (p[0, 1] or p[1, 0]) else "dense"
         return g
     return Gate(np.cos(theta / 2.0) * _i_matrix - 1.0j * np.sin(theta / 2.0) * p)

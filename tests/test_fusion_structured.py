@@ -56,7 +56,8 @@ def test_fused_product_equals_gate_product(n, kmax):
         for b in blocks:
             # block matrix: index bit j <-> bits[j]  ==  big-endian over ascending qubits
             got = _embed(n, b.qubits, b.matrix) @ got
-            assert b.kind == fusion.matrix_kind(b.matrix)
+            # ('half' is a planner-only class of 1-qubit gates; blocks carry 'dense' for it)
+            assert b.kind == fusion.matrix_kind(b.matrix).replace("half", "dense")
             assert len(b.qubits) <= max(kmax, 3)
         assert np.max(np.abs(got - want)) < 1e-12, trial
 
@@ -85,5 +86,11 @@ def test_kinds():
     assert fusion.matrix_kind(orc.gate_matrix("cz")) == "diag"
     assert fusion.matrix_kind(orc.gate_matrix("rzz", theta=0.3)) == "diag"
     assert fusion.matrix_kind(orc.m_rz(0.3)) == "diag"
-    assert fusion.matrix_kind(orc.gate_matrix("h")) == "dense"
+    # 1-qubit gates whose elements are each real or imaginary: half-cost class of the gate pass
+    assert fusion.matrix_kind(orc.gate_matrix("h")) == "half"
+    assert fusion.matrix_kind(orc.gate_matrix("rx", theta=0.3)) == "half"
+    assert fusion.matrix_kind(orc.gate_matrix("ry", theta=0.3)) == "half"
+    assert fusion.matrix_kind(orc.m_r(0.3, 0.4, 0.5)) == "dense"
+    assert fusion.matrix_kind(np.stack([orc.gate_matrix("rx", theta=t) for t in (0.1, 0.2, 0.0)])) == "half"
+    assert fusion.matrix_kind(np.stack([orc.gate_matrix("rx", theta=0.1), orc.m_r(0.3, 0.4, 0.5)])) == "dense"
     assert fusion.matrix_kind(orc.gate_matrix("toffoli")) == "dense"  # 8x8 permutations are not tracked on the host

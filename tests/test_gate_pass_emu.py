@@ -76,6 +76,32 @@ def test_dense_micro_ops_every_position(emu, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_half_cost_one_bit_gates(emu, dtype):
+    """rx / ry / h (every element purely real or purely imaginary) run as LOP_RA / LOP_RB: 4 FMA per amplitude
+    instead of 8, on every register position, same numbers as the oracle"""
+    rng = np.random.default_rng(21)
+    n = 10
+    for trial in range(10):
+        gates = []
+        for _ in range(8):
+            name = ["rx", "ry", "h"][int(rng.integers(3))]
+            m = _bit_matrix("h") if name == "h" else orc.gate_matrix(name, theta=rng.uniform(0, 6.28))
+            gates.append(([int(rng.integers(n))], m))
+        st = _rand_state(rng, n, dtype)
+        ref = _oracle(st, n, gates)
+        info = _run_pass(emu, st, n, gates)
+        assert info["ndense"] == 8 and info["fma"] == 8 * 4, info
+        assert np.max(np.abs(st - ref)) < TOL[dtype] * 4, trial
+    # a general 1-bit gate next to them keeps the full cost
+    gates = [([3], orc.gate_matrix("rx", theta=0.4)), ([5], orc.m_r(0.3, 0.4, 0.5))]
+    st = _rand_state(rng, n, dtype)
+    ref = _oracle(st, n, gates)
+    info = _run_pass(emu, st, n, gates)
+    assert info["fma"] == 4 + 8
+    assert np.max(np.abs(st - ref)) < TOL[dtype] * 4
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
 def test_affine_permutations_cost_no_round(emu, dtype):
     rng = np.random.default_rng(2)
     n = 9

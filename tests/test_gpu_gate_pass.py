@@ -55,6 +55,8 @@ def _random_gates(rng, avail, count, classes):
             out.append(([int(rng.choice(avail))], orc.m_r(*rng.uniform(0, 6.28, size=3))))
         elif c == "rz":
             out.append(([int(rng.choice(avail))], orc.m_rz(rng.uniform(0, 6.28))))
+        elif c == "rxy":  # real diagonal + imaginary / real off-diagonal: the half-cost micro-ops
+            out.append(([int(rng.choice(avail))], orc.gate_matrix(["rx", "ry"][int(rng.integers(2))], theta=rng.uniform(0, 6.28))))
         elif c == "u3":
             out.append((sorted(rng.choice(avail, size=3, replace=False).tolist()), _rand_u(rng, 3)))
         elif c == "toffoli":
@@ -78,7 +80,7 @@ def _random_gates(rng, avail, count, classes):
     return out
 
 
-ALL = ["named1", "r", "rz", "u3", "toffoli", "cnot", "rzz", "mono", "rxx", "u2"]
+ALL = ["named1", "r", "rz", "rxy", "u3", "toffoli", "cnot", "rzz", "mono", "rxx", "u2"]
 
 
 @pytest.mark.parametrize("dtype", ["complex64", "complex128"])
