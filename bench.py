@@ -356,6 +356,46 @@ def config3_vmap(tc, engine, recipes, torch, B=1024, rank=0, world=1, reps=2):
             "parity": {"what": "3 batch elements vs the unbatched circuit", "max_rel_diff": err}}
 
 
+def config_gradient(tc, engine, recipes, torch, n=24, layers=4, reps=2):
+    """SURVEY 8(f) rank 2, next to the configs: value + gradient of the TFIM VQE energy through
+    K.value_and_grad (adjoint-state sweep), wall time per call; parity: one component against a central
+    difference of the engine's own value."""
+    from tensorcircuit_b200 import autodiff
+
+    terms = recipes.tfim_terms(n)
+    pss, ws = [ps for _, ps in terms], [w for w, _ in terms]
+
+    def energy(p):
+        c = tc.Circuit(n)
+        for i in range(n):
+            c.h(i)
+        for l in range(layers):
+            for i in range(n - 1):
+                c.rzz(i, i + 1, theta=p[2 * l, i])
+            for i in range(n):
+                c.rx(i, theta=p[2 * l + 1, i])
+        return tc.templates.measurements.pauli_sum_expectation(c, pss, ws)
+
+    p = np.random.default_rng(0).uniform(0, 2, size=(2 * layers, n))
+    vg = tc.backend.value_and_grad(energy)
+    before = dict(autodiff.ADJOINT_STATS)
+    v, g = vg(p)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        v, g = vg(p)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / reps
+    h = 1e-3
+    e = np.zeros_like(p)
+    e[1, 2] = h
+    fd = (float(energy(p + e)) - float(energy(p - e))) / (2 * h)
+    return {"config": "value_and_grad of a %d-qubit TFIM VQE energy (%d parameters, %d Pauli strings), adjoint-state sweep, complex64, 1 GPU" % (n, p.size, len(pss)),
+            "wall_ms": 1e3 * wall, "value": float(v), "grad_norm": float(np.linalg.norm(g)),
+            "sweeps": autodiff.ADJOINT_STATS["sweeps"] - before["sweeps"], "shift_rule_fallbacks": autodiff.ADJOINT_STATS["fallbacks"] - before["fallbacks"],
+            "parity": {"what": "d/dp[1,2] vs a central difference (h = 1e-3) of the engine's own complex64 value", "gradient": float(g[1, 2]), "central_difference": fd}}
+
+
 def run_ours(args):
     import torch
 
@@ -528,7 +568,7 @@ def run_ours(args):
     }
     if not args.no_configs:
         cfgs = []
-        for fn in (config2_tfim, config3_vmap):
+        for fn in (config2_tfim, config3_vmap, config_gradient):
             try:
                 cfgs.append(fn(tc, engine, recipes, torch))
             except Exception as e:  # extra records never cost the headline number

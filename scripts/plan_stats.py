@@ -58,6 +58,11 @@ def main():
     T = _lib.lib.tcb200_pass_tile_bits(0)
     cost = [0 if b.kind == "perm" else (16 if b.kind in ("diag", "mono") else 4 ** len(b.bits)) for b in blocks]
     weight = [0.0 if b.kind == "perm" else 1.0 for b in blocks]
+    import os
+    if os.environ.get("PLAN_W") == "fma":
+        weight = [0.0 if b.kind == "perm" else (2.0 if b.kind in ("diag", "mono") else (2.0 if fusion.matrix_kind(b.matrix) == "half" else float(2 << len(b.bits)))) for b in blocks]
+    if os.environ.get("PLAN_W") == "gates":
+        weight = [0.0 if b.kind == "perm" else float(b.ngates) for b in blocks]
     passes = fusion.plan_passes([b.bits for b in blocks], n, T, max_hi=a.max_hi, max_ops=a.max_ops, max_mat_elems=1280, max_pass_k=3,
                                 nseeds=a.nseeds, block_cost=cost, block_weight=weight)
     t2 = time.time()

@@ -31,7 +31,8 @@ struct GOp {
     int k;
     int bm;             // matrices held: 1 (shared by the batch) or the batch size (vmap)
     int lb[4];          // logical tile bit of matrix index bit j
-    std::vector<cd> m;  // per held matrix -- dense: D*D row-major; diag: D
+    std::vector<cd> m;  // diag: D entries per held matrix (dense ops use `src`)
+    const double* src = nullptr;  // dense: the caller's bm row-major D x D complex128 matrices (valid during the call)
     int linv[4];        // lin: L^{-1} e_i as k-bit masks (the inverse map is y -> L^{-1} y ^ cinv)
     int cinv;
     int half = 0;       // dense 1-bit gate whose elements are each real or imaginary: 1 = real diagonal +
@@ -120,10 +121,7 @@ int classify(int k, const int* lb, const double* mat, int bm, std::vector<GOp>& 
     g.k = k;
     g.bm = bm;
     for (int i = 0; i < k; ++i) g.lb[i] = lb[i];
-    g.m.resize((size_t)bm * D * D);
-    for (int b = 0; b < bm; ++b)
-        for (int i = 0; i < D; ++i)
-            for (int j = 0; j < D; ++j) g.m[((size_t)b * D + i) * D + j] = M(b, i, j);
+    g.src = mat;
     if (k == 1) {  // exact zeros of the real / imaginary parts (gate matrices are built analytically on the host)
         bool real_diag = true, imag_off = true, real_off = true;
         for (int b = 0; b < bm; ++b) {
@@ -204,12 +202,13 @@ struct Scheduler {
     LPassParams<Real>* q = nullptr;
     LPassInfo info;
     int nmat = 0;
-    int batch = 1;                 // > 1: per-element matrices go to `blob` ([batch][LP_MAT_ELEMS])
+    int batch = 1;                 // > 1: per-element matrices go to `blob` ([batch][bstride])
     ME<Real>* blob = nullptr;
+    size_t bstride = LP_MAT_ELEMS;
 
     // element `idx` of the parameter bank, for batch element b
     void put(int idx, int b, cd z) {
-        if (blob) put_elem<Real>(blob[(size_t)b * LP_MAT_ELEMS + idx], z);
+        if (blob) put_elem<Real>(blob[(size_t)b * bstride + idx], z);
         else put_elem<Real>(q->m[idx], z);
     }
 
@@ -387,10 +386,15 @@ struct Scheduler {
             };
             if (nmat + D * D > LP_MAT_ELEMS) return fail(TCB200_ERR_CAPACITY, "gate pass matrices exceed the parameter bank");
             if (nc >= LP_MAX_CODES) return fail(TCB200_ERR_CAPACITY, "more than %d micro-ops in a round", LP_MAX_CODES);
+            int rm[8];
+            for (int i = 0; i < D; ++i) rm[i] = remap(i);
             for (int b = 0; b < nb; ++b) {
-                const cd* gm = g.m.data() + (size_t)(g.bm > 1 ? b : 0) * D * D;
+                const double* gm = g.src + (size_t)(g.bm > 1 ? b : 0) * 2 * D * D;
                 for (int i = 0; i < D; ++i)
-                    for (int j = 0; j < D; ++j) put(nmat + i * D + j, b, gm[remap(i) * D + remap(j)]);
+                    for (int j = 0; j < D; ++j) {
+                        const double* z = gm + 2 * (rm[i] * D + rm[j]);
+                        put(nmat + i * D + j, b, cd(z[0], z[1]));
+                    }
             }
             uint32_t opc = 0;
             const int p0 = pos[srt[0]], p1 = k > 1 ? pos[srt[1]] : 0, p2 = k > 2 ? pos[srt[2]] : 0;
@@ -476,7 +480,7 @@ struct Scheduler {
 template <typename Real>
 int fill_lpass(LPassParams<Real>& q, LPassInfo& info, void* state, int nbits, int nops, const int* ops_k, const int* ops_bits,
                const double* mats, int n_hi, const int* tile_hi, const int* ops_batched = nullptr, int batch = 1,
-               ME<Real>* blob = nullptr, int swz_mode = SWZ_SW) {
+               ME<Real>* blob = nullptr, int swz_mode = SWZ_SW, bool tight_stride = false) {
     using C = typename CT<Real>::type;
     q.state = static_cast<C*>(state);
     q.bmats = nullptr;
@@ -519,6 +523,14 @@ int fill_lpass(LPassParams<Real>& q, LPassInfo& info, void* state, int nbits, in
         b += k;
         mp += (size_t)bm * (2ll << (2 * k));
     }
+    if (tight_stride && blob) {
+        // per-element blob stride = what the classified ops can need at most (diagonal merges only lower it):
+        // the chunks that travel to the constant bank are then contiguous, no compaction copy
+        size_t ub = 0;
+        for (const GOp& g : s.ops) ub += g.kind == GK_DENSE ? (size_t)1 << (2 * g.k) : (g.kind == GK_DIAG ? 16 : 0);
+        s.bstride = std::min<size_t>(LP_MAT_ELEMS, std::max<size_t>(ub, 1));
+    }
+    q.bstride = (int)s.bstride;
     q.nrounds = 0;
     q.ngb = q.g.T - LP_RB;
     q.tb = q.ngb < 8 ? q.ngb : 8;
@@ -934,6 +946,39 @@ static int lp_sm_count() {
     return sms;
 }
 
+// BATCHED through the constant bank: the per-element matrices of a CHUNK of batch elements sit in a
+// __constant__ array (filled by cudaMemcpyToSymbolAsync before the launch), element blockIdx.y at
+// blockIdx.y * p.bstride.  The offset is warp-uniform, so the matrices reach the FMAs exactly as in the
+// unbatched kernel -- LDCU -> uniform registers, 80 registers, 3 CTAs / SM -- instead of by per-thread
+// L1 loads into vector registers (128 registers, 2 CTAs / SM: 8.8 ms against 2.5 ms per pass of 2^30
+// amplitudes, profiles/r2_config3_launches_summary.txt).
+constexpr int LP_CBANK_ELEMS = 3840;  // 60 KiB of the 64 KiB constant bank
+__constant__ uint4 g_cmat[LP_CBANK_ELEMS];
+
+template <typename Real>
+__global__ void __launch_bounds__(256, sizeof(Real) == 4 ? 3 : 2) lpass_fast_cbank_kernel(const __grid_constant__ LPassParams<Real> p) {
+    using C = typename CT<Real>::type;
+    constexpr int NIT = sizeof(C) == 8 ? 2 : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t tid = threadIdx.x;
+    C* vec = p.state + ((uint64_t)blockIdx.y << p.g.n) + tile_base(p.g, blockIdx.x);
+    const ME<Real>* mats = reinterpret_cast<const ME<Real>*>(g_cmat) + blockIdx.y * p.bstride;
+    lstage_in_fast<C>(p.stage, vec, smem_raw, tid);
+    cp_async_wait_all();
+    __syncthreads();
+    for (int r = 0; r < p.nrounds; ++r) {
+        lround_thread_fast<C, Real, NIT>(smem_raw, p.r[r], mats, tid);
+        __syncthreads();
+    }
+    lstage_out_fast<C>(p.stage, p.out, vec, smem_raw, tid);
+}
+
+// TCB200_CBANK=0: per-element matrices from global memory (lpass_fast_kernel<Real, true>)
+static bool cbank_enabled() {
+    const char* e = getenv("TCB200_CBANK");
+    return !(e && e[0] == '0');
+}
+
 // pinned staging + events for the per-element matrix blobs of batched passes (two buffers, so that
 // the host can fill the blob of pass i + 1 while the copy of pass i is still in flight)
 struct BlobStage {
@@ -980,8 +1025,9 @@ static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, cons
     }
     alignas(64) CUtensorMap tmap;
     bool use_tma = state && !batched && sizeof(Real) == 4 && gate_tma_enabled();
+    const bool want_cbank = batched && state && cbank_enabled();
     int rc = fill_lpass<Real>(q, info, state, nbits, nops, ops_k, ops_bits, mats, n_hi, tile_hi, ops_batched, (int)batch, blob,
-                              use_tma ? SWZ_HW128 : SWZ_SW);
+                              use_tma ? SWZ_HW128 : SWZ_SW, want_cbank);
     if (rc) return rc;
     if (use_tma && (!q.fast || tma_encode_state_map(state, nbits, 1, q.g, batch, &q.tp, &tmap) != 0)) {
         use_tma = false;  // not eligible (small state, alignment, coordinate range): plan again for the LDGSTS layout
@@ -1006,10 +1052,37 @@ static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, cons
     dim3 grid((unsigned)ntiles, (unsigned)batch);
     dim3 block(1u << q.stb);
     if (batched) {
-        // only the used prefix of every element's blob travels
         const size_t used = (size_t)info.mat_elems * sizeof(ME<Real>);
+        const size_t bstride = (size_t)q.bstride;  // elements between two batch elements in the pinned blob
+        if (q.fast && used && want_cbank && bstride <= (size_t)LP_CBANK_ELEMS) {
+            // chunks of batch elements through the constant bank
+            static bool cattr = false;
+            if (!cattr) {
+                TCB_CUDA(cudaFuncSetAttribute(lpass_fast_cbank_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+                cattr = true;
+            }
+            const int64_t per = std::max<int64_t>(1, std::min<int64_t>(batch, (int64_t)(LP_CBANK_ELEMS / bstride)));
+            C* state0 = q.state;
+            // the whole blob goes to the device workspace in ONE host-to-device copy; the chunks then reach the
+            // constant bank by device-to-device copies (no PCIe latency between two kernels of a pass)
+            const size_t total_bytes = ((size_t)(batch - 1) * bstride) * sizeof(ME<Real>) + used;
+            TCB_CUDA(cudaMemcpyAsync(workspace, blob, total_bytes, cudaMemcpyHostToDevice, st));
+            TCB_CUDA(cudaEventRecord(bs.ev[slot], st));
+            const unsigned char* wsb = static_cast<const unsigned char*>(workspace);
+            for (int64_t c0 = 0; c0 < batch; c0 += per) {
+                const int64_t nb = std::min<int64_t>(per, batch - c0);
+                TCB_CUDA(cudaMemcpyToSymbolAsync(g_cmat, wsb + (size_t)c0 * bstride * sizeof(ME<Real>),
+                                                 ((size_t)(nb - 1) * bstride) * sizeof(ME<Real>) + used, 0, cudaMemcpyDeviceToDevice, st));
+                q.state = state0 + ((uint64_t)c0 << nbits);
+                lpass_fast_cbank_kernel<Real><<<dim3((unsigned)ntiles, (unsigned)nb), block, smem, st>>>(q);
+                TCB_LAUNCH_CHECK("lpass_fast_cbank_kernel");
+            }
+            q.state = state0;
+            return 0;
+        }
+        // only the used prefix of every element's blob travels
         if (used) {
-            TCB_CUDA(cudaMemcpy2DAsync(workspace, LP_MAT_ELEMS * sizeof(ME<Real>), blob, LP_MAT_ELEMS * sizeof(ME<Real>), used, (size_t)batch,
+            TCB_CUDA(cudaMemcpy2DAsync(workspace, LP_MAT_ELEMS * sizeof(ME<Real>), blob, bstride * sizeof(ME<Real>), used, (size_t)batch,
                                        cudaMemcpyHostToDevice, st));
         }
         TCB_CUDA(cudaEventRecord(bs.ev[slot], st));
