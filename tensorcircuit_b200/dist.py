@@ -478,7 +478,13 @@ class DistState:
 
     def sample(self, uniforms: Any) -> np.ndarray:
         """CDF sampling over the sharded state; returns *logical* basis-state indices (int64).
-        Every rank receives all uniforms; each resolves those that fall into its CDF interval."""
+        Every rank receives all uniforms; each resolves those that fall into its CDF interval.
+
+        The CDF runs over the amplitudes in their current PHYSICAL order (rank-major, then the local
+        physical bits): after a remap that is a permutation of the logical order, so the same ``status``
+        draws from the same distribution but not the same bitstrings as a single-GPU run -- samples are
+        reproducible for a fixed GPU count and circuit, not across GPU counts (restoring the identity
+        layout first would cost up to two more all-to-all remaps of the state)."""
         dev = self.local.buf.device
         mine = float(self.local.norm2()[0])
         tot = torch.zeros(self.G, dtype=torch.float64, device=dev)
@@ -492,8 +498,13 @@ class DistState:
         buf = torch.from_numpy(phys_idx).to(dev)
         dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=self.group)
         phys_idx = buf.cpu().numpy()
-        # rounding at shard boundaries can leave a shot unowned: give it to the last amplitude
-        phys_idx = np.where(phys_idx < 0, (1 << self.n) - 1, phys_idx)
+        # rounding at a shard boundary can leave a shot unowned: it goes to the last amplitude of the shard
+        # whose CDF interval it falls next to (not to the global last index, which would bias |1..1>)
+        lost = np.nonzero(phys_idx < 0)[0]
+        if lost.size:
+            u = uniforms.reshape(-1)[torch.from_numpy(lost)].cpu().numpy() if isinstance(uniforms, torch.Tensor) else np.asarray(uniforms, dtype=np.float64).reshape(-1)[lost]
+            k = np.clip(np.searchsorted(np.cumsum(t), total * (1.0 - np.asarray(u, dtype=np.float64)), side="left"), 0, self.G - 1)
+            phys_idx[lost] = (k.astype(np.int64) << self.nloc) | ((1 << self.nloc) - 1)
         # physical -> logical bit order
         out = np.zeros_like(phys_idx)
         for b in range(self.n):
