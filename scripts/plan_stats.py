@@ -1,6 +1,7 @@
 """Host-only planning statistics of a recipe (no GPU): structure-aware fusion -> pass plan -> the
 gate-pass scheduler's dry run (tcb200_gate_pass_info) per pass."""
 import argparse
+import os
 import collections
 import sys
 import time
@@ -64,7 +65,8 @@ def main():
     if os.environ.get("PLAN_W") == "gates":
         weight = [0.0 if b.kind == "perm" else float(b.ngates) for b in blocks]
     passes = fusion.plan_passes([b.bits for b in blocks], n, T, max_hi=a.max_hi, max_ops=a.max_ops, max_mat_elems=1280, max_pass_k=3,
-                                nseeds=a.nseeds, block_cost=cost, block_weight=weight)
+                                nseeds=a.nseeds, block_cost=cost, block_weight=weight,
+                                block_diag=None if os.environ.get("PLAN_NODIAG") else [b.kind == "diag" for b in blocks])
     t2 = time.time()
     tot = np.zeros(8)
     for p in passes:

@@ -9,7 +9,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <stdio.h>
+
 #include <algorithm>
+#include <chrono>
 #include <complex>
 #include <vector>
 
@@ -222,17 +225,35 @@ struct Scheduler {
         d = 0;
     }
 
+    // Dependencies by shared tile bits in program order, except that diagonal ops commute with each other: a
+    // diagonal op is ordered only against the non-diagonal ops around it (an rzz ladder is not a chain), a
+    // non-diagonal op against every diagonal op since the previous non-diagonal one on that bit.
     void build_deps() {
         const int n = (int)ops.size();
         preds.assign(n, {});
-        int last[LP_MAX_T];
+        int last[LP_MAX_T];                      // last non-diagonal op per bit
+        std::vector<int> dsince[LP_MAX_T];       // diagonal ops after it
         for (int t = 0; t < LP_MAX_T; ++t) last[t] = -1;
+        auto add = [&](int i, int p) {
+            if (p >= 0 && std::find(preds[i].begin(), preds[i].end(), p) == preds[i].end()) preds[i].push_back(p);
+        };
         for (int i = 0; i < n; ++i) {
+            const bool dg = ops[i].kind == GK_DIAG;
             for (int j = 0; j < ops[i].k; ++j) {
-                const int p = last[ops[i].lb[j]];
-                if (p >= 0 && std::find(preds[i].begin(), preds[i].end(), p) == preds[i].end()) preds[i].push_back(p);
+                const int b = ops[i].lb[j];
+                if (dg) {
+                    add(i, last[b]);
+                    dsince[b].push_back(i);
+                } else {
+                    if (!dsince[b].empty()) {
+                        for (int p : dsince[b]) add(i, p);
+                        dsince[b].clear();
+                    } else {
+                        add(i, last[b]);
+                    }
+                    last[b] = i;
+                }
             }
-            for (int j = 0; j < ops[i].k; ++j) last[ops[i].lb[j]] = i;
         }
         done.assign(n, 0);
     }
@@ -979,6 +1000,35 @@ static bool cbank_enabled() {
     return !(e && e[0] == '0');
 }
 
+// TCB200_TIMING=1: host microseconds spent in (0) classification + scheduling + matrix packing and (1) everything
+// after it (copies, launches, waits for a pinned buffer), printed when the library is unloaded
+struct HostTimerTotals {
+    double us[2] = {0, 0};
+    long calls = 0;
+    bool on = false;
+    HostTimerTotals() {
+        const char* e = getenv("TCB200_TIMING");
+        on = e && e[0] == '1';
+    }
+    ~HostTimerTotals() {
+        if (on) fprintf(stderr, "[tcb200 timing] gate passes: %ld calls, plan+pack %.1f ms, copy+launch %.1f ms\n", calls, us[0] / 1e3, us[1] / 1e3);
+    }
+};
+static HostTimerTotals g_host_timer;
+struct HostTimer {
+    int slot;
+    bool running;
+    std::chrono::steady_clock::time_point t0;
+    explicit HostTimer(int s) : slot(s), running(g_host_timer.on), t0(std::chrono::steady_clock::now()) {}
+    void stop() {
+        if (!running) return;
+        running = false;
+        g_host_timer.us[slot] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        if (slot == 0) g_host_timer.calls++;
+    }
+    ~HostTimer() { stop(); }
+};
+
 // pinned staging + events for the per-element matrix blobs of batched passes (two buffers, so that
 // the host can fill the blob of pass i + 1 while the copy of pass i is still in flight)
 struct BlobStage {
@@ -1026,6 +1076,7 @@ static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, cons
     alignas(64) CUtensorMap tmap;
     bool use_tma = state && !batched && sizeof(Real) == 4 && gate_tma_enabled();
     const bool want_cbank = batched && state && cbank_enabled();
+    HostTimer timer_fill(0);
     int rc = fill_lpass<Real>(q, info, state, nbits, nops, ops_k, ops_bits, mats, n_hi, tile_hi, ops_batched, (int)batch, blob,
                               use_tma ? SWZ_HW128 : SWZ_SW, want_cbank);
     if (rc) return rc;
@@ -1034,6 +1085,8 @@ static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, cons
         rc = fill_lpass<Real>(q, info, state, nbits, nops, ops_k, ops_bits, mats, n_hi, tile_hi, ops_batched, (int)batch, blob);
         if (rc) return rc;
     }
+    timer_fill.stop();
+    HostTimer timer_launch(1);
     if (info_out) *info_out = info;
     if (!state) return 0;  // dry run (tcb200_gate_pass_info)
     const uint64_t ntiles = 1ull << (nbits - q.g.T);

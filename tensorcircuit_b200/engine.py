@@ -259,7 +259,8 @@ class DeviceState:
         weight = [0.0 if b.kind == KIND_PERM else 1.0 for b in blocks]
         max_hi = min(self.gate_pass_max_hi, 9 if (self.nbits > T and T - (1 if self.amp_bytes == 8 else 0) == 12) else 8)
         passes = plan_passes([b.bits for b in blocks], self.nbits, T, max_hi=max_hi, max_ops=self.gate_pass_max_ops,
-                             max_mat_elems=_lib.GATE_PASS_MAT_ELEMS, max_pass_k=4, block_cost=cost, block_weight=weight)
+                             max_mat_elems=_lib.GATE_PASS_MAT_ELEMS, max_pass_k=4, block_cost=cost, block_weight=weight,
+                             block_diag=[b.kind == "diag" for b in blocks])
         nlaunch = 0
         for p in passes:
             blks = [blocks[i] for i in p.block_ids]

@@ -510,7 +510,7 @@ _PASS_CACHE: Dict[Any, List[Pass]] = {}
 def plan_passes(block_bits: Sequence[Tuple[int, ...]], nbits: int, tile_bits: int, max_hi: int = 6,
                 max_ops: int = 16, max_mat_elems: int = 1536, max_pass_k: int = 4, nseeds: int = 8,
                 block_cost: Optional[Sequence[int]] = None, block_weight: Optional[Sequence[float]] = None,
-                jitter_seed: Optional[int] = None) -> List[Pass]:
+                jitter_seed: Optional[int] = None, block_diag: Optional[Sequence[bool]] = None) -> List[Pass]:
     """List scheduling of fused blocks into tile passes, with a one-pass lookahead.
 
     A tile holds the ``tile_bits - h`` lowest index bits plus ``h <= max_hi`` gathered high bits;
@@ -529,19 +529,33 @@ def plan_passes(block_bits: Sequence[Tuple[int, ...]], nbits: int, tile_bits: in
     # jitter_seed: break the greedy's ties (equal number of new gathered bits) at random instead of
     # in program order -- plan_passes_best keeps the best of several such plans
     jit = np.random.default_rng(jitter_seed) if jitter_seed is not None else None
-    key = (tuple(block_bits), nbits, tile_bits, max_hi, max_ops, max_mat_elems, max_pass_k, nseeds, tuple(cost), tuple(weight), jitter_seed)
+    # block_diag: diagonal blocks commute with each other, so a diagonal block is only ordered against the
+    # non-diagonal blocks around it -- an rzz ladder is 27 independent blocks, not a chain from qubit 0 to n-1
+    # (any order consistent with this relaxed DAG gives the same product up to rounding)
+    diag = [bool(x) for x in block_diag] if block_diag is not None else [False] * len(block_bits)
+    key = (tuple(block_bits), nbits, tile_bits, max_hi, max_ops, max_mat_elems, max_pass_k, nseeds, tuple(cost), tuple(weight), jitter_seed,
+           tuple(diag) if any(diag) else None)
     hit = _PASS_CACHE.get(key)
     if hit is not None:
         return hit
     nb = len(block_bits)
     preds: List[set] = [set() for _ in range(nb)]
     succs: List[List[int]] = [[] for _ in range(nb)]
-    last: Dict[int, int] = {}
+    last: Dict[int, int] = {}           # per bit: the last non-diagonal block
+    dsince: Dict[int, List[int]] = {}   # per bit: the diagonal blocks after it
     for i, bits in enumerate(block_bits):
         for q in bits:
-            if q in last:
-                preds[i].add(last[q])
-            last[q] = i
+            if diag[i]:
+                if q in last:
+                    preds[i].add(last[q])
+                dsince.setdefault(q, []).append(i)
+            else:
+                if dsince.get(q):
+                    preds[i].update(dsince[q])
+                    dsince[q] = []
+                elif q in last:
+                    preds[i].add(last[q])
+                last[q] = i
     for i in range(nb):
         for p in preds[i]:
             succs[p].append(i)

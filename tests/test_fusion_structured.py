@@ -94,3 +94,40 @@ def test_kinds():
     assert fusion.matrix_kind(np.stack([orc.gate_matrix("rx", theta=t) for t in (0.1, 0.2, 0.0)])) == "half"
     assert fusion.matrix_kind(np.stack([orc.gate_matrix("rx", theta=0.1), orc.m_r(0.3, 0.4, 0.5)])) == "dense"
     assert fusion.matrix_kind(orc.gate_matrix("toffoli")) == "dense"  # 8x8 permutations are not tracked on the host
+
+
+@pytest.mark.parametrize("n", [5, 7])
+def test_pass_plan_reorders_only_commuting_diagonals(n):
+    """plan_passes(block_diag=...) orders a diagonal block only against the non-diagonal blocks around it (an
+    rzz ladder is not a dependency chain): the product of the blocks taken in PASS order is still the circuit"""
+    rng = np.random.default_rng(100 + n)
+    for trial in range(8):
+        ops = []
+        for _ in range(45):
+            c = int(rng.integers(0, 6))
+            if c <= 2:  # plenty of diagonal gates sharing qubits
+                q = tuple(int(x) for x in rng.choice(n, size=2, replace=False))
+                ops.append(GateOp(q, orc.gate_matrix(["rzz", "cz"][c % 2], **({"theta": rng.uniform(0, 6.28)} if c % 2 == 0 else {})), "d2"))
+            elif c == 3:
+                ops.append(GateOp((int(rng.integers(n)),), orc.m_rz(rng.uniform(0, 6.28)), "rz"))
+            elif c == 4:
+                ops.append(GateOp((int(rng.integers(n)),), orc.gate_matrix("rx", theta=rng.uniform(0, 6.28)), "rx"))
+            else:
+                q = tuple(int(x) for x in rng.choice(n, size=2, replace=False))
+                ops.append(GateOp(q, orc.gate_matrix("cnot"), "cnot"))
+        want = np.eye(2**n, dtype=np.complex128)
+        for op in ops:
+            want = _embed(n, op.qubits, np.asarray(op.matrix)) @ want
+        blocks = fusion.fuse_structured(ops, n, 2)
+        diag = [b.kind == "diag" for b in blocks]
+        assert any(diag)
+        # a 4-bit tile with at most 2 gathered bits forces many passes and a lot of reordering
+        passes = fusion.plan_passes([b.bits for b in blocks], n, 4, max_hi=2, max_ops=6, max_pass_k=3, block_diag=diag)
+        order = [i for p in passes for i in p.block_ids]
+        assert sorted(order) == list(range(len(blocks)))
+        got = np.eye(2**n, dtype=np.complex128)
+        for i in order:
+            got = _embed(n, blocks[i].qubits, blocks[i].matrix) @ got
+        assert np.max(np.abs(got - want)) < 1e-12, trial
+        plain = fusion.plan_passes([b.bits for b in blocks], n, 4, max_hi=2, max_ops=6, max_pass_k=3)
+        assert len(passes) <= len(plain)
