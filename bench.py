@@ -266,12 +266,22 @@ def config2_tfim(tc, engine, recipes, torch, reps=3):
     torch.cuda.synchronize()
     engine.reset_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    # gate phase = fusion (cached by structure) + pass planning + the gate passes; the Python recording of the
+    # 248 gate calls is done before the clock starts (it is in `gate_phase_with_recording_ms`)
+    g_ms = 0.0
+    t_rec = 0.0
     for _ in range(reps):
-        c = gates()
-    e1.record()
-    torch.cuda.synchronize()
-    g_ms = e0.elapsed_time(e1) / reps
+        t0 = time.perf_counter()
+        c = recipes.build(tc.Circuit(n), ops)
+        torch.cuda.synchronize()
+        e0.record()
+        c._ensure_state()
+        e1.record()
+        torch.cuda.synchronize()
+        t_rec += time.perf_counter() - t0
+        g_ms += e0.elapsed_time(e1)
+    g_ms /= reps
+    g_rec_ms = 1e3 * t_rec / reps
     passes = engine.STATS["apply_launches"] // reps
     rounds = engine.STATS["gate_pass_rounds"] // reps
     fma = engine.STATS["gate_pass_fma_per_amp"] / reps
@@ -309,7 +319,7 @@ def config2_tfim(tc, engine, recipes, torch, reps=3):
     peak, _ = measured_peak()
     return {"config": "28-qubit TFIM VQE energy (H layer + %d x (rzz ladder, rx layer); 2n = %d Pauli strings through a loop of c.expectation_ps), complex64, 1 GPU" % (layers, len(pss)),
             "recorded_gates": len(ops), "gate_passes": passes, "gate_pass_rounds": rounds, "fma_per_amplitude": fma,
-            "gate_phase_ms": g_ms, "gate_phase_gbs": passes * 2 * st_bytes / (g_ms * 1e-3) / 1e9, "gate_phase_frac_of_hbm_peak": passes * 2 * st_bytes / (g_ms * 1e-3) / 1e9 / peak,
+            "gate_phase_ms": g_ms, "gate_phase_with_recording_ms": g_rec_ms, "gate_phase_gbs": passes * 2 * st_bytes / (g_ms * 1e-3) / 1e9, "gate_phase_frac_of_hbm_peak": passes * 2 * st_bytes / (g_ms * 1e-3) / 1e9 / peak,
             "energy_ms": x_ms, "energy_launches": xl, "energy_reads_of_state_gbs": xl * st_bytes / (x_ms * 1e-3) / 1e9, "energy": energy,
             "parity": {"what": "same ansatz at n=24: complex64 vs complex128 energy", "c64": es[0], "c128": es[1], "rel_diff": abs(es[0] - es[1]) / max(1e-12, abs(es[1]))}}
 
