@@ -493,3 +493,101 @@ def vectorized_value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequenc
         return np.asarray(vals), (grads[0] if single else tuple(grads))
 
     return wrapper
+
+
+# ---- vjp / jvp / jacobians / hessian on top of the sweep (abstract_backend.py:1461-1658) -----------------
+def _as_tuple(x: Any) -> Tuple[Tuple[Any, ...], bool]:
+    if isinstance(x, (tuple, list)):
+        return tuple(x), True
+    return (x,), False
+
+
+def _component(f: Callable[..., Any], i: Optional[int], weights: Optional[np.ndarray] = None) -> Callable[..., Any]:
+    """scalar function of the same arguments: component ``i`` of ``f`` (flattened), or sum(weights * f)"""
+
+    def g(*a: Any, **k: Any) -> Any:
+        out = f(*a, **k)
+        if isinstance(out, (tuple, list)):
+            raise NotImplementedError("jacobians / vjp of functions with several outputs")
+        flat = out.reshape([-1]) if isinstance(out, BatchArray) else np.reshape(np.asarray(out), [-1])
+        if i is not None:
+            return flat[i]
+        acc = None
+        for j, w in enumerate(weights):  # type: ignore[arg-type]
+            if w != 0:
+                t = flat[j] * w
+                acc = t if acc is None else acc + t
+        return acc if acc is not None else flat[0] * 0.0
+
+    return g
+
+
+def vjp(f: Callable[..., Any], inputs: Any, v: Any) -> Tuple[Any, Any]:
+    """(f(*inputs), v^T J): the vector-Jacobian product is the gradient of sum(v * f) -- ONE adjoint sweep
+    whatever the number of outputs (abstract_backend.py:1484-1507)."""
+    ins, many = _as_tuple(inputs)
+    value = f(*ins)
+    w = np.real(np.asarray(v, dtype=np.complex128)).reshape(-1)
+    g = grad(_component(f, None, w), argnums=tuple(range(len(ins))))(*ins)
+    return value, (tuple(g) if many else g[0])
+
+
+def jacrev(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0) -> Callable[..., Any]:
+    """Jacobian of a vector of expectation-value expressions, output axes first (abstract_backend.py:1574-1648):
+    one adjoint sweep per output component."""
+    single = isinstance(argnums, int)
+    nums: Tuple[int, ...] = (argnums,) if single else tuple(argnums)  # type: ignore[assignment]
+
+    def wrapper(*args: Any, **kws: Any) -> Any:
+        values = np.asarray(f(*args, **kws))
+        m = int(values.size)
+        rows = [grad(_component(f, i), argnums=nums)(*args, **kws) for i in range(m)]
+        out = []
+        for pos, a in enumerate(nums):
+            shape = tuple(values.shape) + tuple(np.shape(args[a]))
+            out.append(np.stack([np.asarray(r[pos]) for r in rows]).reshape(shape))
+        return out[0] if single else tuple(out)
+
+    return wrapper
+
+
+jacfwd = jacrev  # same array for one output and one argument; there is no separate forward mode here
+
+
+def jvp(f: Callable[..., Any], inputs: Any, v: Any) -> Tuple[Any, Any]:
+    """(f(*inputs), J v) (abstract_backend.py:1461-1482), assembled from the reverse-mode Jacobian"""
+    ins, _ = _as_tuple(inputs)
+    vs, _ = _as_tuple(v)
+    value = f(*ins)
+    J = jacrev(f, argnums=tuple(range(len(ins))))(*ins)
+    out_shape = np.shape(np.asarray(value))
+    acc = np.zeros(out_shape)
+    for Ja, va in zip(J, vs):
+        acc = acc + np.tensordot(np.asarray(Ja), np.real(np.asarray(va)), axes=np.ndim(va)).reshape(out_shape)
+    return value, acc
+
+
+def hessian(f: Callable[..., Any], argnums: int = 0, step: float = 1e-4) -> Callable[..., Any]:
+    """Hessian of a scalar loss: central differences (step ``step``) of the EXACT adjoint gradient, symmetrised.
+    The reference nests forward over reverse mode (abstract_backend.py:1650-1658); there is no second-order sweep here,
+    so the result carries a truncation error of O(step^2) and, in complex64, rounding noise of ~1e-7 / step."""
+    if not isinstance(argnums, int):
+        raise NotImplementedError("hessian with respect to several arguments")
+    g = grad(f, argnums=argnums)
+
+    def wrapper(*args: Any, **kws: Any) -> Any:
+        x = np.array(np.real(np.asarray(args[argnums])), dtype=np.float64)
+        P = x.size
+        H = np.zeros((P, P))
+        for k in range(P):
+            h = step * max(1.0, abs(x.reshape(-1)[k]))
+            up, dn = x.copy().reshape(-1), x.copy().reshape(-1)
+            up[k] += h
+            dn[k] -= h
+            a_up, a_dn = list(args), list(args)
+            a_up[argnums], a_dn[argnums] = up.reshape(x.shape), dn.reshape(x.shape)
+            H[:, k] = (np.asarray(g(*a_up, **kws)).reshape(-1) - np.asarray(g(*a_dn, **kws)).reshape(-1)) / (2 * h)
+        H = 0.5 * (H + H.T)
+        return H.reshape(x.shape + x.shape)
+
+    return wrapper

@@ -455,18 +455,31 @@ class B200Backend:
 
     vvag = vectorized_value_and_grad
 
-    def _no_ad(name: str):  # type: ignore[misc]
-        def f(self, *a: Any, **k: Any) -> Any:
-            raise NotImplementedError("%s: only value_and_grad / grad / vvag of expectation-value losses are built (autodiff.py)" % name)
+    # vjp / jvp / Jacobians / Hessian on top of the adjoint sweep (abstract_backend.py:1461-1658)
+    def vjp(self, f: Callable[..., Any], inputs: Any, v: Any) -> Any:
+        from . import autodiff
 
-        return f
+        return autodiff.vjp(f, inputs, v)
 
-    jvp = _no_ad("jvp")
-    vjp = _no_ad("vjp")
-    jacfwd = _no_ad("jacfwd")
-    jacrev = _no_ad("jacrev")
-    hessian = _no_ad("hessian")
-    del _no_ad
+    def jvp(self, f: Callable[..., Any], inputs: Any, v: Any) -> Any:
+        from . import autodiff
+
+        return autodiff.jvp(f, inputs, v)
+
+    def jacrev(self, f: Callable[..., Any], argnums: Any = 0) -> Callable[..., Any]:
+        from . import autodiff
+
+        return autodiff.jacrev(f, argnums=argnums)
+
+    def jacfwd(self, f: Callable[..., Any], argnums: Any = 0) -> Callable[..., Any]:
+        from . import autodiff
+
+        return autodiff.jacfwd(f, argnums=argnums)
+
+    def hessian(self, f: Callable[..., Any], argnums: Any = 0) -> Callable[..., Any]:
+        from . import autodiff
+
+        return autodiff.hessian(f, argnums=argnums)
 
 
 _INSTANCE: Optional[B200Backend] = None

@@ -1056,7 +1056,7 @@ def test_value_and_grad_limits(eng):
     with pytest.raises(NotImplementedError):
         K.value_and_grad(uses_inputs)(np.array([0.3]))
     with pytest.raises(NotImplementedError):
-        K.hessian(lambda x: x)
+        K.hessian(lambda x: x, argnums=(0, 1))  # (hessian / jacobians of one argument exist: tests/test_operators.py)
     with pytest.raises(ValueError):
         K.value_and_grad(lambda p: p * np.ones(2))(np.array([0.3]))  # not a scalar loss
     # a loss that does not touch a circuit at all still differentiates (direct dependence only)
