@@ -41,6 +41,17 @@ from . import parallel  # noqa: F401
 
 backend = _backend_module.get_backend()
 
+# Recording a circuit allocates a few small objects per gate; with torch and numpy loaded, a full (generation-2)
+# cyclic collection walks their whole module heap and stalls the host for 50-170 ms every few thousand gate calls --
+# longer than all kernels of a 30-qubit step together.  Everything imported so far is module-level and lives for the
+# whole process anyway: move it to the permanent generation (TCB200_GC_FREEZE=0 to leave the collector alone).
+import gc as _gc  # noqa: E402
+import os as _os  # noqa: E402
+
+if _os.environ.get("TCB200_GC_FREEZE", "1") != "0":
+    _gc.collect()
+    _gc.freeze()
+
 
 def about() -> None:
     """tensorcircuit/about.py: versions of what the engine runs on"""

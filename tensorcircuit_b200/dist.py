@@ -506,9 +506,14 @@ class DistState:
             k = np.clip(np.searchsorted(np.cumsum(t), total * (1.0 - np.asarray(u, dtype=np.float64)), side="left"), 0, self.G - 1)
             phys_idx[lost] = (k.astype(np.int64) << self.nloc) | ((1 << self.nloc) - 1)
         # physical -> logical bit order
-        out = np.zeros_like(phys_idx)
+        same = 0
         for b in range(self.n):
-            out |= ((phys_idx >> self.phys[b]) & 1) << b
+            if self.phys[b] == b:
+                same |= 1 << b
+        out = phys_idx & np.int64(same)  # bits that sit where they belong move in one operation
+        for b in range(self.n):
+            if self.phys[b] != b:
+                out |= ((phys_idx >> self.phys[b]) & 1) << b
         return out
 
     def gather_state(self) -> np.ndarray:
