@@ -46,7 +46,7 @@ _MAX_BATCH_AMPS = 1 << 28
 
 
 class _Query:
-    def __init__(self, circ: Any, fl: Sequence[int], sg: Sequence[int], ny: Sequence[int]):
+    def __init__(self, circ: Any, fl: Sequence[int], sg: Sequence[int], ny: Sequence[int], need_key: bool = True):
         self.nqubits = circ._nqubits
         self.circ = circ  # strong reference: the circuit (and its id) outlives the trace
         # matrix [D, D], or [B, D, D] when the recording itself was run on a batch of nudged parameters
@@ -55,11 +55,15 @@ class _Query:
         # queries on the same gate sequence share their shifted simulations.  The key is the gate
         # CONTENT (qubits + matrix bytes), not the circuit object: sample_expectation_ps appends and
         # removes basis rotations on one circuit, and ids are reused after garbage collection.
-        h = hashlib.blake2b(digest_size=16)
-        for qubits, M in self.ops:
-            h.update(repr((qubits, M.shape)).encode())
-            h.update(np.ascontiguousarray(M).tobytes())
-        self.key = (self.nqubits, len(self.ops), h.digest())
+        # (only the queries of the device run are grouped; replayed ones are matched by position and their
+        # matrices carry a batch axis of all nudged parameters -- hashing those was 20 % of a gradient call)
+        self.key = None
+        if need_key:
+            h = hashlib.blake2b(digest_size=16)
+            for qubits, M in self.ops:
+                h.update(repr((qubits, M.shape)).encode())
+                h.update(np.ascontiguousarray(M).tobytes())
+            self.key = (self.nqubits, len(self.ops), h.digest())
         self.fl, self.sg, self.ny = list(fl), list(sg), list(ny)
         self.values: Optional[np.ndarray] = None  # complex [nterms]
 
@@ -121,7 +125,7 @@ class _ReplayState:
 
     def expectation_terms(self, fl: Sequence[int], sg: Sequence[int], ny: Sequence[int]) -> np.ndarray:
         i = len(self._trace.queries)
-        q = _Query(self._circ, fl, sg, ny)
+        q = _Query(self._circ, fl, sg, ny, need_key=False)
         self._trace.queries.append(q)
         if self._trace.replay is None or i >= len(self._trace.replay) or np.shape(self._trace.replay[i])[-1] != len(fl):
             raise RuntimeError("value_and_grad: the structure of the function changed between evaluations")

@@ -48,11 +48,18 @@ struct GOp {
 int classify(int k, const int* lb, const double* mat, int bm, std::vector<GOp>& out) {
     const int D = 1 << k;
     auto M = [&](int b, int i, int j) { return cd(mat[2 * (((size_t)b * D + i) * D + j)], mat[2 * (((size_t)b * D + i) * D + j) + 1]); };
-    auto any_nz = [&](int i, int j) {
-        for (int b = 0; b < bm; ++b)
-            if (M(b, i, j) != cd(0, 0)) return true;
-        return false;
-    };
+    // union of the non-zero patterns of the bm matrices, in one sweep over the data (a vmap batch of 1024
+    // diagonal gates would otherwise be scanned once per zero entry and check)
+    bool nzp[16][16];
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) nzp[i][j] = false;
+    for (int b = 0; b < bm; ++b) {
+        const double* mb = mat + 2 * (size_t)b * D * D;
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j)
+                if (mb[2 * (i * D + j)] != 0.0 || mb[2 * (i * D + j) + 1] != 0.0) nzp[i][j] = true;
+    }
+    auto any_nz = [&](int i, int j) { return nzp[i][j]; };
     // monomial?  (exact zeros: gate matrices are built analytically on the host)
     std::vector<int> perm(D, -1);
     bool mono = true;
