@@ -368,39 +368,47 @@ struct Scheduler {
         int last_dg = -1;  // matrix offset of a diagonal table the next diagonal op can merge into
         const int nb = blob ? batch : 1;
         std::vector<cd> dgtab((size_t)nb * 16);
+        auto flush_dg = [&]() {  // the finished table of a run of diagonal ops goes to the parameter bank / blob
+            if (last_dg < 0) return;
+            for (int b = 0; b < nb; ++b)
+                for (int x = 0; x < 16; ++x) put(last_dg + x, b, dgtab[(size_t)b * 16 + x]);
+            last_dg = -1;
+        };
         for (int oi : members) {
             const GOp& g = ops[oi];
             int pos[4];
             for (int j = 0; j < g.k; ++j) pos[j] = (int)(std::find(R.begin(), R.end(), g.lb[j]) - R.begin());
             if (g.kind == GK_DIAG) {
                 const int D = 1 << g.k;
-                auto entry = [&](int b, int x) {
+                int xidx[16];  // table index -> entry of this op's diagonal
+                for (int x = 0; x < 16; ++x) {
                     int idx = 0;
                     for (int j = 0; j < g.k; ++j) idx |= ((x >> pos[j]) & 1) << j;
-                    return g.m[(size_t)(g.bm > 1 ? b : 0) * D + idx];
-                };
-                if (last_dg >= 0) {  // consecutive diagonal ops: one table (product kept in double)
-                    for (int b = 0; b < nb; ++b)
-                        for (int x = 0; x < 16; ++x) {
-                            dgtab[(size_t)b * 16 + x] *= entry(b, x);
-                            put(last_dg + x, b, dgtab[(size_t)b * 16 + x]);
-                        }
+                    xidx[x] = idx;
+                }
+                const size_t bstep = g.bm > 1 ? (size_t)D : 0;
+                if (last_dg >= 0) {  // consecutive diagonal ops: one table (product kept in double, written once)
+                    for (int b = 0; b < nb; ++b) {
+                        const cd* e = g.m.data() + (size_t)b * bstep;
+                        cd* t = dgtab.data() + (size_t)b * 16;
+                        for (int x = 0; x < 16; ++x) t[x] *= e[xidx[x]];
+                    }
                     continue;
                 }
                 if (nmat + 16 > LP_MAT_ELEMS) return fail(TCB200_ERR_CAPACITY, "gate pass matrices exceed the parameter bank");
                 if (nc >= LP_MAX_CODES) return fail(TCB200_ERR_CAPACITY, "more than %d micro-ops in a round", LP_MAX_CODES);
-                for (int b = 0; b < nb; ++b)
-                    for (int x = 0; x < 16; ++x) {
-                        dgtab[(size_t)b * 16 + x] = entry(b, x);
-                        put(nmat + x, b, dgtab[(size_t)b * 16 + x]);
-                    }
+                for (int b = 0; b < nb; ++b) {
+                    const cd* e = g.m.data() + (size_t)b * bstep;
+                    cd* t = dgtab.data() + (size_t)b * 16;
+                    for (int x = 0; x < 16; ++x) t[x] = e[xidx[x]];
+                }
                 r.code[nc++] = LOP_DG | ((uint32_t)nmat << 8);
                 last_dg = nmat;
                 nmat += 16;
                 info.fma_per_amp += 4;
                 continue;
             }
-            last_dg = -1;
+            flush_dg();
             // dense: sort the positions ascending and permute the matrix index bits to match
             const int k = g.k, D = 1 << k;
             int srt[4];
@@ -414,15 +422,13 @@ struct Scheduler {
             };
             if (nmat + D * D > LP_MAT_ELEMS) return fail(TCB200_ERR_CAPACITY, "gate pass matrices exceed the parameter bank");
             if (nc >= LP_MAX_CODES) return fail(TCB200_ERR_CAPACITY, "more than %d micro-ops in a round", LP_MAX_CODES);
-            int rm[8];
+            int rm[8], smap[64];
             for (int i = 0; i < D; ++i) rm[i] = remap(i);
+            for (int i = 0; i < D; ++i)
+                for (int j = 0; j < D; ++j) smap[i * D + j] = 2 * (rm[i] * D + rm[j]);
             for (int b = 0; b < nb; ++b) {
                 const double* gm = g.src + (size_t)(g.bm > 1 ? b : 0) * 2 * D * D;
-                for (int i = 0; i < D; ++i)
-                    for (int j = 0; j < D; ++j) {
-                        const double* z = gm + 2 * (rm[i] * D + rm[j]);
-                        put(nmat + i * D + j, b, cd(z[0], z[1]));
-                    }
+                for (int e = 0; e < D * D; ++e) put(nmat + e, b, cd(gm[smap[e]], gm[smap[e] + 1]));
             }
             uint32_t opc = 0;
             const int p0 = pos[srt[0]], p1 = k > 1 ? pos[srt[1]] : 0, p2 = k > 2 ? pos[srt[2]] : 0;
@@ -439,6 +445,7 @@ struct Scheduler {
             nmat += D * D;
             info.fma_per_amp += (k == 1 && g.half) ? 4.0 : 4.0 * D;
         }
+        flush_dg();
         r.ncodes = (uint32_t)nc | (vec ? 0x100u : 0u);
         info.rounds++;
         return 0;
