@@ -192,9 +192,15 @@ int tcb200_apply_gate_pass(void* state, int nbits, int dtype, int nops, const in
  * The same gate pass for backend.vmap (tensorcircuit/backends/jax_backend.py:718-730): gate i
  * carries either one matrix shared by the batch (ops_batched[i] == 0) or one per batch element
  * (ops_batched[i] != 0: ops_mats holds [batch][4^k] for it).  Classification uses the union of
- * the non-zero patterns over the batch, so one schedule serves every element; batch element b
- * (grid.y) reads its own matrices from `workspace` (DEVICE, tcb200_gate_pass_batched_workspace_bytes),
- * which the call fills through pinned staging on `stream`.
+ * the non-zero patterns over the batch, so one schedule serves every element.  The per-element
+ * matrices travel through pinned staging into `workspace` (DEVICE,
+ * tcb200_gate_pass_batched_workspace_bytes) on `stream`; in the production shape the pass is then cut
+ * into chunks of as many batch elements as fit 60 KiB of matrices, each chunk is copied device to
+ * device into the library's __constant__ array and batch element b (grid.y) reads its matrices at a
+ * warp-uniform offset of the constant bank (uniform-register operands, like the unbatched kernel).
+ * The constant array is one per process: concurrent batched passes from several streams or host
+ * threads are serialised by the library.  TCB200_CBANK=0 (and states of one tile or less) read the
+ * matrices from `workspace` directly.
  */
 size_t tcb200_gate_pass_batched_workspace_bytes(int dtype, int64_t batch);
 int tcb200_apply_gate_pass_batched(void* state, int nbits, int dtype, int nops, const int* ops_k,

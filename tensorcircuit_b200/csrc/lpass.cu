@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <chrono>
 #include <complex>
+#include <mutex>
 #include <vector>
 
 #include "lpass.cuh"
@@ -1130,6 +1131,14 @@ static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, cons
             }
             const int64_t per = std::max<int64_t>(1, std::min<int64_t>(batch, (int64_t)(LP_CBANK_ELEMS / bstride)));
             C* state0 = q.state;
+            // the constant array is one per process: passes issued from different host threads / on different
+            // streams are serialised against each other (host mutex for the issue order, an event for the device)
+            static std::mutex cbank_mutex;
+            static cudaEvent_t cbank_done = nullptr;
+            static cudaStream_t cbank_stream = nullptr;
+            std::lock_guard<std::mutex> cbank_lock(cbank_mutex);
+            if (!cbank_done) TCB_CUDA(cudaEventCreateWithFlags(&cbank_done, cudaEventDisableTiming));
+            else if (cbank_stream != st) TCB_CUDA(cudaStreamWaitEvent(st, cbank_done, 0));
             // the whole blob goes to the device workspace in ONE host-to-device copy; the chunks then reach the
             // constant bank by device-to-device copies (no PCIe latency between two kernels of a pass)
             const size_t total_bytes = ((size_t)(batch - 1) * bstride) * sizeof(ME<Real>) + used;
@@ -1145,6 +1154,8 @@ static int launch_lpass(void* state, int nbits, int nops, const int* ops_k, cons
                 TCB_LAUNCH_CHECK("lpass_fast_cbank_kernel");
             }
             q.state = state0;
+            TCB_CUDA(cudaEventRecord(cbank_done, st));
+            cbank_stream = st;
             return 0;
         }
         // only the used prefix of every element's blob travels
