@@ -83,7 +83,7 @@ def _load() -> ctypes.CDLL:
         "tcb200_apply_pauli_sum_workspace_bytes": (c_size_t, [c_int]),
         "tcb200_apply_pauli_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_double), c_int64, c_void_p, c_size_t, c_void_p]),
         "tcb200_transition_local_max_ops": (c_int, []),
-        "tcb200_transition_local_workspace_bytes": (c_size_t, [c_int]),
+        "tcb200_transition_local_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
         "tcb200_transition_local": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_double), c_void_p, c_void_p, c_size_t, c_void_p]),
         "tcb200_sample": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_double, c_double, c_void_p, c_size_t, c_void_p]),
         "tcb200_sample_workspace_bytes": (c_size_t, [c_int]),

@@ -19,6 +19,8 @@
 //                        closed form of the rows of quantum.py:1461-1482)
 //   * transition_kernel: <bra| G_j |ket> for a list of local (<= 2-bit) operators G_j = dM_j/dtheta M_j^+,
 //                        every operator of a launch evaluated on the same pair of states.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -165,6 +167,10 @@ struct TransOp {
 };
 struct TransParams {
     int nbits, nops;
+    int first;    // this launch handles the operators first .. first + gridDim.y - 1
+    int pstride;  // partial-sum slots per operator
+    int pslot0;   // first slot of this launch
+    int pad;
     TransOp op[TR_MAX_OPS];
 };
 
@@ -172,7 +178,7 @@ template <typename C>
 __global__ void __launch_bounds__(256) transition_kernel(const C* __restrict__ bra, const C* __restrict__ ket,
                                                          const __grid_constant__ TransParams p, double* __restrict__ partials) {
     __shared__ double red[8][2];
-    const TransOp& op = p.op[blockIdx.y];
+    const TransOp& op = p.op[p.first + blockIdx.y];
     const int k = op.k, D = 1 << k;
     const uint64_t ngroups = 1ull << (p.nbits - k);
     double re = 0.0, im = 0.0;
@@ -223,11 +229,46 @@ __global__ void __launch_bounds__(256) transition_kernel(const C* __restrict__ b
             re += red[w][0];
             im += red[w][1];
         }
-        double* o = partials + ((uint64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
+        double* o = partials + ((uint64_t)(p.first + blockIdx.y) * p.pstride + p.pslot0 + blockIdx.x) * 2;
         o[0] = re;
         o[1] = im;
     }
 }
+
+// fixed-order sum of the partial slots of every operator; out index through a small map (the host sorts the
+// operators into chunk-local and far ones)
+struct TransFinalParams {
+    int nslots;
+    int map[TR_MAX_OPS];
+};
+__global__ void __launch_bounds__(COO_THREADS) trans_final_kernel(const double* __restrict__ partials, const __grid_constant__ TransFinalParams f,
+                                                                   double* __restrict__ out) {
+    __shared__ double red[COO_THREADS / 32][2];
+    const double* src = partials + (uint64_t)blockIdx.x * f.nslots * 2;
+    const int tid = threadIdx.x;
+    double re = 0.0, im = 0.0;
+    for (int c = tid; c < f.nslots; c += COO_THREADS) {
+        re += src[2 * c];
+        im += src[2 * c + 1];
+    }
+    re = sp_warp_sum(re);
+    im = sp_warp_sum(im);
+    if ((tid & 31) == 0) {
+        red[tid >> 5][0] = re;
+        red[tid >> 5][1] = im;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        re = im = 0.0;
+        for (int w = 0; w < COO_THREADS / 32; ++w) {
+            re += red[w][0];
+            im += red[w][1];
+        }
+        out[2 * f.map[blockIdx.x]] = re;
+        out[2 * f.map[blockIdx.x] + 1] = im;
+    }
+}
+
 
 }  // namespace tcb
 
@@ -306,7 +347,27 @@ int tcb200_apply_pauli_sum(const void* src, void* dst, int nbits, int dtype, int
 }
 
 int tcb200_transition_local_max_ops(void) { return TR_MAX_OPS; }
-size_t tcb200_transition_local_workspace_bytes(int nops) { return (size_t)(nops < 1 ? 1 : nops) * TR_CTAS * 2 * sizeof(double); }
+
+// Operators whose bits all lie below the chunk size are evaluated chunk by chunk: every launch covers one
+// L2-sized chunk of both states for ALL such operators, so the chunk comes from HBM once and the other
+// operators read it from L2 (one read of the two states for the whole group instead of one per operator).
+// Operators with a bit above the chunk size stream the whole states, one read each.
+static int trans_chunk_bits(int dtype) {
+    const char* e = getenv("TCB200_TRANS_CHUNK_BITS");  // tests force tiny chunks
+    if (e && e[0]) {
+        const int v = atoi(e);
+        if (v >= 2) return v;
+    }
+    return dtype == TCB200_C64 ? 22 : 21;  // 2 x 32 MiB of amplitudes per chunk: half of the 126 MB L2
+}
+static int trans_nchunks(int nbits, int dtype) {
+    const int cb = trans_chunk_bits(dtype);
+    return nbits >= cb + 2 ? 1 << (nbits - cb) : 1;
+}
+
+size_t tcb200_transition_local_workspace_bytes(int nops, int nbits, int dtype) {
+    return (size_t)(nops < 1 ? 1 : nops) * TR_CTAS * (size_t)trans_nchunks(nbits, dtype) * 2 * sizeof(double);
+}
 
 int tcb200_transition_local(const void* bra, const void* ket, int nbits, int dtype, int nops, const int* ops_k, const int* ops_bits,
                             const double* ops_mats, double* out_dev, void* workspace, size_t ws_bytes, void* stream) {
@@ -314,15 +375,20 @@ int tcb200_transition_local(const void* bra, const void* ket, int nbits, int dty
     if (dtype != TCB200_C64 && dtype != TCB200_C128) return fail(TCB200_ERR_ARG, "bad dtype %d", dtype);
     if (nbits < 1 || nbits > 40) return fail(TCB200_ERR_ARG, "nbits=%d out of range", nbits);
     if (nops < 1 || nops > TR_MAX_OPS) return fail(TCB200_ERR_ARG, "nops=%d out of range (max %d per call)", nops, TR_MAX_OPS);
-    if (!workspace || ws_bytes < tcb200_transition_local_workspace_bytes(nops))
-        return fail(TCB200_ERR_WORKSPACE, "transition_local needs %zu bytes of workspace", tcb200_transition_local_workspace_bytes(nops));
+    if (!workspace || ws_bytes < tcb200_transition_local_workspace_bytes(nops, nbits, dtype))
+        return fail(TCB200_ERR_WORKSPACE, "transition_local needs %zu bytes of workspace", tcb200_transition_local_workspace_bytes(nops, nbits, dtype));
     static thread_local TransParams* tp = nullptr;
     if (!tp) tp = new TransParams();
     TransParams& p = *tp;
-    p.nbits = nbits;
-    p.nops = nops;
+    TransFinalParams fin;
+    const int cb = trans_chunk_bits(dtype);
+    int nchunks = trans_nchunks(nbits, dtype);
+    // validate, then order the operators: chunk-local ones first
+    struct In { int k, b0, b1; const double* m; int idx; };
+    In in[TR_MAX_OPS];
     const int* b = ops_bits;
     const double* m = ops_mats;
+    int nlocal = 0;
     for (int o = 0; o < nops; ++o) {
         const int k = ops_k[o];
         if (k < 1 || k > 2) return fail(TCB200_ERR_UNSUPPORTED, "local operator of %d bits (max 2)", k);
@@ -331,24 +397,58 @@ int tcb200_transition_local(const void* bra, const void* ket, int nbits, int dty
             if (b[i] < 0 || b[i] >= nbits) return fail(TCB200_ERR_ARG, "bit %d out of range", b[i]);
             if (i > 0 && b[i] <= b[i - 1]) return fail(TCB200_ERR_ARG, "bits must be strictly ascending");
         }
-        p.op[o].k = k;
-        p.op[o].b0 = b[0];
-        p.op[o].b1 = k == 2 ? b[1] : 0;
-        const int D = 1 << k;
-        for (int i = 0; i < D * D; ++i) p.op[o].m[i] = make_double2(m[2 * i], m[2 * i + 1]);
+        in[o] = In{k, b[0], k == 2 ? b[1] : 0, m, o};
+        if (b[k - 1] < cb) ++nlocal;
         b += k;
-        m += 2 * D * D;
+        m += 2 * (1 << (2 * k));
+    }
+    if (nlocal < 2) nchunks = 1;  // nothing to share
+    int lo = 0, hi = nchunks > 1 ? nlocal : 0;
+    for (int o = 0; o < nops; ++o) {
+        const bool local = nchunks > 1 && (in[o].k == 2 ? in[o].b1 : in[o].b0) < cb;
+        const int at = nchunks > 1 ? (local ? lo++ : hi++) : o;
+        p.op[at].k = in[o].k;
+        p.op[at].b0 = in[o].b0;
+        p.op[at].b1 = in[o].b1;
+        const int D = 1 << in[o].k;
+        for (int i = 0; i < D * D; ++i) p.op[at].m[i] = make_double2(in[o].m[2 * i], in[o].m[2 * i + 1]);
+        fin.map[at] = in[o].idx;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double* partials = static_cast<double*>(workspace);
-    const dim3 grid(TR_CTAS, (unsigned)nops);
-    if (dtype == TCB200_C64)
-        transition_kernel<float2><<<grid, 256, 0, st>>>(static_cast<const float2*>(bra), static_cast<const float2*>(ket), p, partials);
-    else
-        transition_kernel<double2><<<grid, 256, 0, st>>>(static_cast<const double2*>(bra), static_cast<const double2*>(ket), p, partials);
-    TCB_LAUNCH_CHECK("transition_kernel");
-    coo_final_kernel<<<(unsigned)nops, COO_THREADS, 0, st>>>(partials, TR_CTAS, out_dev);
-    TCB_LAUNCH_CHECK("coo_final_kernel");
+    const int pstride = TR_CTAS * nchunks;
+    p.nops = nops;
+    p.pstride = pstride;
+    fin.nslots = pstride;
+    if (nchunks > 1) TCB_CUDA(cudaMemsetAsync(partials, 0, (size_t)nops * pstride * 2 * sizeof(double), st));
+    const size_t amp = dtype == TCB200_C64 ? 8 : 16;
+    auto launch = [&](int first, int count, int nb, size_t chunk, int slot0) {
+        p.nbits = nb;
+        p.first = first;
+        p.pslot0 = slot0;
+        const unsigned char* br = static_cast<const unsigned char*>(bra) + (chunk << nb) * amp;
+        const unsigned char* kt = static_cast<const unsigned char*>(ket) + (chunk << nb) * amp;
+        const dim3 grid(TR_CTAS, (unsigned)count);
+        if (dtype == TCB200_C64)
+            transition_kernel<float2><<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(br), reinterpret_cast<const float2*>(kt), p, partials);
+        else
+            transition_kernel<double2><<<grid, 256, 0, st>>>(reinterpret_cast<const double2*>(br), reinterpret_cast<const double2*>(kt), p, partials);
+    };
+    if (nchunks > 1) {
+        for (int c = 0; c < nchunks; ++c) {
+            launch(0, nlocal, cb, (size_t)c, c * TR_CTAS);
+            TCB_LAUNCH_CHECK("transition_kernel");
+        }
+        if (nops > nlocal) {
+            launch(nlocal, nops - nlocal, nbits, 0, 0);
+            TCB_LAUNCH_CHECK("transition_kernel");
+        }
+    } else {
+        launch(0, nops, nbits, 0, 0);
+        TCB_LAUNCH_CHECK("transition_kernel");
+    }
+    trans_final_kernel<<<(unsigned)nops, COO_THREADS, 0, st>>>(partials, fin, out_dev);
+    TCB_LAUNCH_CHECK("trans_final_kernel");
     return 0;
 }
 

@@ -512,7 +512,7 @@ class DeviceState:
         ks = np.asarray([1], dtype=np.int32)
         bits = np.asarray([0], dtype=np.int32)
         mats = np.ascontiguousarray(np.eye(2, dtype=np.complex128).reshape(-1))
-        ws = self._workspace(lib.tcb200_transition_local_workspace_bytes(1))
+        ws = self._workspace(lib.tcb200_transition_local_workspace_bytes(1, self.nbits, self.dt))
         out = torch.empty((1, 2), dtype=torch.float64, device=self.device)
         check(lib.tcb200_transition_local(_ptr(bra.buf[bra_row]), _ptr(self.buf[row]), self.nbits, self.dt, 1, _lib.iptr(ks), _lib.iptr(bits),
                                           _lib.dptr(mats.view(np.float64)), _ptr(out), _ptr(ws), ws.numel(), _stream()))
@@ -548,7 +548,7 @@ class DeviceState:
             ks = np.asarray([len(b) for b, _ in chunk], dtype=np.int32)
             bits = np.asarray([x for b, _ in chunk for x in b], dtype=np.int32)
             mats = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.complex128).reshape(-1) for _, m in chunk]))
-            ws = self._workspace(lib.tcb200_transition_local_workspace_bytes(len(chunk)))
+            ws = self._workspace(lib.tcb200_transition_local_workspace_bytes(len(chunk), self.nbits, self.dt))
             out = torch.empty((len(chunk), 2), dtype=torch.float64, device=self.device)
             check(lib.tcb200_transition_local(_ptr(self.buf[bra_row]), _ptr(self.buf[ket_row]), self.nbits, self.dt, len(chunk), _lib.iptr(ks),
                                               _lib.iptr(bits), _lib.dptr(mats.view(np.float64)), _ptr(out), _ptr(ws), ws.numel(), _stream()))
