@@ -17,6 +17,8 @@ from functools import partial, reduce
 from operator import mul
 from typing import Any, Callable, List, Optional, Sequence, Union
 
+import math
+
 import numpy as np
 import scipy.linalg
 
@@ -59,9 +61,12 @@ _toffoli_matrix = _bd(np.eye(4), _cnot_matrix)
 _fredkin_matrix = _bd(np.eye(4), _swap_matrix)
 
 
+_NLEGS = {1 << k: k for k in range(0, 41)}
+
+
 def _nlegs(size: int) -> int:
-    n = int(round(np.log2(size)))
-    if 2**n != size:
+    n = _NLEGS.get(int(size))  # (a table: this sits on the path of every recorded gate)
+    if n is None:
         raise ValueError("gate tensor size %d is not a power of two" % size)
     return n
 
@@ -306,6 +311,9 @@ def _cos_sin_batched(theta: Any, a: np.ndarray, b: np.ndarray) -> Any:
 
 
 def _rot(p: np.ndarray, theta: Any) -> Gate:
+    if type(theta) in _REAL_SCALARS:  # plain real angle: scalar math instead of 0-d array arithmetic
+        h = 0.5 * float(theta)
+        return Gate(math.cos(h) * _i_matrix - (1.0j * math.sin(h)) * p)
     theta = _s(theta)
     if is_batched(theta):
         g = Gate(_cos_sin_batched(theta / 2.0, _i_matrix, p))
@@ -386,9 +394,24 @@ def exponential_gate(unitary: Tensor = None, theta: float = None, name: str = "n
 exp_gate = exponential_gate
 
 
+_EYES: dict = {}
+_EXP1_CACHE: dict = {}
+_REAL_SCALARS = (float, int, np.float64, np.float32)
+
+
 def exponential_gate_unity(unitary: Tensor = None, theta: float = None, half: bool = False, name: str = "none", **kws: Any) -> Gate:
     kws = _alias_unitary(kws)
     unitary = kws.get("unitary", unitary)
+    if type(theta) in _REAL_SCALARS and isinstance(unitary, np.ndarray):
+        # plain real angle (the common case on the recording path): scalar math, cached generator
+        ent = _EXP1_CACHE.get(id(unitary))
+        if ent is None or ent[0] is not unitary:
+            um = np.asarray(unitary, dtype=CDT)
+            d = 2 ** (_nlegs(um.size) // 2)
+            ent = _EXP1_CACHE[id(unitary)] = (unitary, um.reshape(d, d), np.eye(d, dtype=CDT), [2] * _nlegs(um.size))
+        t = float(theta) * (0.5 if half is True else 1.0)
+        mat = math.cos(t) * ent[2] - (1.0j * math.sin(t)) * ent[1]
+        return Gate(mat.reshape(ent[3]), name="exp1-" + name)
     theta = _s(theta)
     u = np.asarray(unitary, dtype=CDT)
     n = _nlegs(u.size)
@@ -401,7 +424,10 @@ def exponential_gate_unity(unitary: Tensor = None, theta: float = None, half: bo
         g = Gate(mat.reshape([2] * n), name="exp1-" + name)
         g.kind = "diag" if not um[~np.eye(d, dtype=bool)].any() else "dense"
         return g
-    mat = np.cos(theta) * np.eye(d) - 1.0j * np.sin(theta) * u.reshape(d, d)
+    eye = _EYES.get(d)
+    if eye is None:
+        eye = _EYES.setdefault(d, np.eye(d))
+    mat = np.cos(theta) * eye - 1.0j * np.sin(theta) * u.reshape(d, d)
     return Gate(reshape2(mat), name="exp1-" + name)
 
 
