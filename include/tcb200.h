@@ -361,8 +361,10 @@ int tcb200_apply_pauli_sum(const void* src, void* dst, int nbits, int dtype, int
  * bit i of the operator, HOST arrays) between two device states, all in one launch.  In the adjoint
  * sweep G_j = dM_j/dtheta M_j^+, bra = lambda_j, ket = psi_j, and 2 Re of the result is the
  * derivative of the energy through gate j (jax_backend.py:668-776).  out_dev: DEVICE double [nops][2].
- * Operators whose bits all lie inside an L2-sized chunk (2^22 complex64 / 2^21 complex128 amplitudes) are
- * evaluated chunk by chunk, all of them per chunk: one HBM read of the two states for the whole group. */
+ * The operators are packed into groups of four amplitude-index bits; a thread loads the 16 + 16 amplitudes
+ * that differ in those bits once and evaluates every operator of the group from registers (one read of the
+ * two states per bit group instead of one per operator), and groups whose bits all lie inside an L2-sized
+ * chunk (2^22 complex64 / 2^21 complex128 amplitudes) are evaluated chunk by chunk. */
 int tcb200_transition_local_max_ops(void);
 size_t tcb200_transition_local_workspace_bytes(int nops, int nbits, int dtype);
 int tcb200_transition_local(const void* bra, const void* ket, int nbits, int dtype, int nops, const int* ops_k, const int* ops_bits,

@@ -235,6 +235,148 @@ __global__ void __launch_bounds__(256) transition_kernel(const C* __restrict__ b
     }
 }
 
+// ---- the same matrix elements, several operators per load ------------------------------------------
+// transition_kernel reads the two states once per operator.  Here the operators of a call are packed into
+// BIT GROUPS of four amplitude-index bits: a thread loads the 16 amplitudes of both states that differ in those
+// bits once and evaluates every operator of the group (1-bit operators on any of the four bits, 2-bit operators
+// on any pair of them) from registers -- one read of the two states per bit group instead of one per operator
+// (a layer of 28 single-qubit taps: 7 reads instead of 28).  Products in the state's precision, accumulation in
+// float64 per thread (shared-memory slots, no atomics), fixed-order reductions.
+constexpr int TT_MAX_GROUPS = 16;  // bit groups per launch (kernel-parameter bank)
+constexpr int TT_MAX_OPS = 6;      // operators per bit group
+
+struct TTOp {
+    int kind;  // 0..3: 1-bit operator on group position p; 4..9: 2-bit operator on positions (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
+    int out;   // index of the operator in the caller's list
+    int pad[2];
+    double2 m[16];
+};
+struct TTGroup {
+    int bit[4];  // ascending amplitude-index bits of the group
+    int nops;
+    int pad[3];
+    TTOp op[TT_MAX_OPS];
+};
+struct TTParams {
+    int nbits, ngroups, pstride, pslot0;
+    TTGroup g[TT_MAX_GROUPS];
+};
+
+template <typename C, typename R, int P0>
+__device__ __forceinline__ void tt_one(const C* ps, const C* lm, const double2* m, double& cr, double& ci) {
+    const R m00r = (R)m[0].x, m00i = (R)m[0].y, m01r = (R)m[1].x, m01i = (R)m[1].y;
+    const R m10r = (R)m[2].x, m10i = (R)m[2].y, m11r = (R)m[3].x, m11i = (R)m[3].y;
+    R ar = 0, ai = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int lo = r & ((1 << P0) - 1);
+        const int i0 = ((r >> P0) << (P0 + 1)) | lo, i1 = i0 | (1 << P0);
+        const R t0r = m00r * ps[i0].x - m00i * ps[i0].y + m01r * ps[i1].x - m01i * ps[i1].y;
+        const R t0i = m00r * ps[i0].y + m00i * ps[i0].x + m01r * ps[i1].y + m01i * ps[i1].x;
+        const R t1r = m10r * ps[i0].x - m10i * ps[i0].y + m11r * ps[i1].x - m11i * ps[i1].y;
+        const R t1i = m10r * ps[i0].y + m10i * ps[i0].x + m11r * ps[i1].y + m11i * ps[i1].x;
+        ar += lm[i0].x * t0r + lm[i0].y * t0i + lm[i1].x * t1r + lm[i1].y * t1i;
+        ai += lm[i0].x * t0i - lm[i0].y * t0r + lm[i1].x * t1i - lm[i1].y * t1r;
+    }
+    cr = (double)ar;
+    ci = (double)ai;
+}
+
+template <typename C, typename R, int P0, int P1>
+__device__ __forceinline__ void tt_two(const C* ps, const C* lm, const double2* m, double& cr, double& ci) {
+    R ar = 0, ai = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int base = 0, rb = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (b != P0 && b != P1) {
+                base |= ((r >> rb) & 1) << b;
+                ++rb;
+            }
+        const int idx[4] = {base, base | (1 << P0), base | (1 << P1), base | (1 << P0) | (1 << P1)};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            R tr = 0, ti = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const R mr = (R)m[a * 4 + b].x, mi = (R)m[a * 4 + b].y;
+                tr += mr * ps[idx[b]].x - mi * ps[idx[b]].y;
+                ti += mr * ps[idx[b]].y + mi * ps[idx[b]].x;
+            }
+            ar += lm[idx[a]].x * tr + lm[idx[a]].y * ti;
+            ai += lm[idx[a]].x * ti - lm[idx[a]].y * tr;
+        }
+    }
+    cr = (double)ar;
+    ci = (double)ai;
+}
+
+template <typename C, typename R>
+__global__ void __launch_bounds__(256) transition_tile_kernel(const C* __restrict__ bra, const C* __restrict__ ket,
+                                                              const __grid_constant__ TTParams p, double* __restrict__ partials) {
+    __shared__ double sacc[TT_MAX_OPS][256][2];
+    __shared__ double red[8][2];
+    const TTGroup& G = p.g[blockIdx.y];
+    const int tid = threadIdx.x;
+    for (int o = 0; o < TT_MAX_OPS; ++o) sacc[o][tid][0] = sacc[o][tid][1] = 0.0;
+    const int b0 = G.bit[0], b1 = G.bit[1], b2 = G.bit[2], b3 = G.bit[3];
+    const uint64_t ngi = 1ull << (p.nbits - 4);
+    for (uint64_t gi = (uint64_t)blockIdx.x * 256 + tid; gi < ngi; gi += (uint64_t)gridDim.x * 256) {
+        uint64_t base = ((gi >> b0) << (b0 + 1)) | (gi & ((1ull << b0) - 1ull));
+        base = ((base >> b1) << (b1 + 1)) | (base & ((1ull << b1) - 1ull));
+        base = ((base >> b2) << (b2 + 1)) | (base & ((1ull << b2) - 1ull));
+        base = ((base >> b3) << (b3 + 1)) | (base & ((1ull << b3) - 1ull));
+        C ps[16], lm[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const uint64_t idx = base | ((uint64_t)(t & 1) << b0) | ((uint64_t)((t >> 1) & 1) << b1) | ((uint64_t)((t >> 2) & 1) << b2) |
+                                 ((uint64_t)((t >> 3) & 1) << b3);
+            ps[t] = ket[idx];
+            lm[t] = bra[idx];
+        }
+#pragma unroll 1
+        for (int o = 0; o < G.nops; ++o) {
+            const double2* m = G.op[o].m;
+            double cr = 0.0, ci = 0.0;
+            switch (G.op[o].kind) {
+                case 0: tt_one<C, R, 0>(ps, lm, m, cr, ci); break;
+                case 1: tt_one<C, R, 1>(ps, lm, m, cr, ci); break;
+                case 2: tt_one<C, R, 2>(ps, lm, m, cr, ci); break;
+                case 3: tt_one<C, R, 3>(ps, lm, m, cr, ci); break;
+                case 4: tt_two<C, R, 0, 1>(ps, lm, m, cr, ci); break;
+                case 5: tt_two<C, R, 0, 2>(ps, lm, m, cr, ci); break;
+                case 6: tt_two<C, R, 0, 3>(ps, lm, m, cr, ci); break;
+                case 7: tt_two<C, R, 1, 2>(ps, lm, m, cr, ci); break;
+                case 8: tt_two<C, R, 1, 3>(ps, lm, m, cr, ci); break;
+                default: tt_two<C, R, 2, 3>(ps, lm, m, cr, ci); break;
+            }
+            sacc[o][tid][0] += cr;
+            sacc[o][tid][1] += ci;
+        }
+    }
+    for (int o = 0; o < G.nops; ++o) {
+        double re = sp_warp_sum(sacc[o][tid][0]);
+        double im = sp_warp_sum(sacc[o][tid][1]);
+        __syncthreads();
+        if ((tid & 31) == 0) {
+            red[tid >> 5][0] = re;
+            red[tid >> 5][1] = im;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            re = im = 0.0;
+            for (int w = 0; w < 8; ++w) {
+                re += red[w][0];
+                im += red[w][1];
+            }
+            double* out = partials + ((uint64_t)G.op[o].out * p.pstride + p.pslot0 + blockIdx.x) * 2;
+            out[0] = re;
+            out[1] = im;
+        }
+    }
+}
+
 // fixed-order sum of the partial slots of every operator; out index through a small map (the host sorts the
 // operators into chunk-local and far ones)
 struct TransFinalParams {
@@ -401,6 +543,123 @@ int tcb200_transition_local(const void* bra, const void* ket, int nbits, int dty
         if (b[k - 1] < cb) ++nlocal;
         b += k;
         m += 2 * (1 << (2 * k));
+    }
+    {
+        const char* e = getenv("TCB200_TRANS_TILE");  // =0: one read of the states per operator (transition_kernel)
+        if (nbits >= 4 && !(e && e[0] == '0')) {
+            // ---- bit groups: operators sharing <= 4 bits are evaluated from one load of 16 + 16 amplitudes ----
+            struct Grp { int bits[4]; int nb; int ops[TT_MAX_OPS]; int nops; };
+            std::vector<Grp> grps;
+            std::vector<int> order(nops);
+            for (int o = 0; o < nops; ++o) order[o] = o;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return in[a].b0 < in[c].b0; });
+            for (int oi : order) {
+                const In& op = in[oi];
+                const int ob[2] = {op.b0, op.b1};
+                int placed = -1;
+                for (int gi = (int)grps.size() - 1; gi >= 0 && gi >= (int)grps.size() - 4 && placed < 0; --gi) {
+                    Grp& g = grps[gi];
+                    if (g.nops >= TT_MAX_OPS) continue;
+                    int add = 0;
+                    for (int i = 0; i < op.k; ++i) {
+                        bool have = false;
+                        for (int j = 0; j < g.nb; ++j) have = have || g.bits[j] == ob[i];
+                        if (!have) ++add;
+                    }
+                    if (g.nb + add > 4) continue;
+                    for (int i = 0; i < op.k; ++i) {
+                        bool have = false;
+                        for (int j = 0; j < g.nb; ++j) have = have || g.bits[j] == ob[i];
+                        if (!have) g.bits[g.nb++] = ob[i];
+                    }
+                    g.ops[g.nops++] = oi;
+                    placed = gi;
+                }
+                if (placed < 0) {
+                    Grp g;
+                    g.nb = 0;
+                    g.nops = 0;
+                    for (int i = 0; i < op.k; ++i) g.bits[g.nb++] = ob[i];
+                    g.ops[g.nops++] = oi;
+                    grps.push_back(g);
+                }
+            }
+            static thread_local TTParams* ttp = nullptr;
+            if (!ttp) ttp = new TTParams();
+            TTParams& q = *ttp;
+            const size_t amp = dtype == TCB200_C64 ? 8 : 16;
+            std::vector<int> local_ids, far_ids;
+            for (size_t gi = 0; gi < grps.size(); ++gi) {
+                Grp& g = grps[gi];
+                for (int cand = 0; g.nb < 4; ++cand) {  // pad with the lowest free bits: the tile is always 16 amplitudes
+                    bool have = false;
+                    for (int j = 0; j < g.nb; ++j) have = have || g.bits[j] == cand;
+                    if (!have) g.bits[g.nb++] = cand;
+                }
+                std::sort(g.bits, g.bits + 4);
+                (nchunks > 1 && g.bits[3] < cb ? local_ids : far_ids).push_back((int)gi);
+            }
+            if (local_ids.size() < 2) {  // nothing to share inside a chunk
+                far_ids.insert(far_ids.end(), local_ids.begin(), local_ids.end());
+                local_ids.clear();
+                nchunks = 1;
+            }
+            cudaStream_t st = static_cast<cudaStream_t>(stream);
+            double* partials = static_cast<double*>(workspace);
+            const int pstride = TR_CTAS * nchunks;
+            if (nchunks > 1) TCB_CUDA(cudaMemsetAsync(partials, 0, (size_t)nops * pstride * 2 * sizeof(double), st));
+            static const int pair_index[4][4] = {{-1, 4, 5, 6}, {-1, -1, 7, 8}, {-1, -1, -1, 9}, {-1, -1, -1, -1}};
+            auto fill = [&](const std::vector<int>& ids, size_t from, int count) {
+                q.ngroups = count;
+                for (int c = 0; c < count; ++c) {
+                    const Grp& g = grps[ids[from + c]];
+                    TTGroup& tg = q.g[c];
+                    for (int j = 0; j < 4; ++j) tg.bit[j] = g.bits[j];
+                    tg.nops = g.nops;
+                    for (int o = 0; o < g.nops; ++o) {
+                        const In& op = in[g.ops[o]];
+                        int pos[2] = {0, 0};
+                        const int ob[2] = {op.b0, op.b1};
+                        for (int i = 0; i < op.k; ++i)
+                            for (int j = 0; j < 4; ++j)
+                                if (g.bits[j] == ob[i]) pos[i] = j;
+                        tg.op[o].kind = op.k == 1 ? pos[0] : pair_index[pos[0]][pos[1]];
+                        tg.op[o].out = op.idx;
+                        const int D = 1 << op.k;
+                        for (int i = 0; i < D * D; ++i) tg.op[o].m[i] = make_double2(op.m[2 * i], op.m[2 * i + 1]);
+                    }
+                }
+            };
+            auto launch_tiles = [&](int nb, size_t chunk, int slot0) {
+                q.nbits = nb;
+                q.pstride = pstride;
+                q.pslot0 = slot0;
+                const unsigned char* br = static_cast<const unsigned char*>(bra) + (chunk << nb) * amp;
+                const unsigned char* kt = static_cast<const unsigned char*>(ket) + (chunk << nb) * amp;
+                const dim3 grid(TR_CTAS, (unsigned)q.ngroups);
+                if (dtype == TCB200_C64)
+                    transition_tile_kernel<float2, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(br), reinterpret_cast<const float2*>(kt), q, partials);
+                else
+                    transition_tile_kernel<double2, double><<<grid, 256, 0, st>>>(reinterpret_cast<const double2*>(br), reinterpret_cast<const double2*>(kt), q, partials);
+            };
+            for (size_t from = 0; from < local_ids.size(); from += TT_MAX_GROUPS) {
+                fill(local_ids, from, (int)std::min<size_t>(TT_MAX_GROUPS, local_ids.size() - from));
+                for (int c = 0; c < nchunks; ++c) {
+                    launch_tiles(cb, (size_t)c, c * TR_CTAS);
+                    TCB_LAUNCH_CHECK("transition_tile_kernel");
+                }
+            }
+            for (size_t from = 0; from < far_ids.size(); from += TT_MAX_GROUPS) {
+                fill(far_ids, from, (int)std::min<size_t>(TT_MAX_GROUPS, far_ids.size() - from));
+                launch_tiles(nbits, 0, 0);
+                TCB_LAUNCH_CHECK("transition_tile_kernel");
+            }
+            fin.nslots = pstride;
+            for (int o = 0; o < nops; ++o) fin.map[o] = o;
+            trans_final_kernel<<<(unsigned)nops, COO_THREADS, 0, st>>>(partials, fin, out_dev);
+            TCB_LAUNCH_CHECK("trans_final_kernel");
+            return 0;
+        }
     }
     if (nlocal < 2) nchunks = 1;  // nothing to share
     int lo = 0, hi = nchunks > 1 ? nlocal : 0;
