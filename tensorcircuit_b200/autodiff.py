@@ -370,15 +370,20 @@ def value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0
         # 3. per parameter: direct dependence of the host arithmetic + the gates it moves
         dtype = _circuit.cons.dtypestr
         grads = []
-        for i in nums:
+        # queries asked of the same circuit prefix (a loop of expectation_ps calls) form one group
+        groups: Dict[Any, List[int]] = {}
+        for qi, qb in enumerate(base.queries):
+            groups.setdefault(qb.key, []).append(qi)
+        leader = {qi: members[0] for members in groups.values() for qi in members}
+        # the derivative-carrying gates of ALL differentiated arguments go through one sweep per circuit:
+        # per group leader (argument position, parameter k, gate j, D)
+        all_pending: List[List[Tuple[int, int, int, np.ndarray]]] = [[] for _ in base.queries]
+        gflat: List[np.ndarray] = []
+        for pos, i in enumerate(nums):
             theta = args[i]
             g = np.zeros(theta.size)
+            gflat.append(g)
             flat = theta.reshape(-1)
-            # queries asked of the same circuit prefix (a loop of expectation_ps calls) form one group
-            groups: Dict[Any, List[int]] = {}
-            for qi, qb in enumerate(base.queries):
-                groups.setdefault(qb.key, []).append(qi)
-            leader = {qi: members[0] for members in groups.values() for qi in members}
             pending: List[List[Tuple[int, int, np.ndarray]]] = [[] for _ in base.queries]  # per group leader: (k, gate j, D)
             swept = False
             try:  # all 2P nudged recordings in ONE host pass, the way vmap runs a batch of parameters
@@ -435,25 +440,29 @@ def value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0
                         if np.abs(D).max() > 1e-12:
                             pending[qi].append((k, j, D))
             for qi, lst in enumerate(pending):
-                if not lst:
-                    continue
-                members = groups[base.queries[qi].key]
-                merged = _Query.__new__(_Query)  # all terms of the group in one batched evaluation
-                merged.nqubits, merged.ops = base.queries[qi].nqubits, base.queries[qi].ops
-                merged.fl = [x for m in members for x in base.queries[m].fl]
-                merged.sg = [x for m in members for x in base.queries[m].sg]
-                merged.ny = [x for m in members for x in base.queries[m].ny]
-                wts = np.concatenate([dl_de[m] for m in members])
-                merged.circ, merged.ny = base.queries[qi].circ, list(merged.ny)
-                contrib = _adjoint_contrib(merged, wts, lst, dtype) if _ADJOINT else None
-                if contrib is None:
-                    ADJOINT_STATS["fallbacks"] += 1
-                    diff = _shift_batch(merged, merged, [(j, D) for _, j, D in lst], dtype)  # [nshift, nterms]
-                    de = 0.5 * np.real(diff)  # d E_t / d theta through that gate
-                    contrib = de @ wts
-                for (k, _, _), c in zip(lst, contrib):
-                    g[k] += c
-            grads.append(g.reshape(theta.shape))
+                all_pending[qi].extend((pos, k, j, D) for k, j, D in lst)
+        for qi, lst4 in enumerate(all_pending):
+            if not lst4:
+                continue
+            lst = [(k, j, D) for _, k, j, D in lst4]
+            members = groups[base.queries[qi].key]
+            merged = _Query.__new__(_Query)  # all terms of the group in one batched evaluation
+            merged.nqubits, merged.ops = base.queries[qi].nqubits, base.queries[qi].ops
+            merged.fl = [x for m in members for x in base.queries[m].fl]
+            merged.sg = [x for m in members for x in base.queries[m].sg]
+            merged.ny = [x for m in members for x in base.queries[m].ny]
+            wts = np.concatenate([dl_de[m] for m in members])
+            merged.circ, merged.ny = base.queries[qi].circ, list(merged.ny)
+            contrib = _adjoint_contrib(merged, wts, lst, dtype) if _ADJOINT else None
+            if contrib is None:
+                ADJOINT_STATS["fallbacks"] += 1
+                diff = _shift_batch(merged, merged, [(j, D) for _, j, D in lst], dtype)  # [nshift, nterms]
+                de = 0.5 * np.real(diff)  # d E_t / d theta through that gate
+                contrib = de @ wts
+            for (pos, k, _, _), c in zip(lst4, contrib):
+                gflat[pos][k] += c
+        for pos, i in enumerate(nums):
+            grads.append(gflat[pos].reshape(np.shape(args[i])))
         gr: Any = grads[0] if single else tuple(grads)
         val: Any = np.asarray(value)
         return ((val, aux), gr) if has_aux else (val, gr)
