@@ -567,6 +567,19 @@ class Circuit:
             for q, p in d.items():
                 ps[q] = p
             pss.append(ps)
+        st = self._ensure_state()  # (a state hook may turn the circuit into a batched one: autodiff replays)
+        if self._batch is None and self.lazy_expectation:
+            # the other reference idiom for an energy -- a loop over c.expectation((gates.x(), [i])) ... ,
+            # benchmarks/scripts/vqe_tc.py:74-81 -- joins the same pool of pending terms as expectation_ps: all
+            # calls on one state are evaluated as one launch group when a value is read
+            if self._pool is None:
+                self._pool = TermPool(self)
+            lterms = []
+            for (c, _), ps in zip(terms, pss):
+                d = ps2xyz(ps)
+                fl, sg, ny = self._pauli_masks(d["x"], d["y"], d["z"])
+                lterms.append((self._pool, self._pool.add(fl, sg, ny), complex(c)))
+            return LazyScalar(lterms, 0j, "c", self._dtype)
         vals = self.expectation_ps_many(pss)
         tot: Any = 0.0
         for i, (c, _) in enumerate(terms):

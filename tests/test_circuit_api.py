@@ -1287,3 +1287,45 @@ def test_expectation_ps_loop_is_coalesced(eng):
     assert isinstance(v, np.ndarray)
     np.testing.assert_allclose(v, o.expectation_ps(x=[1], z=[2]), atol=2e-5)
     np.testing.assert_allclose(build(tc.Circuit).expectation_ps(x=[1], z=[2]), v, atol=1e-7)
+
+
+def test_expectation_loop_is_coalesced(eng):
+    """The benchmark scripts' idiom -- a loop over c.expectation((gates.x(), [i])) and two-operator calls
+    (benchmarks/scripts/vqe_tc.py:74-81, ``tfi_energy``) -- joins the same pool of pending terms as expectation_ps:
+    one launch group when the energy is read."""
+    K = tc.backend
+    n = 7
+    th = np.random.default_rng(5).uniform(0, 2 * np.pi, size=(2, n))
+
+    def build(cls):
+        c = cls(n)
+        for i in range(n):
+            c.ry(i, theta=th[0, i])
+        for i in range(n - 1):
+            c.cnot(i, i + 1)
+        for i in range(n):
+            c.rx(i, theta=th[1, i])
+        return c
+
+    def tfi_energy(c, j=1.0, h=-1.0):  # body of vqe_tc.py:74-81
+        e = 0.0
+        for i in range(n):
+            e += h * c.expectation((tc.gates.x(), [i]))
+        for i in range(n - 1):
+            e += j * c.expectation((tc.gates.z(), [i]), (tc.gates.z(), [(i + 1) % n]))
+        return e
+
+    c = build(tc.Circuit)
+    st = c._ensure_state()
+    calls = []
+    orig = st.expectation_terms
+    st.expectation_terms = lambda fl, sg, ny: (calls.append(len(fl)), orig(fl, sg, ny))[1]
+    e = K.real(tfi_energy(c))
+    assert calls == []
+    o = build(OracleCircuit)
+    want = sum(-o.expectation_ps(x=[i]).real for i in range(n)) + sum(o.expectation_ps(z=[i, i + 1]).real for i in range(n - 1))
+    np.testing.assert_allclose(float(e), want, atol=2e-5)
+    assert calls == [2 * n - 1]
+    # a non-Pauli operator (a projector: two Pauli terms) goes through the same pool
+    p0 = tc.gates.Gate(np.array([[1.0, 0.0], [0.0, 0.0]]))
+    np.testing.assert_allclose(float(np.real(c.expectation((p0, [2])))), 0.5 * (1 + o.expectation_ps(z=[2]).real), atol=2e-5)
