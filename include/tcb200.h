@@ -356,6 +356,14 @@ size_t tcb200_apply_pauli_sum_workspace_bytes(int nterms);
 int tcb200_apply_pauli_sum(const void* src, void* dst, int nbits, int dtype, int nterms, const uint64_t* flip, const uint64_t* sign,
                            const double* coef, int64_t batch, void* workspace, size_t ws_bytes, void* stream);
 
+/* dst = coef * H src  (accumulate == 0)  or  dst += coef * H src  for a sparse operator in CSR form on the DEVICE
+ * (indptr: int64 [2^nbits + 1], indices: int64 [nnz], vals: complex128 [nnz]); one thread per row, the entries of a
+ * row are summed in storage order.  This is lambda = H psi for a generic sparse Hamiltonian -- the seed of the
+ * adjoint sweep when the loss goes through templates/measurements.py:173-188 (sparse_expectation) instead of Pauli
+ * strings.  src and dst are distinct device buffers of one state each. */
+int tcb200_csr_matvec(const void* src, void* dst, int nbits, int dtype, const int64_t* indptr_dev, const int64_t* indices_dev,
+                      const void* vals_dev, double coef_re, double coef_im, int accumulate, void* stream);
+
 /* <bra| G_j |ket> for up to tcb200_transition_local_max_ops() local operators G_j (1 or 2 bits each;
  * ops_bits ascending amplitude-index bits, ops_mats row-major complex128 with matrix index bit i <->
  * bit i of the operator, HOST arrays) between two device states, all in one launch.  In the adjoint

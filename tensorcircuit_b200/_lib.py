@@ -82,6 +82,7 @@ def _load() -> ctypes.CDLL:
         "tcb200_coo_expectation": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
         "tcb200_apply_pauli_sum_workspace_bytes": (c_size_t, [c_int]),
         "tcb200_apply_pauli_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_double), c_int64, c_void_p, c_size_t, c_void_p]),
+        "tcb200_csr_matvec": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_void_p]),
         "tcb200_transition_local_max_ops": (c_int, []),
         "tcb200_transition_local_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
         "tcb200_transition_local": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_double), c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -106,7 +107,7 @@ EXPORTS = [
     "tcb200_expect_single_flip_max_terms", "tcb200_expect_single_flip_workspace_bytes", "tcb200_expect_single_flip", "tcb200_expect_z_max_terms", "tcb200_expect_z_min_bits", "tcb200_expect_z_workspace_bytes", "tcb200_expect_z", "tcb200_sample",
     "tcb200_sample_workspace_bytes", "tcb200_run_circuit_host",
     "tcb200_coo_expectation_workspace_bytes", "tcb200_coo_expectation", "tcb200_apply_pauli_sum_workspace_bytes", "tcb200_apply_pauli_sum",
-    "tcb200_transition_local_max_ops", "tcb200_transition_local_workspace_bytes", "tcb200_transition_local",
+    "tcb200_transition_local_max_ops", "tcb200_transition_local_workspace_bytes", "tcb200_transition_local", "tcb200_csr_matvec",
 ]
 
 

@@ -65,7 +65,12 @@ class _Query:
                 h.update(np.ascontiguousarray(M).tobytes())
             self.key = (self.nqubits, len(self.ops), h.digest())
         self.fl, self.sg, self.ny = list(fl), list(sg), list(ny)
+        self.coo: Any = None  # a device-resident sparse operator instead of Pauli strings (one value)
         self.values: Optional[np.ndarray] = None  # complex [nterms]
+
+    @property
+    def nterms(self) -> int:
+        return 1 if self.coo is not None else len(self.fl)
 
 
 class _Trace:
@@ -104,6 +109,20 @@ class _RecordingState:
         return r
 
 
+def _record_coo(self: Any, op: Any) -> np.ndarray:
+    r = self._real.coo_expectation(op)
+    if self._real.batch != 1:
+        raise NotImplementedError("value_and_grad of a function that vmaps internally")
+    q = _Query(self._circ, [], [], [])
+    q.coo = op  # (same key as the Pauli queries on this circuit: they share one sweep)
+    q.values = np.array([r[0]], dtype=np.complex128)
+    self._trace.queries.append(q)
+    return r
+
+
+_RecordingState.coo_expectation = _record_coo  # type: ignore[attr-defined]
+
+
 class _ReplayState:
     """No device at all: gates are only recorded by the Circuit, queries return stored values
     (tiled over the batch when the recording runs on a batch of nudged parameters)."""
@@ -131,6 +150,16 @@ class _ReplayState:
             raise RuntimeError("value_and_grad: the structure of the function changed between evaluations")
         v = np.asarray(self._trace.replay[i], dtype=np.complex128)
         return v if v.ndim == 2 else np.tile(v[None, :], (self.batch, 1))
+
+    def coo_expectation(self, op: Any) -> np.ndarray:
+        i = len(self._trace.queries)
+        q = _Query(self._circ, [], [], [], need_key=False)
+        q.coo = op
+        self._trace.queries.append(q)
+        if self._trace.replay is None or i >= len(self._trace.replay) or np.shape(self._trace.replay[i])[-1] != 1:
+            raise RuntimeError("value_and_grad: the structure of the function changed between evaluations")
+        v = np.asarray(self._trace.replay[i], dtype=np.complex128)
+        return v[:, 0] if v.ndim == 2 else np.tile(v[None, :], (self.batch, 1))[:, 0]
 
     def __getattr__(self, name: str) -> Any:
         raise NotImplementedError("value_and_grad: %s() is not differentiable (only expectation values are)" % name)
@@ -255,9 +284,17 @@ def _adjoint_contrib(q: _Query, weights: np.ndarray, lst: List[Tuple[int, int, n
     st2.copy_row_from(0, src, 0)
     coef = [w * (-1j) ** (int(y) & 3) for w, y in zip(weights, q.ny)]
     keep = [t for t in range(len(coef)) if coef[t] != 0]
-    if not keep:
+    coos = [(op, w) for op, w in getattr(q, "coos", []) if w != 0]
+    if not keep and not coos:
         return np.zeros(len(lst))
-    st2.apply_pauli_sum_rows(0, 1, [q.fl[t] for t in keep], [q.sg[t] for t in keep], [coef[t] for t in keep])
+    for op, _ in coos:
+        op.csr()
+        if not getattr(op, "hermitian", True):
+            return None  # 2 Re <H psi| d psi> is the derivative only for a Hermitian H
+    if keep:
+        st2.apply_pauli_sum_rows(0, 1, [q.fl[t] for t in keep], [q.sg[t] for t in keep], [coef[t] for t in keep])
+    for ci, (op, w) in enumerate(coos):  # lambda += w H psi, row by row of the CSR form
+        st2.apply_csr_rows(0, 1, op, coef=w, accumulate=bool(keep) or ci > 0)
     out = np.zeros(len(lst))
     pending_undo: List[Tuple[Tuple[int, ...], np.ndarray]] = []
     on_qubit: Dict[int, List[int]] = {}  # qubit -> indices into pending_undo (only those can fail to commute with a tap)
@@ -448,13 +485,19 @@ def value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0
             members = groups[base.queries[qi].key]
             merged = _Query.__new__(_Query)  # all terms of the group in one batched evaluation
             merged.nqubits, merged.ops = base.queries[qi].nqubits, base.queries[qi].ops
-            merged.fl = [x for m in members for x in base.queries[m].fl]
-            merged.sg = [x for m in members for x in base.queries[m].sg]
-            merged.ny = [x for m in members for x in base.queries[m].ny]
-            wts = np.concatenate([dl_de[m] for m in members])
+            pauli = [m for m in members if base.queries[m].coo is None]
+            merged.fl = [x for m in pauli for x in base.queries[m].fl]
+            merged.sg = [x for m in pauli for x in base.queries[m].sg]
+            merged.ny = [x for m in pauli for x in base.queries[m].ny]
+            wts = np.concatenate([dl_de[m] for m in pauli]) if pauli else np.zeros(0)
+            # sparse-operator queries of the group: (operator, d loss / d value)
+            merged.coos = [(base.queries[m].coo, float(dl_de[m][0])) for m in members if base.queries[m].coo is not None]
             merged.circ, merged.ny = base.queries[qi].circ, list(merged.ny)
             contrib = _adjoint_contrib(merged, wts, lst, dtype) if _ADJOINT else None
             if contrib is None:
+                if merged.coos:
+                    raise NotImplementedError("value_and_grad through a sparse-matrix Hamiltonian needs the adjoint sweep: unitary gates, "
+                                              "derivative-carrying gates on <= 2 qubits, a Hermitian operator")
                 ADJOINT_STATS["fallbacks"] += 1
                 diff = _shift_batch(merged, merged, [(j, D) for _, j, D in lst], dtype)  # [nshift, nterms]
                 de = 0.5 * np.real(diff)  # d E_t / d theta through that gate

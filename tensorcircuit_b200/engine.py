@@ -131,6 +131,21 @@ class DeviceCOO:
         self.cols = torch.from_numpy(c).to(dev)
         self.vals = torch.from_numpy(v).to(dev)
 
+    def csr(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """(indptr, indices, values) of the same operator in CSR form on the device, built once (host sort of the
+        stored elements): what ``lambda = H psi`` of the adjoint sweep walks row by row"""
+        if getattr(self, "_csr", None) is None:
+            import scipy.sparse as sp
+
+            m = sp.coo_matrix((self.vals.cpu().numpy(), (self.rows.cpu().numpy(), self.cols.cpu().numpy())), shape=self.shape).tocsr()
+            m.sum_duplicates()
+            herm = abs(m - m.getH())
+            self.hermitian = bool(herm.nnz == 0 or herm.max() <= 1e-10 * max(1.0, abs(m).max()))
+            dev = self.rows.device
+            self._csr = (torch.from_numpy(m.indptr.astype(np.int64)).to(dev), torch.from_numpy(m.indices.astype(np.int64)).to(dev),
+                         torch.from_numpy(m.data.astype(np.complex128)).to(dev))
+        return self._csr
+
     @classmethod
     def from_scipy(cls, m: Any, device: Any = None) -> "DeviceCOO":
         m = m.tocoo()
@@ -536,6 +551,17 @@ class DeviceState:
         ws = self._workspace(lib.tcb200_apply_pauli_sum_workspace_bytes(nt))
         check(lib.tcb200_apply_pauli_sum(_ptr(self.buf[src_row]), _ptr(self.buf[dst_row]), self.nbits, self.dt, nt, _lib.u64ptr(f), _lib.u64ptr(g),
                                          _lib.dptr(c.view(np.float64)), 1, _ptr(ws), ws.numel(), _stream()))
+        STATS["apply_launches"] += 1
+
+    def apply_csr_rows(self, src_row: int, dst_row: int, op: "DeviceCOO", coef: complex = 1.0, accumulate: bool = False) -> None:
+        """self[dst_row] (+)= coef * H self[src_row] for a device-resident sparse operator"""
+        assert src_row != dst_row
+        if op.dim != 1 << self.nbits:
+            raise ValueError("operator of dimension %d on a state of %d qubits" % (op.dim, self.nbits))
+        indptr, indices, vals = op.csr()
+        c = complex(coef)
+        check(lib.tcb200_csr_matvec(_ptr(self.buf[src_row]), _ptr(self.buf[dst_row]), self.nbits, self.dt, _ptr(indptr), _ptr(indices), _ptr(vals),
+                                    c.real, c.imag, 1 if accumulate else 0, _stream()))
         STATS["apply_launches"] += 1
 
     def transition_local(self, bra_row: int, ket_row: int, ops: Sequence[Tuple[Sequence[int], np.ndarray]]) -> np.ndarray:

@@ -223,6 +223,14 @@ class FakeState:
             acc += c * (1 - 2 * par) * src[r ^ np.uint64(int(f))]
         self.np[dst_row] = acc.astype(self.np.dtype)
 
+    def apply_csr_rows(self, src_row, dst_row, op, coef=1.0, accumulate=False):
+        import scipy.sparse as sp
+
+        m = sp.coo_matrix((op.vals, (op.rows, op.cols)), shape=op.shape).tocsr()
+        op.hermitian = bool(abs(m - m.getH()).max() <= 1e-10) if m.nnz else True
+        r = coef * (m @ self.np[src_row].astype(np.complex128))
+        self.np[dst_row] = (self.np[dst_row].astype(np.complex128) + r if accumulate else r).astype(self.np.dtype)
+
     def transition_local(self, bra_row, ket_row, ops):
         n = self.nbits
         bra = self.np[bra_row].astype(np.complex128)
@@ -247,6 +255,13 @@ class FakeCOO:
         if self.rows.size and (min(self.rows.min(), self.cols.min()) < 0 or max(self.rows.max(), self.cols.max()) >= dim):
             raise ValueError("sparse operator index outside [0, %d)" % dim)
         self.dim, self.nnz, self.shape = int(dim), int(self.rows.size), (int(dim), int(dim))
+
+    def csr(self):
+        import scipy.sparse as sp
+
+        m = sp.coo_matrix((self.vals, (self.rows, self.cols)), shape=self.shape).tocsr()
+        self.hermitian = bool(abs(m - m.getH()).max() <= 1e-10) if m.nnz else True
+        return m
 
     @classmethod
     def from_scipy(cls, m, device=None):
