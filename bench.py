@@ -564,7 +564,7 @@ def run_ours(args):
                      "traffic": (bytes_per_launch * traffic["dram_bytes_per_algorithmic_byte"]) if traffic and "dram_bytes_per_algorithmic_byte" in traffic else None,
                      "traffic_source": (traffic or {}).get("source"),
                      "fp32_fma_per_amp_per_launch": fma_per_amp / max(1, npass),
-                     "note": "a pass holds ~4 fused 4x4 blocks: HBM time and FP32 time are of the same size and overlap only partly (DESIGN.md 4); see roofline_fp32 and roofline_single_block"},
+                     "note": "a pass holds ~5 fused 4x4 blocks (85 FMA per amplitude): a light pass (<= 1 round) runs at 1.0 of the copy peak through this kernel, a heavy one is bound by issue slots inside its register-tile rounds (ncu: profiles/r2_lpass_phase_stalls.txt); fewer, fuller passes lower this fraction and the step time together (DESIGN.md 4.1); see roofline_fp32 and roofline_single_block"},
         "roofline_single_block": dict(probe, bound="hbm", kernel="dense_kernel", peak=peak, unit="GB/s"),
         "roofline_fp32": {"bound": "fp32 (CUDA cores)", "achieved": fma_total / (apply_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "T FMA/s",
                           "frac": fma_total / (apply_ms * 1e-3) / 1e12 / fp32_peak, "fma_per_amplitude_per_step": fma_per_amp,
