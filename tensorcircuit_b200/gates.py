@@ -281,6 +281,16 @@ def u_gate(theta: float = 0, phi: float = 0, lbd: float = 0) -> Gate:
 
 
 def _rmat(theta: Any, alpha: Any, phi: Any) -> Any:
+    if type(theta) in _REAL_SCALARS and type(alpha) in _REAL_SCALARS and type(phi) in _REAL_SCALARS:
+        # plain real angles (the recording path of the random-circuit benchmark): scalar math, same formula
+        ct, st = math.cos(float(theta)), math.sin(float(theta))
+        sa, ca = math.sin(float(alpha)), math.cos(float(alpha))
+        return (
+            ct * _i_matrix
+            - (1.0j * math.cos(float(phi)) * sa * st) * _x_matrix
+            - (1.0j * math.sin(float(phi)) * sa * st) * _y_matrix
+            - (1.0j * st * ca) * _z_matrix
+        )
     theta, alpha, phi = _s(theta), _s(alpha), _s(phi)
     return (
         np.cos(theta) * _i_matrix
