@@ -195,7 +195,7 @@ class PauliSum:
     (``tocoo`` / ``todense``, host, scipy -- same element values as the reference's)."""
 
     def __init__(self, ls: Sequence[Sequence[int]], weight: Optional[Sequence[float]] = None):
-        self.ls = np.asarray(ls, dtype=np.int64).reshape(len(ls), -1)
+        self.ls = np.real(np.asarray(ls)).astype(np.int64).reshape(len(ls), -1)  # (tc.array_to_tensor hands over complex arrays)
         if self.ls.size and (self.ls.min() < 0 or self.ls.max() > 3):
             raise ValueError("Pauli strings are sequences of 0 (I), 1 (X), 2 (Y), 3 (Z)")
         self.weight = np.ones(len(self.ls)) if weight is None else np.asarray(weight).reshape(-1)
@@ -259,7 +259,7 @@ def PauliStringSum2COO(ls: Sequence[Sequence[int]], weight: Optional[Sequence[fl
     sparse tensor."""
     if not numpy:
         return PauliSum(ls, weight)
-    ls = np.asarray(ls, dtype=np.int64)
+    ls = np.real(np.asarray(ls)).astype(np.int64)
     w = np.ones(len(ls)) if weight is None else np.asarray(weight)
     acc = None
     for i in range(len(ls)):
