@@ -52,6 +52,22 @@ if _os.environ.get("TCB200_GC_FREEZE", "1") != "0":
     _gc.collect()
     _gc.freeze()
 
+# A vmap batch of 1024 parameter sets records one [1024, 4, 4] complex128 matrix per two-qubit gate (256 KiB) and keeps
+# it until the flush.  glibc serves every request above 128 KiB with a fresh mmap, so each of those arrays is 64 first-touch
+# page faults (2-3 us each on a virtualised host) and a munmap afterwards: 110 of the 200 us a batched rzz costs, half of
+# the host time of config 3.  Keep requests up to 32 MiB on the heap and do not trim it, so the pages of one call are
+# reused by the next (TCB200_MALLOPT=0 to leave the allocator alone).
+if _os.environ.get("TCB200_MALLOPT", "1") != "0":
+    try:
+        import ctypes as _ctypes
+
+        _libc = _ctypes.CDLL("libc.so.6")
+        _libc.mallopt(-3, 32 << 20)  # M_MMAP_THRESHOLD (32 MiB is the largest value glibc accepts)
+        _libc.mallopt(-1, 1 << 30)  # M_TRIM_THRESHOLD
+        _libc.mallopt(-2, 64 << 20)  # M_TOP_PAD
+    except (OSError, AttributeError):  # not glibc: nothing to tune
+        pass
+
 
 def about() -> None:
     """tensorcircuit/about.py: versions of what the engine runs on"""

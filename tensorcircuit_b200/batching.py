@@ -10,6 +10,7 @@ Only parameter-sized data lives here (host, float64); nothing O(2^n)."""
 
 from __future__ import annotations
 
+import math
 from typing import Any, Callable, Dict, Sequence, Tuple
 
 import numpy as np
@@ -53,7 +54,7 @@ class BatchArray:
 
     @property
     def size(self) -> int:
-        return int(np.prod(self.shape, dtype=np.int64))
+        return math.prod(self.a.shape[1:])
 
     def __len__(self) -> int:
         if self.ndim == 0:

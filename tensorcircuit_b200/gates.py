@@ -315,12 +315,21 @@ def _ceye(d: int) -> np.ndarray:
     return e
 
 
-def _cos_sin_batched(theta: Any, a: np.ndarray, b: np.ndarray) -> Any:
-    """cos(theta) a - i sin(theta) b for a vmap batch of angles, in a handful of numpy calls on
-    the raw [B] vector (the generic BatchArray arithmetic costs ~10 calls per gate)"""
-    th = theta.a.reshape(-1)
-    if not th.imag.any():
-        th = th.real
+def _cos_sin_batched(theta: Any, a: np.ndarray, b: np.ndarray, scale: float = 1.0) -> Any:
+    """cos(scale theta) a - i sin(scale theta) b for a vmap batch of angles (the BatchArray as the user passed it,
+    real or complex), in a handful of numpy calls on the raw [B] vector (the generic BatchArray arithmetic costs
+    ~10 calls per gate)"""
+    th = theta.a
+    if th.size != th.shape[0]:
+        raise ValueError("gate parameter must be a scalar per batch element, got shape %r" % (tuple(theta.shape),))
+    th = th.reshape(-1)
+    if th.dtype.kind == "c":
+        if not th.imag.any():
+            th = th.real
+    elif th.dtype != np.float64:
+        th = th.astype(np.float64)
+    if scale != 1.0:
+        th = th * scale
     c, s_ = np.cos(th), -1.0j * np.sin(th)
     # [B, 2] x [2, d*d]: one small matrix product builds the whole block (a zero entry of a and b stays an exact
     # zero; where both are non-zero the entries are +-1 / +-i, so the result is one exactly rounded addition).  One
@@ -340,14 +349,14 @@ def _rot(p: np.ndarray, theta: Any) -> Gate:
     if type(theta) in _REAL_SCALARS:  # plain real angle: scalar math instead of 0-d array arithmetic
         h = 0.5 * float(theta)
         return Gate(math.cos(h) * _i_matrix - (1.0j * math.sin(h)) * p)
-    theta = _s(theta)
     if is_batched(theta):
-        g = Gate(_cos_sin_batched(theta / 2.0, _i_matrix, p))
+        g = Gate(_cos_sin_batched(theta, _i_matrix, p, 0.5))
         # (not the planner's half-cost class: with per-element matrices a merged block saves more -- one
         # matrix fetch and one dispatch per amplitude group -- than the halved FMAs of an unmerged rx / ry;
         # config 3: 131 ms merged, 151 ms unmerged)
         g.kind = "diag" if not (p[0, 1] or p[1, 0]) else "dense"
         return g
+    theta = _s(theta)
     return Gate(np.cos(theta / 2.0) * _i_matrix - 1.0j * np.sin(theta / 2.0) * p)
 
 
@@ -422,6 +431,7 @@ exp_gate = exponential_gate
 
 _EYES: dict = {}
 _EXP1_CACHE: dict = {}
+_EXP1_BATCHED: dict = {}
 _REAL_SCALARS = (float, int, np.float64, np.float32)
 
 
@@ -438,23 +448,26 @@ def exponential_gate_unity(unitary: Tensor = None, theta: float = None, half: bo
         t = float(theta) * (0.5 if half is True else 1.0)
         mat = math.cos(t) * ent[2] - (1.0j * math.sin(t)) * ent[1]
         return Gate(mat.reshape(ent[3]), name="exp1-" + name)
-    theta = _s(theta)
+    if is_batched(theta):
+        ent = _EXP1_BATCHED.get(id(unitary)) if isinstance(unitary, np.ndarray) else None
+        if ent is None or ent[0] is not unitary:
+            um = np.asarray(unitary, dtype=CDT)
+            n = _nlegs(um.size)
+            d = 2 ** (n // 2)
+            um = um.reshape(d, d)
+            ent = (unitary, um, _ceye(d), [2] * n, "diag" if not um[~np.eye(d, dtype=bool)].any() else "dense")
+            if isinstance(unitary, np.ndarray):  # stable objects for the basis cache of _cos_sin_batched
+                _EXP1_BATCHED[id(unitary)] = ent
+        mat = _cos_sin_batched(theta, ent[2], ent[1], 0.5 if half is True else 1.0)
+        g = Gate(mat.reshape(ent[3]), name="exp1-" + name)
+        g.kind = ent[4]
+        return g
     u = np.asarray(unitary, dtype=CDT)
     n = _nlegs(u.size)
     d = 2 ** (n // 2)
+    theta = _s(theta)
     if half is True:
         theta = theta / 2.0
-    if is_batched(theta):
-        um = u.reshape(d, d)
-        if isinstance(unitary, np.ndarray):  # stable objects for the basis cache of _cos_sin_batched
-            ent = _EXP1_CACHE.get(id(unitary))
-            if ent is None or ent[0] is not unitary:
-                ent = _EXP1_CACHE[id(unitary)] = (unitary, um, np.eye(d, dtype=CDT), [2] * n)
-            um = ent[1]
-        mat = _cos_sin_batched(theta, _ceye(d), um)
-        g = Gate(mat.reshape([2] * n), name="exp1-" + name)
-        g.kind = "diag" if not um[~np.eye(d, dtype=bool)].any() else "dense"
-        return g
     eye = _EYES.get(d)
     if eye is None:
         eye = _EYES.setdefault(d, np.eye(d))

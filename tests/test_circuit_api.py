@@ -608,6 +608,33 @@ def test_vmap_hea_energy(eng):
     assert tc.backend.jit(energy) is energy
 
 
+def test_vmap_batched_angle_types(eng):
+    """Batched rotation / exp1 matrices come from the raw batch vector (gates._cos_sin_batched): integer,
+    float32 and complex-typed angles, the half-angle of rzz / rxx and the full angle of exp1 all give the
+    unbatched matrices; a vector angle per batch element is rejected (gates.py:463-636, 826-865)."""
+    from tensorcircuit_b200 import gates
+    from tensorcircuit_b200.batching import BatchArray
+
+    th = np.array([0, 1, 2, 5])
+    zz = np.kron(np.diag([1.0, -1.0]), np.diag([1.0, -1.0]))
+    for conv in (lambda a: a, lambda a: a.astype(np.float32) * 0.37, lambda a: a * 0.21 + 0.0j, lambda a: a * (0.3 + 0.1j)):
+        a = conv(th)
+        for build in (lambda t: gates.rx_gate(theta=t), lambda t: gates.ry_gate(theta=t), lambda t: gates.rz_gate(theta=t),
+                      lambda t: gates.rzz_gate(theta=t), lambda t: gates.rxx_gate(theta=t),
+                      lambda t: gates.exp1_gate(unitary=zz, theta=t), lambda t: gates.exp1_gate(unitary=zz, theta=t, half=True)):
+            got = build(BatchArray(a)).matrix().a
+            assert got.shape[0] == len(th)
+            for b in range(len(th)):
+                t = a[b].item()
+                if isinstance(t, complex) and t.imag == 0:
+                    t = t.real
+                np.testing.assert_allclose(np.asarray(got[b]), build(t).matrix(), atol=1e-13)
+    with pytest.raises(ValueError):
+        gates.rx_gate(theta=BatchArray(np.zeros((4, 2))))
+    with pytest.raises(ValueError):
+        gates.rzz_gate(theta=BatchArray(np.zeros((4, 3))))
+
+
 # ---- pass planner --------------------------------------------------------------------------------
 @pytest.mark.parametrize("rt_gates", [2, 12])
 @pytest.mark.parametrize("dtype,tol", [("complex64", 1e-5), ("complex128", 1e-11)])
