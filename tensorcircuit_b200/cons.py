@@ -90,10 +90,18 @@ def get_contractor(method: Optional[str] = None, *args: Any, **kws: Any) -> Any:
     return None
 
 
-def set_distributed(flag: bool = True) -> bool:
+def set_distributed(flag: bool = True, sample_order: Optional[str] = None) -> bool:
     """Shard every Circuit's state vector over the ranks of the default process group (top
     log2(G) index bits = rank; see tensorcircuit_b200.dist).  SPMD: all ranks run the same
-    script and get identical host-side results."""
+    script and get identical host-side results.  ``sample_order="logical"`` makes ``c.sample(status=...)``
+    return the single-GPU indices for the same uniforms (the state is brought back to the identity layout
+    first: up to two more remaps); the default "physical" samples in place."""
+    if sample_order is not None:
+        if sample_order not in ("physical", "logical"):
+            raise ValueError("sample_order must be 'physical' or 'logical'")
+        from .dist import DistState
+
+        DistState.sample_order = sample_order
     _rebind("distributed_state", bool(flag))
     return bool(flag)
 

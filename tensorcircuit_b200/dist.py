@@ -23,6 +23,7 @@ tests run the same scheduler over gloo with an emulated local engine)."""
 from __future__ import annotations
 
 import math
+import os
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -411,6 +412,75 @@ class DistState:
             self._swap_local_bits(self.phys[q], free.pop(0))
         self.remap()
 
+    def _swap_local_many(self, pairs: Sequence[Tuple[int, int]]) -> None:
+        """A sequence of physical local bit exchanges as ONE planned run of passes: the SWAPs are permutation blocks,
+        which the gate pass executes as index remaps, so a whole bit permutation costs a few passes over the shard
+        (one per set of bits that fits a tile), not one per exchange."""
+        blocks = []
+        for pa, pb in pairs:
+            if pa == pb:
+                continue
+            lo, hi = sorted((pa, pb))
+            blocks.append(Block(qubits=(self.nloc - 1 - hi, self.nloc - 1 - lo), bits=(lo, hi), matrix=_SWAP, batched=False, ngates=0, kind="perm"))
+            la, lb = self.logical_at(pa), self.logical_at(pb)
+            self.phys[la], self.phys[lb] = pb, pa
+        if not blocks:
+            return
+        if self.use_passes and hasattr(self.local, "apply_planned"):
+            self.stats["swap_passes"] += int(self.local.apply_planned(blocks))
+        else:
+            for b in blocks:
+                self.local.apply_block(b)
+            self.stats["swap_passes"] += len(blocks)
+
+    def restore_identity(self) -> None:
+        """Bring the state back to the layout it started in (logical bit b at physical bit b: the reference's flat
+        vector split G ways): at most two remaps plus the passes of two local bit permutations.  Queries that depend on
+        the ORDER of the amplitudes (the CDF of ``sample(status=...)``) are then the single-GPU ones."""
+        if self.phys == list(range(self.n)):
+            return
+        want_top = list(range(self.nloc, self.n))  # logical bits that belong to the rank index, slot j = bit nloc + j
+        if self.G > 1 and any(self.phys[b] != b for b in want_top):
+            top0 = self.nloc - self.g
+            if any(self.is_global_bit(b) for b in want_top):
+                # some wanted bits are global in a wrong slot or next to strangers: every global bit comes down first;
+                # a wanted bit inside the window would go up in exchange, so it is parked below the window before
+                free = [p for p in range(top0 - 1, -1, -1) if self.logical_at(p) not in want_top]
+                pairs = []
+                for b in want_top:
+                    if top0 <= self.phys[b] < self.nloc:
+                        if not free:
+                            raise RuntimeError("no free local bit to park a qubit before the remap")
+                        pairs.append((self.phys[b], free.pop(0)))
+                self._swap_local_many(pairs)
+                self.remap()
+            # all wanted bits are local now: logical bit nloc + j goes to window position top0 + j, then up
+            pairs = []
+            cur = list(self.phys)
+            for j, b in enumerate(want_top):
+                src, dst = cur[b], top0 + j
+                if src != dst:
+                    pairs.append((src, dst))
+                    other = cur.index(dst)
+                    cur[b], cur[other] = dst, src
+            self._swap_local_many(pairs)
+            self.remap()
+        # local bits: selection by exchanges, all in one planned run
+        pairs = []
+        cur = list(self.phys)
+        for p in range(self.nloc):
+            if cur[p] != p:
+                src = cur[p]
+                pairs.append((src, p))
+                other = cur.index(p)
+                cur[p], cur[other] = p, src
+        self._swap_local_many(pairs)
+        assert self.phys == list(range(self.n)), self.phys
+
+    # how sample() orders the CDF: "physical" (no data movement; reproducible for a fixed GPU count) or "logical"
+    # (restore_identity() first: the same indices as a single-GPU run for the same uniforms, up to CDF ties)
+    sample_order = os.environ.get("TCB200_DIST_SAMPLE_ORDER", "physical")
+
     # -- queries ----------------------------------------------------------------------------------------
     def norm2(self) -> float:
         v = torch.tensor([float(self.local.norm2()[0])], dtype=torch.float64, device=self.local.buf.device)
@@ -476,15 +546,22 @@ class DistState:
             pending = [t for t in pending if t not in set(now)]
         return out
 
-    def sample(self, uniforms: Any) -> np.ndarray:
+    def sample(self, uniforms: Any, logical_order: Optional[bool] = None) -> np.ndarray:
         """CDF sampling over the sharded state; returns *logical* basis-state indices (int64).
         Every rank receives all uniforms; each resolves those that fall into its CDF interval.
 
-        The CDF runs over the amplitudes in their current PHYSICAL order (rank-major, then the local
+        By default the CDF runs over the amplitudes in their current PHYSICAL order (rank-major, then the local
         physical bits): after a remap that is a permutation of the logical order, so the same ``status``
         draws from the same distribution but not the same bitstrings as a single-GPU run -- samples are
-        reproducible for a fixed GPU count and circuit, not across GPU counts (restoring the identity
-        layout first would cost up to two more all-to-all remaps of the state)."""
+        reproducible for a fixed GPU count and circuit, not across GPU counts.  ``logical_order=True``
+        (or ``DistState.sample_order = "logical"`` / ``tc.set_distributed(True, sample_order="logical")``) restores
+        the identity layout first (``restore_identity``: up to two more remaps and a few local passes): the
+        CDF is then the reference's (circuit.py:915-935 over the flat vector) and the indices are those of a
+        single-GPU run for the same uniforms, up to ties between adjacent CDF values."""
+        if logical_order is None:
+            logical_order = self.sample_order == "logical"
+        if logical_order:
+            self.restore_identity()
         dev = self.local.buf.device
         mine = float(self.local.norm2()[0])
         tot = torch.zeros(self.G, dtype=torch.float64, device=dev)

@@ -57,6 +57,21 @@ def main():
             for q in range(n):
                 emp = np.mean(1 - 2 * ((s_idx >> (n - 1 - q)) & 1))
                 assert abs(emp - o.expectation_ps(z=[q]).real) < 0.03, (q, emp)
+            # logical order: identity layout restored (<= 2 more remaps), then the single-GPU rule on the flat vector
+            # (circuit.py:915-935); mismatches only where a uniform falls between two adjacent CDF values
+            remaps0 = ds.stats["remaps"]
+            s_log = ds.sample(u, logical_order=True)
+            assert ds.phys == list(range(n)) and ds.stats["remaps"] - remaps0 <= 2
+            dev = ds.gather_state().astype(np.complex128)
+            assert np.linalg.norm(dev - ref) / np.linalg.norm(ref) < 1e-5
+            cdf = np.cumsum(np.abs(dev) ** 2)
+            r = cdf[-1] * (1 - u)
+            want_s = np.minimum(np.searchsorted(cdf, r, side="left"), 2**n - 1)
+            bad = np.nonzero(s_log != want_s)[0]
+            assert len(bad) < 50, (mode, kf, len(bad))
+            for i in bad:
+                lo_ = min(int(s_log[i]), int(want_s[i]))
+                assert abs(cdf[lo_] - r[i]) <= 1e-9 * cdf[-1], (i, s_log[i], want_s[i])
             del ds
     # public API, SPMD
     tc.set_distributed(True)

@@ -72,6 +72,33 @@ def main():
             chk = torch.from_numpy(s_idx.copy())
             dist.broadcast(chk, 0)
             assert np.array_equal(chk.numpy(), s_idx)
+            # logical order: the layout goes back to the identity (<= 2 remaps), the state is unchanged as a logical
+            # vector, and the indices are those of the reference rule on the flat vector (circuit.py:915-935)
+            assert ds.phys != list(range(n))
+            remaps0 = ds.stats["remaps"]
+            s_log = ds.sample(u, logical_order=True)
+            assert ds.phys == list(range(n)) and ds.stats["remaps"] - remaps0 <= 2
+            got3 = ds.gather_state()
+            assert np.linalg.norm(got3 - o.state()) / np.linalg.norm(o.state()) < tol
+            p3 = np.abs(got3.astype(np.complex128)) ** 2
+            cdf3 = np.cumsum(p3)
+            r3 = cdf3[-1] * (1 - u)
+            want3 = np.minimum(np.searchsorted(cdf3, r3, side="left"), 2**n - 1)
+            bad = np.nonzero(s_log != want3)[0]
+            assert len(bad) < 10, (mode, dtype, len(bad))
+            for i in bad:  # ties between adjacent CDF values only
+                lo_ = min(int(s_log[i]), int(want3[i]))
+                assert abs(cdf3[lo_] - r3[i]) <= 1e-9 * cdf3[-1], (i, s_log[i], want3[i])
+            assert np.array_equal(ds.sample(u, logical_order=True), s_log)  # idempotent, no further movement
+            # gates after the restored layout still run (the map is consistent)
+            ds.run(blocks[:6])
+            psi = o.state().astype(np.complex128)
+            for blk in blocks[:6]:
+                k = len(blk.qubits)
+                t = np.tensordot(np.asarray(blk.matrix).reshape([2] * (2 * k)), psi.reshape([2] * n), axes=(list(range(k, 2 * k)), list(blk.qubits)))
+                psi = np.moveaxis(t, list(range(k)), list(blk.qubits)).reshape(-1)
+            got4 = ds.gather_state()
+            assert np.linalg.norm(got4 - psi) / np.linalg.norm(psi) < 2 * tol, (mode, dtype)
     # vmap batch sharding (no data-path collective; one all-gather at the end)
     import tensorcircuit_b200 as tc
 

@@ -1356,3 +1356,21 @@ def test_expectation_loop_is_coalesced(eng):
     # a non-Pauli operator (a projector: two Pauli terms) goes through the same pool
     p0 = tc.gates.Gate(np.array([[1.0, 0.0], [0.0, 0.0]]))
     np.testing.assert_allclose(float(np.real(c.expectation((p0, [2])))), 0.5 * (1 + o.expectation_ps(z=[2]).real), atol=2e-5)
+
+
+def test_set_distributed_sample_order():
+    """tc.set_distributed(..., sample_order=): "logical" = single-GPU indices for the same uniforms (dist.py restore_identity),
+    "physical" = in place; anything else is an error.  (The sharded run itself: tests/test_dist_gloo.py, tests/test_dist_gpu.py.)"""
+    from tensorcircuit_b200.dist import DistState
+
+    old = DistState.sample_order
+    try:
+        tc.set_distributed(False, sample_order="logical")
+        assert DistState.sample_order == "logical"
+        tc.set_distributed(False, sample_order="physical")
+        assert DistState.sample_order == "physical"
+        with pytest.raises(ValueError):
+            tc.set_distributed(False, sample_order="sorted")
+    finally:
+        DistState.sample_order = old
+        tc.set_distributed(False)
