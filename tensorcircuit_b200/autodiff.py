@@ -445,12 +445,21 @@ def value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequence[int]] = 0
                         raise RuntimeError("structure")
                     if leader[qi] != qi or not any(np.any(dl_de[m]) for m in groups[qb.key]):
                         continue
+                    # gates that see the parameters carry a [2P, d, d] matrix; all gates of one width in one pass
+                    by_shape: Dict[Any, List[int]] = {}
                     for j, (_, Mb) in enumerate(qt.ops):
-                        if Mb.ndim != 3:
-                            continue  # this gate does not see the parameters
-                        Dall = (Mb[0::2] - Mb[1::2]) / (2 * hs)[:, None, None]
-                        for k in np.nonzero(np.abs(Dall).reshape(P, -1).max(axis=1) > 1e-12)[0]:
-                            pending[qi].append((int(k), j, Dall[k]))
+                        if Mb.ndim == 3:
+                            by_shape.setdefault(Mb.shape, []).append(j)
+                    found: List[Tuple[int, int, np.ndarray]] = []
+                    for js in by_shape.values():
+                        Mall = np.stack([qt.ops[j][1] for j in js])  # [gates, 2P, d, d]
+                        Dall = (Mall[:, 0::2] - Mall[:, 1::2]) / (2 * hs)[None, :, None, None]
+                        hit = np.abs(Dall).reshape(len(js), P, -1).max(axis=2) > 1e-12
+                        for gi, k in zip(*np.nonzero(hit)):
+                            found.append((js[gi], int(k), Dall[gi, k]))
+                    found.sort(key=lambda t: (t[0], t[1]))
+                    for j, k, D in found:
+                        pending[qi].append((k, j, D))
                 swept = True
             except (TypeError, ValueError, NotImplementedError, RuntimeError, AttributeError, IndexError):
                 g[:] = 0.0  # f is not batch-transparent (same requirement as vmap): one recording per nudge
