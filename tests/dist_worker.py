@@ -116,6 +116,32 @@ def main():
     got = tc.backend.vmap(f)(th)
     want = np.cos(th[:, 0]) + np.sin(th[:, 1])
     assert got.shape == (B,) and np.allclose(got, want, atol=1e-5)
+    # public API: c.sample(status=...) on the sharded state in logical order == the single-process run, index by index
+    # (circuit.py:915-935; complex128 so that the two pass plans agree far below the CDF spacing)
+    from tensorcircuit_b200.dist import DistState as _DS
+
+    tc.set_dtype("complex128")
+    try:
+        n2 = 9
+        ops2 = recipes.random_circuit(n2, 4, seed=11)
+        u2 = np.random.default_rng(9).random(500)
+        tc.set_distributed(True, sample_order="logical")
+        cd = recipes.build(tc.Circuit(n2), ops2)
+        s_d = np.asarray(cd.sample(batch=500, allow_state=True, status=u2, format="sample_int"))
+        assert cd._state.ds.stats["remaps"] >= 1
+        tc.set_distributed(False)
+        c1 = recipes.build(tc.Circuit(n2), ops2)
+        s_1 = np.asarray(c1.sample(batch=500, allow_state=True, status=u2, format="sample_int"))
+        assert int(np.sum(s_d != s_1)) <= 1, int(np.sum(s_d != s_1))
+        # in place (physical order) the same uniforms give the same distribution but other indices
+        tc.set_distributed(True, sample_order="physical")
+        cp = recipes.build(tc.Circuit(n2), ops2)
+        s_p = np.asarray(cp.sample(batch=500, allow_state=True, status=u2, format="sample_int"))
+        assert s_p.shape == s_1.shape
+    finally:
+        tc.set_distributed(False)
+        _DS.sample_order = "physical"
+        tc.set_dtype("complex64")
     dist.barrier()
     if rank == 0:
         print("DIST_OK world=%d" % world)
